@@ -1,0 +1,419 @@
+// genvox_b200 — backward through time of the Tacotron2 decoder recurrence.
+//
+// The reference has no backward source: `loss["loss"].backward()` at
+// /root/reference/models/tts/tacotron2.py:520 drives torch autograd over the graph built by
+// Decoder.forward (:365-388).  Here the reverse-time chain (what is truly sequential) runs as
+// five launches per step; every gradient that is a sum over time (all weight gradients,
+// d processed_memory, d memory) is computed afterwards by time-batched GEMMs / reductions:
+//   per step t = T-1..0:
+//     S1  decoder-LSTM pointwise backward                      -> DGD[t]
+//     S2  d x_dec = DGD[t] . W_dec          (skinny GEMM)      -> d h_att, d ctx, d h_dec(t-1)
+//     S3  attention backward (gvx_attention.cuh)               -> d e, d q, d conv, d w/d cum carries
+//     S4  d h_att += d q . W_query, attention-LSTM pointwise backward (fused epilogue) -> DGA[t]
+//     S5  d x_att = DGA[t] . W_att          (skinny GEMM)      -> d prenet_out, d ctx(t-1), d h_att(t-1)
+//   afterwards: cuBLAS sgemm (plain time-batched GEMMs) for d W of both LSTMs, projection, query,
+//   memory layer, prenet; custom reductions for d v / d location_dense / d location_conv / d pm.
+#pragma once
+#include <cublas_v2.h>
+
+#include "../../include/genvox_b200.h"
+#include "gvx_attention.cuh"
+#include "gvx_common.cuh"
+#include "gvx_gemm.cuh"
+#include "gvx_layout.cuh"
+#include "gvx_misc.cuh"
+
+namespace gvx {
+int check_dims(const gvx_dims *d);
+
+#define GVX_CUBLAS(expr)                                                                             \
+    do {                                                                                             \
+        cublasStatus_t s__ = (expr);                                                                 \
+        if (s__ != CUBLAS_STATUS_SUCCESS) {                                                          \
+            snprintf(gvx::g_err, sizeof(gvx::g_err), "%s:%d: %s -> cublas status %d", __FILE__, __LINE__, #expr, (int)s__); \
+            return 1;                                                                                \
+        }                                                                                            \
+    } while (0)
+
+static int blas(cublasHandle_t *out, cudaStream_t st) {
+    static thread_local cublasHandle_t h = nullptr;
+    if (!h) {
+        GVX_CUBLAS(cublasCreate(&h));
+        GVX_CUBLAS(cublasSetMathMode(h, CUBLAS_DEFAULT_MATH));    // true fp32 sgemm (no TF32), like torch's default
+    }
+    GVX_CUBLAS(cublasSetStream(h, st));
+    *out = h;
+    return 0;
+}
+
+// row-major helpers: C[M,N] (ldc) = alpha * op(A) . op(B) + beta * C
+// NN: A [M,K] (lda), B [K,N] (ldb)
+static int gemm_nn(cudaStream_t st, int M, int N, int K, const float *A, int lda, const float *B, int ldb, float *C, int ldc,
+                   float beta) {
+    cublasHandle_t h;
+    GVX_TRY(blas(&h, st));
+    const float alpha = 1.f;
+    GVX_CUBLAS(cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, N, M, K, &alpha, B, ldb, A, lda, &beta, C, ldc));
+    return 0;
+}
+// TN: A [K,M] (lda), B [K,N] (ldb):  C = A^T . B   (weight gradients: sum over the K = T*B rows)
+static int gemm_tn(cudaStream_t st, int M, int N, int K, const float *A, int lda, const float *B, int ldb, float *C, int ldc,
+                   float beta) {
+    cublasHandle_t h;
+    GVX_TRY(blas(&h, st));
+    const float alpha = 1.f;
+    GVX_CUBLAS(cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, N, M, K, &alpha, B, ldb, A, lda, &beta, C, ldc));
+    return 0;
+}
+// column sums of a row-major X [rows, ncols] (ld): out[c] = sum_r X[r, c]
+static int colsum(cudaStream_t st, const float *X, int rows, int ncols, int ld, const float *ones, float *out) {
+    cublasHandle_t h;
+    GVX_TRY(blas(&h, st));
+    const float alpha = 1.f, beta = 0.f;
+    GVX_CUBLAS(cublasSgemv(h, CUBLAS_OP_N, ncols, rows, &alpha, X, ld, ones, 1, &beta, out, 1));
+    return 0;
+}
+
+// S1: decoder-LSTM pointwise backward.  d h_dropped = dh1 (+ dh2)
+__global__ void k_lstm_bwd_pointwise(const float *__restrict__ dh1, int ld1, const float *__restrict__ dh2, int ld2,
+                                     DropCfg drop, uint32_t site, uint32_t t, int row_offset,
+                                     const float *__restrict__ gates, const float *__restrict__ c_prev,
+                                     const float *__restrict__ c_new, float *__restrict__ dc, float *__restrict__ dgates,
+                                     int B, int HID) {
+    const int total = B * HID;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int b = i / HID, u = i - b * HID;
+        float dh = dh1[(size_t)b * ld1 + u];
+        if (dh2) dh += dh2[(size_t)b * ld2 + u];
+        const float mult = drop_mult(drop, site, t, (uint32_t)(b + row_offset), (uint32_t)u);
+        const float4 ga = *reinterpret_cast<const float4 *>(gates + (size_t)b * 4 * HID + 4 * u);
+        float dcp;
+        const float4 dp = lstm_bwd_point(dh, mult, ga, c_prev[i], c_new[i], dc[i], dcp);
+        dc[i] = dcp;
+        *reinterpret_cast<float4 *>(dgates + (size_t)b * 4 * HID + 4 * u) = dp;
+    }
+}
+
+// prenet backward mask: dz = dy * 2 * [y > 0]   (y = relu(z) * keep * 2, tacotron2.py:143)
+__global__ void k_prenet_bwd_mask(const float *dy, int ldy, const float *__restrict__ y, int rows, int P, float *dz) {
+    const size_t total = (size_t)rows * P;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / P;
+        const int c = (int)(i - r * P);
+        dz[i] = y[i] > 0.f ? 2.f * dy[r * ldy + c] : 0.f;
+    }
+}
+
+// packed bias gradient [4*HID] (row 4u+g) -> torch order (g*HID+u), written to both b_ih and b_hh
+__global__ void k_unpack_bias_grad(const float *__restrict__ db, int HID, float *__restrict__ d_ih, float *__restrict__ d_hh) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * HID; i += gridDim.x * blockDim.x) {
+        const int u = i >> 2, g = i & 3;
+        d_ih[g * HID + u] = db[i];
+        d_hh[g * HID + u] = db[i];
+    }
+}
+
+// Post-pass 1: for every token (b, n), over all t:  d s = d e * v * (1 - th^2)
+//   d pm[b,n,d] = sum_t d s;  d v[d] += sum d e * th;  d Wld[d,f] += sum d s * conv[f]
+// blockDim = D threads (thread = d); per-block partials of d Wld / d v are reduced by k_reduce_partials.
+template <int FMAX>
+__global__ void k_attn_post_dense(const float *__restrict__ TH, const float *__restrict__ DE, const float *__restrict__ CONVS,
+                                  const float *__restrict__ v, int T, int B, int N, int D, int F, float *__restrict__ DPM,
+                                  float *__restrict__ part /* [grid][D*F + D] */) {
+    const int d = threadIdx.x;
+    float wacc[FMAX];
+#pragma unroll
+    for (int f = 0; f < FMAX; ++f) wacc[f] = 0.f;
+    float vacc = 0.f;
+    const float vd = d < D ? v[d] : 0.f;
+    const size_t tok_stride = (size_t)B * N;
+    for (int tok = blockIdx.x; tok < B * N; tok += gridDim.x) {
+        float pacc = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const size_t row = (size_t)t * tok_stride + tok;
+            const float de = DE[row];
+            if (de == 0.f) continue;      // masked tokens contribute exactly zero
+            const float th = d < D ? TH[row * D + d] : 0.f;
+            const float ds = de * vd * (1.f - th * th);
+            pacc += ds;
+            vacc = fmaf(de, th, vacc);
+            const float *cv = CONVS + row * F;
+#pragma unroll
+            for (int f = 0; f < FMAX; ++f)
+                if (f < F) wacc[f] = fmaf(ds, cv[f], wacc[f]);
+        }
+        if (d < D) DPM[(size_t)tok * D + d] = pacc;
+    }
+    if (d < D) {
+        float *p = part + (size_t)blockIdx.x * (D * F + D);
+#pragma unroll
+        for (int f = 0; f < FMAX; ++f)
+            if (f < F) p[d * F + f] = wacc[f];
+        p[D * F + d] = vacc;
+    }
+}
+
+// Post-pass 2: d Wlc[f,c,k] = sum_{t,b,n} d conv[t,b,n,f] * wcat[t,b,c,n+k-pad]
+//   wcat channel 0 = alignments of step t-1 (zeros at t = 0), channel 1 = cum before step t.
+__global__ void k_attn_post_conv(const float *__restrict__ DCONV, const float *__restrict__ ALIGN,
+                                 const float *__restrict__ CUMS, int T, int B, int N, int F, int KS,
+                                 float *__restrict__ part /* [grid][F*2*KS] */) {
+    extern __shared__ __align__(16) float sm[];
+    const int pad = (KS - 1) / 2, NP = N + KS - 1;
+    float *wcat = sm;                       // [2][NP]
+    float *dcv = sm + 2 * NP;               // [N][F+1]
+    const int nout = F * 2 * KS;
+    // each thread owns outputs o = tid, tid + blockDim, ... (at most 8)
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int item = blockIdx.x; item < T * B; item += gridDim.x) {
+        const int t = item / B, b = item - t * B;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * NP; i += blockDim.x) {
+            const int c = i / NP, n = i - c * NP - pad;
+            float x = 0.f;
+            if (n >= 0 && n < N) {
+                if (c == 0) x = t > 0 ? ALIGN[((size_t)b * T + (t - 1)) * N + n] : 0.f;
+                else x = CUMS[((size_t)b * T + t) * N + n];
+            }
+            wcat[i] = x;
+        }
+        const float *src = DCONV + ((size_t)t * B + b) * N * F;
+        for (int i = threadIdx.x; i < N * F; i += blockDim.x) {
+            const int n = i / F, f = i - n * F;
+            dcv[n * (F + 1) + f] = src[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int o = threadIdx.x + i * blockDim.x;
+            if (o < nout) {
+                const int f = o / (2 * KS), ck = o - f * 2 * KS, c = ck / KS, k = ck - c * KS;
+                const float *x = wcat + c * NP + k;
+                float a = acc[i];
+                for (int n = 0; n < N; ++n) a = fmaf(dcv[n * (F + 1) + f], x[n], a);
+                acc[i] = a;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int o = threadIdx.x + i * blockDim.x;
+        if (o < nout) part[(size_t)blockIdx.x * nout + o] = acc[i];
+    }
+}
+
+// out[i] = sum_blk part[blk * stride + off + i], fixed order
+__global__ void k_reduce_partials(const float *__restrict__ part, int nblk, int stride, int off, int n, float *__restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < nblk; ++k) s += part[(size_t)k * stride + off + i];
+        out[i] = s;
+    }
+}
+
+}  // namespace gvx
+
+using namespace gvx;
+
+extern "C" int gvx_dec_train_bwd(const gvx_dims *dd, const gvx_weights *w, const void *packed_, const float *memory,
+                                 const int64_t *mem_lengths, int B, int N, int T, uint64_t seed, int training,
+                                 int row_offset, const float *d_mel, const float *d_gate, const float *d_align,
+                                 const void *stash_, void *workspace, const gvx_grads *g, float *d_memory, void *stream) {
+    GVX_TRY(check_dims(dd));
+    GVX_CHECK(w && packed_ && memory && d_mel && d_gate && stash_ && workspace && g && d_memory, "null argument");
+    GVX_CHECK(B > 0 && N > 0 && T > 0, "B, N, T must be positive");
+    const Dims d(*dd);
+    GVX_CHECK(d.F <= 64 && d.D <= 512, "backward supports loc_filters <= 64 and att_dim <= 512");
+    GVX_CHECK(d.F * 2 * d.KS <= 8 * 512, "location conv too large for the backward reduction kernel");
+    const StashL S(d, B, N, T);
+    const BwdL W(d, B, N, T);
+    const PackedL PL(d);
+    const float *packed = (const float *)packed_;
+    const float *s = (const float *)stash_;
+    float *x = (float *)workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int TB = T * B;
+    const size_t BA = (size_t)B * d.A, BH = (size_t)B * d.H, BE = (size_t)B * d.E;
+
+    GVX_CUDA(cudaMemsetAsync(x + W.DW, 0, (size_t)B * N * sizeof(float), st));
+    GVX_CUDA(cudaMemsetAsync(x + W.DCUM, 0, (size_t)B * N * sizeof(float), st));
+    GVX_CUDA(cudaMemsetAsync(x + W.DCD, 0, BH * sizeof(float), st));
+    GVX_CUDA(cudaMemsetAsync(x + W.DCA, 0, BA * sizeof(float), st));
+    k_fill_f32<<<grid_for((size_t)TB), 256, 0, st>>>(x + W.ONES, (size_t)TB, 1.f);
+    GVX_LAUNCHED(1);
+
+    // upstream gradients, time-major; d [h_dec | ctx] through the projections for every frame at once
+    k_pack_dout<<<grid_for((size_t)TB * d.OL), 256, 0, st>>>(d_mel, d_gate, B, d.M, d.OL, T, x + W.DOUT);
+    GVX_LAUNCHED(1);
+    GVX_CUDA(cudaGetLastError());
+    GVX_TRY(gemm_nn(st, TB, d.Kp, d.M + 1, x + W.DOUT, d.OL, packed + PL.Wpg, d.Kp, x + W.DHC, d.Kp, 0.f));
+
+    const DropCfg drop_dec = make_drop(seed, d.p_dec, training), drop_att = make_drop(seed, d.p_att, training);
+    for (int t = T - 1; t >= 0; --t) {
+        const bool last = t == T - 1;
+        float *dxd = x + W.DXD + (size_t)(t & 1) * B * d.Kd;
+        const float *dxd_next = x + W.DXD + (size_t)((t + 1) & 1) * B * d.Kd;
+        float *dxa = x + W.DXA + (size_t)t * B * d.Ka;
+        const float *dxa_next = x + W.DXA + (size_t)(t + 1) * B * d.Ka;
+        // S1
+        {
+        ProfScope ps(PS_BWD_DEC_POINT, st);
+        k_lstm_bwd_pointwise<<<grid_for(BH), 256, 0, st>>>(
+            x + W.DHC + (size_t)t * B * d.Kp, d.Kp, last ? nullptr : dxd_next + d.A + d.E, d.Kd, drop_dec, SITE_DEC,
+            (uint32_t)t, row_offset, s + S.GD + (size_t)t * 4 * BH, s + S.CD + t * BH, s + S.CD + (t + 1) * BH, x + W.DCD,
+            x + W.DGD + (size_t)t * 4 * BH, B, d.H);
+        GVX_LAUNCHED(1);
+        }
+        GVX_CUDA(cudaGetLastError());
+        // S2
+        {
+            ProfScope ps(PS_BWD_DEC_GEMM, st);
+            GemmIn gi = gemm_in(packed + PL.WdT, 4 * d.H, d.Kd, B);
+            add_seg(gi, x + W.DGD + (size_t)t * 4 * BH, 4 * d.H, 4 * d.H);
+            EpiStore e;
+            memset(&e, 0, sizeof(e));
+            e.out = dxd;
+            e.ldo = d.Kd;
+            GVX_TRY((launch_gemm<16, EpiStore>(gi, e, st)));
+        }
+        // S3
+        {
+            ProfScope ps(PS_BWD_ATTENTION, st);
+            AttnBwdArgs a;
+            memset(&a, 0, sizeof(a));
+            a.s = AttnShape{B, N, d.D, d.E, d.F, d.KS};
+            a.memory = memory; a.wlc = w->loc_conv_w; a.wld = w->loc_dense_w; a.v = w->v_w; a.lengths = mem_lengths;
+            a.w_t = s + S.ALIGN + (size_t)t * N; a.w_bstride = (long long)T * N;
+            a.th = s + S.TH + (size_t)t * B * N * d.D;
+            a.dctx1 = x + W.DHC + (size_t)t * B * d.Kp + d.H; a.ld1 = d.Kp;
+            a.dctx2 = dxd + d.A; a.ld2 = d.Kd;
+            a.dctx3 = last ? nullptr : dxa_next + d.P; a.ld3 = d.Ka;
+            a.d_align = d_align ? d_align + (size_t)t * N : nullptr; a.da_bstride = (long long)T * N;
+            a.dw_carry = x + W.DW; a.dcum_carry = x + W.DCUM;
+            a.dctx_out = x + W.DCTX + t * BE;
+            a.de_out = x + W.DE + (size_t)t * B * N;
+            a.dq_out = x + W.DQ + (size_t)t * B * d.D;
+            a.dconv_out = x + W.DCONV + (size_t)t * B * N * d.F;
+            GVX_TRY(launch_attention_bwd(a, st));
+        }
+        // S4
+        {
+            ProfScope ps(PS_BWD_ATT_POINT, st);
+            GemmIn gi = gemm_in(packed + PL.WqT, d.D, d.A, B);
+            add_seg(gi, x + W.DQ + (size_t)t * B * d.D, d.D, d.D);
+            EpiLstmBwd e;
+            memset(&e, 0, sizeof(e));
+            e.add1 = dxd; e.ld1 = d.Kd;
+            e.add2 = last ? nullptr : dxa_next + d.P + d.E; e.ld2 = d.Ka;
+            e.drop = drop_att; e.site = SITE_ATT; e.t = (uint32_t)t; e.row_offset = row_offset;
+            e.gates = s + S.GA + (size_t)t * 4 * BA; e.c_prev = s + S.CA + t * BA; e.c_new = s + S.CA + (t + 1) * BA;
+            e.dc = x + W.DCA; e.dgates = x + W.DGA + (size_t)t * 4 * BA; e.HID = d.A;
+            GVX_TRY((launch_gemm<8, EpiLstmBwd>(gi, e, st)));
+        }
+        // S5
+        {
+            ProfScope ps(PS_BWD_ATT_GEMM, st);
+            GemmIn gi = gemm_in(packed + PL.WaT, 4 * d.A, d.Ka, B);
+            add_seg(gi, x + W.DGA + (size_t)t * 4 * BA, 4 * d.A, 4 * d.A);
+            EpiStore e;
+            memset(&e, 0, sizeof(e));
+            e.out = dxa;
+            e.ldo = d.Ka;
+            GVX_TRY((launch_gemm<16, EpiStore>(gi, e, st)));
+        }
+    }
+
+    // ---------------- time-batched gradients ----------------
+    ProfScope ps_batched(PS_BWD_BATCHED, st);
+    // projections (linear_projection + gate_layer): d Wpg = DOUT^T . [HD[1:], CTX[1:]]
+    float *tmp = x + W.TMP;
+    GVX_TRY(gemm_tn(st, d.M + 1, d.H, TB, x + W.DOUT, d.OL, s + S.HD + BH, d.H, tmp, d.Kp, 0.f));
+    GVX_TRY(gemm_tn(st, d.M + 1, d.E, TB, x + W.DOUT, d.OL, s + S.CTX + BE, d.E, tmp + d.H, d.Kp, 0.f));
+    GVX_CUDA(cudaMemcpyAsync(g->proj_w, tmp, (size_t)d.M * d.Kp * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    GVX_CUDA(cudaMemcpyAsync(g->gate_w, tmp + (size_t)d.M * d.Kp, (size_t)d.Kp * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    GVX_TRY(colsum(st, x + W.DOUT, TB, d.M + 1, d.OL, x + W.ONES, x + W.DBIAS));
+    GVX_CUDA(cudaMemcpyAsync(g->proj_b, x + W.DBIAS, (size_t)d.M * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    GVX_CUDA(cudaMemcpyAsync(g->gate_b, x + W.DBIAS + d.M, sizeof(float), cudaMemcpyDeviceToDevice, st));
+
+    // decoder LSTM: d Wd (packed) = DGD^T . [HA[1:], CTX[1:], HD[:T]]
+    GVX_TRY(gemm_tn(st, 4 * d.H, d.A, TB, x + W.DGD, 4 * d.H, s + S.HA + BA, d.A, x + W.DWD, d.Kd, 0.f));
+    GVX_TRY(gemm_tn(st, 4 * d.H, d.E, TB, x + W.DGD, 4 * d.H, s + S.CTX + BE, d.E, x + W.DWD + d.A, d.Kd, 0.f));
+    GVX_TRY(gemm_tn(st, 4 * d.H, d.H, TB, x + W.DGD, 4 * d.H, s + S.HD, d.H, x + W.DWD + d.A + d.E, d.Kd, 0.f));
+    k_unpack_lstm_grad<<<grid_for((size_t)4 * d.H * d.Kd), 256, 0, st>>>(x + W.DWD, d.H, d.A + d.E, g->dec_w_ih, g->dec_w_hh);
+    GVX_LAUNCHED(1);
+    GVX_TRY(colsum(st, x + W.DGD, TB, 4 * d.H, 4 * d.H, x + W.ONES, x + W.DBIAS));
+    k_unpack_bias_grad<<<grid_for((size_t)4 * d.H), 256, 0, st>>>(x + W.DBIAS, d.H, g->dec_b_ih, g->dec_b_hh);
+    GVX_LAUNCHED(1);
+    // attention LSTM: d Wa (packed) = DGA^T . [PRE2, CTX[:T], HA[:T]]
+    GVX_TRY(gemm_tn(st, 4 * d.A, d.P, TB, x + W.DGA, 4 * d.A, s + S.PRE2, d.P, x + W.DWA, d.Ka, 0.f));
+    GVX_TRY(gemm_tn(st, 4 * d.A, d.E, TB, x + W.DGA, 4 * d.A, s + S.CTX, d.E, x + W.DWA + d.P, d.Ka, 0.f));
+    GVX_TRY(gemm_tn(st, 4 * d.A, d.A, TB, x + W.DGA, 4 * d.A, s + S.HA, d.A, x + W.DWA + d.P + d.E, d.Ka, 0.f));
+    k_unpack_lstm_grad<<<grid_for((size_t)4 * d.A * d.Ka), 256, 0, st>>>(x + W.DWA, d.A, d.P + d.E, g->att_w_ih, g->att_w_hh);
+    GVX_LAUNCHED(1);
+    GVX_TRY(colsum(st, x + W.DGA, TB, 4 * d.A, 4 * d.A, x + W.ONES, x + W.DBIAS));
+    k_unpack_bias_grad<<<grid_for((size_t)4 * d.A), 256, 0, st>>>(x + W.DBIAS, d.A, g->att_b_ih, g->att_b_hh);
+    GVX_LAUNCHED(1);
+    GVX_CUDA(cudaGetLastError());
+    // query layer: d Wq [D, A] = DQ^T . HA[1:]
+    GVX_TRY(gemm_tn(st, d.D, d.A, TB, x + W.DQ, d.D, s + S.HA + BA, d.A, g->query_w, d.A, 0.f));
+
+    // attention parameters that sum over (t, b, n)
+    {
+        const int nblk = W.post_blocks;
+        const int threads = (d.D + 31) & ~31;
+        GVX_CHECK(threads <= 512, "att_dim too large");
+        if (d.F <= 32) {
+            k_attn_post_dense<32><<<nblk, threads, 0, st>>>(s + S.TH, x + W.DE, s + S.CONVS, w->v_w, T, B, N, d.D, d.F,
+                                                           x + W.DPM, x + W.PART1);
+        } else {
+            k_attn_post_dense<64><<<nblk, threads, 0, st>>>(s + S.TH, x + W.DE, s + S.CONVS, w->v_w, T, B, N, d.D, d.F,
+                                                           x + W.DPM, x + W.PART1);
+        }
+        GVX_LAUNCHED(1);
+        GVX_CUDA(cudaGetLastError());
+        const int stride = d.D * d.F + d.D;
+        k_reduce_partials<<<grid_for((size_t)d.D * d.F), 256, 0, st>>>(x + W.PART1, nblk, stride, 0, d.D * d.F, g->loc_dense_w);
+    GVX_LAUNCHED(1);
+        k_reduce_partials<<<grid_for((size_t)d.D), 256, 0, st>>>(x + W.PART1, nblk, stride, d.D * d.F, d.D, g->v_w);
+    GVX_LAUNCHED(1);
+        const size_t smem = ((size_t)2 * (N + d.KS - 1) + (size_t)N * (d.F + 1)) * sizeof(float);
+        GVX_CHECK(smem <= 200 * 1024, "token count too large for the conv-gradient kernel");
+        static size_t configured = 0;
+        if (smem > configured) {
+            GVX_CUDA(cudaFuncSetAttribute(k_attn_post_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        k_attn_post_conv<<<nblk, 512, smem, st>>>(x + W.DCONV, s + S.ALIGN, s + S.CUMS, T, B, N, d.F, d.KS, x + W.PART2);
+    GVX_LAUNCHED(1);
+        GVX_CUDA(cudaGetLastError());
+        k_reduce_partials<<<grid_for((size_t)d.F * 2 * d.KS), 256, 0, st>>>(x + W.PART2, nblk, d.F * 2 * d.KS, 0,
+                                                                           d.F * 2 * d.KS, g->loc_conv_w);
+    GVX_LAUNCHED(1);
+        GVX_CUDA(cudaGetLastError());
+    }
+    // memory layer and d memory:  d Wm = DPM^T . memory;  d memory = DPM . Wm + align^T . d ctx (per row)
+    GVX_TRY(gemm_tn(st, d.D, d.E, B * N, x + W.DPM, d.D, memory, d.E, g->memory_w, d.E, 0.f));
+    GVX_TRY(gemm_nn(st, B * N, d.E, d.D, x + W.DPM, d.D, w->memory_w, d.E, d_memory, d.E, 0.f));
+    {
+        cublasHandle_t h;
+        GVX_TRY(blas(&h, st));
+        const float alpha = 1.f, beta = 1.f;
+        // row-major per b: C[N, E] += A[T, N]^T . Bm[T, E];  A = ALIGN[b] (lda N), Bm = DCTX[:, b, :] (ldb B*E)
+        GVX_CUBLAS(cublasSgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_T, d.E, N, T, &alpha, x + W.DCTX, B * d.E,
+                                             (long long)d.E, s + S.ALIGN, N, (long long)T * N, &beta, d_memory, d.E,
+                                             (long long)N * d.E, B));
+    }
+    // prenet (tacotron2.py:140-144): d z2 = d PRE2 * 2 [PRE2 > 0];  d W1 = d z2^T . PRE1;  d PRE1 = d z2 . W1; ...
+    k_prenet_bwd_mask<<<grid_for((size_t)TB * d.P), 256, 0, st>>>(x + W.DXA, d.Ka, s + S.PRE2, TB, d.P, x + W.DZ2);
+    GVX_LAUNCHED(1);
+    GVX_CUDA(cudaGetLastError());
+    GVX_TRY(gemm_tn(st, d.P, d.P, TB, x + W.DZ2, d.P, s + S.PRE1, d.P, g->prenet_w1, d.P, 0.f));
+    GVX_TRY(gemm_nn(st, TB, d.P, d.P, x + W.DZ2, d.P, w->prenet_w1, d.P, x + W.DZ1, d.P, 0.f));
+    k_prenet_bwd_mask<<<grid_for((size_t)TB * d.P), 256, 0, st>>>(x + W.DZ1, d.P, s + S.PRE1, TB, d.P, x + W.DZ1);
+    GVX_LAUNCHED(1);
+    GVX_CUDA(cudaGetLastError());
+    GVX_TRY(gemm_tn(st, d.P, d.M, TB, x + W.DZ1, d.P, s + S.FR, d.M, g->prenet_w0, d.M, 0.f));
+    return 0;
+}
