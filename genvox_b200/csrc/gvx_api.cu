@@ -7,6 +7,7 @@
 #include "gvx_gemm.cuh"
 #include "gvx_layout.cuh"
 #include "gvx_misc.cuh"
+#include "gvx_tc.cuh"
 
 namespace gvx {
 thread_local char g_err[512] = {0};
@@ -359,6 +360,41 @@ int gvx_dec_infer(const gvx_dims *dd, const gvx_weights *w, const void *packed_,
 }
 
 // ---------------------------------------------------------------- single-phase hooks
+int gvx_test_tc_gemm(const float *W, const float *X, int B, int Mtot, int K, int KS, float *out, void *stream) {
+    GVX_CHECK(W && X && out && B > 0 && Mtot > 0 && K > 0 && KS > 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int NPAD = tc_npad(B);
+    GVX_CHECK(NPAD > 0, "batch too large");
+    const int Kpad = (K + TC_KB - 1) / TC_KB * TC_KB, Mtiles = (Mtot + TC_M - 1) / TC_M, ldp = Mtiles * TC_M;
+    __nv_bfloat16 *wimg = nullptr, *ximg = nullptr;
+    float *P = nullptr;
+    int *err = nullptr;
+    GVX_CUDA(cudaMalloc(&wimg, (size_t)Mtiles * TC_M * Kpad * 2));
+    GVX_CUDA(cudaMalloc(&ximg, (size_t)NPAD * Kpad * 2));
+    GVX_CUDA(cudaMalloc(&P, (size_t)KS * B * ldp * 4));
+    GVX_CUDA(cudaMalloc(&err, 4));
+    GVX_CUDA(cudaMemsetAsync(err, 0, 4, st));
+    TcPackW pw;
+    memset(&pw, 0, sizeof(pw));
+    pw.s0 = W; pw.mode = 0; pw.Mtot = Mtot; pw.K = K; pw.ld = K;
+    k_tc_pack_w<<<grid_for((size_t)Mtiles * TC_M * Kpad), 256, 0, st>>>(pw, Mtiles, Kpad, wimg);
+    k_tc_pack_x<<<grid_for((size_t)NPAD * Kpad), 256, 0, st>>>(X, B, K, K, NPAD, Kpad, ximg);
+    TcGemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.Wimg = wimg; a.Ximg = ximg; a.P = P; a.Kpad = Kpad; a.B = B; a.ldp = ldp; a.KS = KS; a.err = err;
+    int rc = launch_tc_gemm(a, Mtiles, st);
+    if (!rc) {
+        k_tc_sum_partials<<<grid_for((size_t)B * Mtot), 256, 0, st>>>(P, KS, B, ldp, Mtot, out, Mtot);
+        int herr = 0;
+        cudaError_t e = cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "tc gemm test: %s", cudaGetErrorString(e)); rc = 1; }
+        else if (herr) { snprintf(g_err, sizeof(g_err), "tc gemm pipeline timeout, code %d", herr); rc = 1; }
+    }
+    cudaFree(wimg); cudaFree(ximg); cudaFree(P); cudaFree(err);
+    return rc;
+}
+
 int gvx_prenet_fwd(const gvx_dims *dd, const gvx_weights *w, const float *frames, int F, int B, uint64_t seed, int t0,
                    int row_offset, float *tmp, float *out, void *stream) {
     GVX_TRY(check_dims(dd));

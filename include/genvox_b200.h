@@ -150,6 +150,10 @@ int gvx_dec_infer(const gvx_dims *d, const gvx_weights *w, const void *packed,
 
 /* ---- single-phase entry points (used by the parity tests to localise a failure) ---- */
 
+/* The tcgen05 / TMEM / TMA gate-GEMM engine on its own: out[B, Mtot] = X[B, K] . W[Mtot, K]^T with both
+ * operands rounded to bf16, fp32 accumulation, the K range split over KS CTAs (test hook; allocates). */
+int gvx_test_tc_gemm(const float *W, const float *X, int B, int Mtot, int K, int KS, float *out, void *stream);
+
 /* Prenet.forward, tacotron2.py:140-144: frames [F, B, n_mels] -> out [F, B, P]; frame f uses
  * Philox t = t0 + f.  tmp: [F, B, P] scratch for the layer-0 output. */
 int gvx_prenet_fwd(const gvx_dims *d, const gvx_weights *w, const float *frames, int F, int B,

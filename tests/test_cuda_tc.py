@@ -1,0 +1,26 @@
+"""GPU tests of the tcgen05 / TMEM / TMA gate-GEMM engine (genvox_b200/csrc/gvx_tc.cuh) on its own:
+out = X . W^T with bf16-rounded operands and fp32 accumulation, against an fp64 matmul of the same
+bf16-rounded operands (so the only difference is the accumulation order: tolerance 2e-6 of max|ref|)."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,M,K,KS", [(64, 128, 64, 1), (64, 256, 128, 1), (16, 128, 64, 1), (64, 4096, 1792, 4),
+                                      (64, 4096, 2560, 4), (5, 81, 1536, 3), (128, 1792, 4096, 10), (32, 200, 100, 2),
+                                      (64, 2560, 4096, 7), (64, 128, 1024, 8), (3, 1024, 128, 2)])
+def test_tc_gemm_matches_bf16_matmul(cuda_device, B, M, K, KS):
+    from genvox_b200 import _native
+    from genvox_b200.decoder import _ptr, _stream
+    lib = _native.load()
+    g = torch.Generator().manual_seed(B * 7919 + M * 31 + K)
+    W = (torch.rand(M, K, generator=g) - 0.5).to(cuda_device)
+    X = (torch.rand(B, K, generator=g) - 0.5).mul(4).to(cuda_device)
+    out = torch.full((B, M), float("nan"), device=cuda_device)
+    _native.check(lib.gvx_test_tc_gemm(_ptr(W), _ptr(X), B, M, K, KS, _ptr(out), _stream()), "gvx_test_tc_gemm")
+    ref = X.bfloat16().double() @ W.bfloat16().double().t()
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    assert err < 2e-6, err
