@@ -178,6 +178,7 @@ def run_ours(args, rank, world, local_rank):
 
     torch.manual_seed(0)                                   # identical init on every rank
     dec = genvox_b200.Decoder(**decoder_dims()).to(dev).train()
+    dec.precision = args.precision
     dec.dropout_row_offset = rank * B                      # ranks draw the rows of one global batch
     opt = make_optimizer(dec)
     memory_h, mel_h, gate_h, lengths_h = (t.pin_memory() for t in synthetic_batch(torch, B, N, T, rank))
@@ -244,9 +245,12 @@ def run_ours(args, rank, world, local_rank):
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": f"BASELINE configs[2]: decoder train step (fwd + loss + BPTT + allreduce + clip + Adam), "
-                                   f"batch {B}/GPU, {N} tokens, {T}x80 mel frames, fp32 arithmetic",
+                                   f"batch {B}/GPU, {N} tokens, {T}x80 mel frames, "
+                                   + ("bf16 tcgen05 gate GEMMs with fp32 accumulation, fp32 pointwise/attention"
+                                      if args.precision == "bf16" else "fp32 arithmetic"),
                        "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "per-step working set (stash + workspace, several GB) is far larger than the 126 MB L2"},
             "e2e": e2e, "gpu_launches": int(launches), "final_loss": final_loss}
@@ -280,7 +284,8 @@ def run_ours(args, rank, world, local_rank):
                 ach = flops / (phases[name]["avg_us"] * 1e-6) / 1e12
                 roofs[name] = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                                "frac": ach / pk["tf_sustained"], "traffic": None, "avg_us": phases[name]["avg_us"],
-                               "peak_source": pk["source"] + " (bf16 sustained; this kernel runs fp32 FFMA)"}
+                               "peak_source": pk["source"] + " (bf16 sustained)"
+                               + ("" if args.precision == "bf16" else "; this kernel runs fp32 FFMA")}
         for name in ("attention", "bwd_attention"):
             if name in phases:
                 nbytes = B * N * (E + D) * 4.0 + B * N * 4.0    # memory + processed memory (or stashed tanh) + weights row
@@ -307,7 +312,8 @@ def run_ours(args, rank, world, local_rank):
         ims = e0.elapsed_time(e1) / reps
         line["infer"] = {"workload": f"BASELINE configs[1]: batch {INFER['B']}, {INFER['N']} tokens, {INFER['steps']} fixed "
                                      "decoder steps (gate ignored), fp32", "decoder_steps_per_s": INFER["steps"] / (ims * 1e-3),
-                         "mel_frames_per_s": INFER["B"] * INFER["steps"] / (ims * 1e-3), "us_per_step": 1e3 * ims / INFER["steps"]}
+                         "mel_frames_per_s": INFER["B"] * INFER["steps"] / (ims * 1e-3), "us_per_step": 1e3 * ims / INFER["steps"],
+                         "precision": args.precision}
         dec.train()
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = {k: v for k, v in cpu_train_leg(2, 1).items() if k != "ms_per_step"}
@@ -321,6 +327,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16",
+                    help="arithmetic of the recurrent GEMMs (BASELINE configs[2] is bf16; fp32 = parity mode)")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -12,7 +12,7 @@ _P = C.c_void_p
 class GvxDims(C.Structure):
     _fields_ = [("n_mels", C.c_int32), ("enc_dim", C.c_int32), ("att_rnn_dim", C.c_int32), ("dec_rnn_dim", C.c_int32),
                 ("prenet_dim", C.c_int32), ("att_dim", C.c_int32), ("loc_filters", C.c_int32), ("loc_kernel", C.c_int32),
-                ("p_att_dropout", C.c_float), ("p_dec_dropout", C.c_float)]
+                ("p_att_dropout", C.c_float), ("p_dec_dropout", C.c_float), ("precision", C.c_int32)]
 
 
 # order == struct gvx_weights / gvx_grads; values are the reference's state_dict keys

@@ -8,9 +8,23 @@
 #include "gvx_layout.cuh"
 #include "gvx_misc.cuh"
 #include "gvx_tc.cuh"
+#include "gvx_bf16.cuh"
 
 namespace gvx {
 thread_local char g_err[512] = {0};
+
+// bf16 mode drivers (gvx_bf16_api.cuh, same translation unit)
+size_t packed_total_bf16(const Dims &d);
+size_t stash_total_bf16(const Dims &d, int B, int N, int T);
+size_t bwd_total_bf16(const Dims &d, int B, int N, int T);
+size_t infer_total_bf16(const Dims &d, int B, int N, int steps);
+int pack_weights_bf16(const Dims &d, const gvx_weights *w, float *packed, cudaStream_t st);
+int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, const float *memory, const float *mel_in,
+                   const int64_t *mem_lengths, int B, int N, int T, uint64_t seed, int training, int row_offset, float *mel_out,
+                   float *gate_out, float *align_out, float *s, cudaStream_t st);
+int infer_bf16(const Dims &d, const gvx_weights *w, const float *packed, const float *memory, const int64_t *mem_lengths, int B,
+               int N, int max_steps, float gate_threshold, int ignore_gate, uint64_t seed, int training, int row_offset,
+               float *mel_out, float *gate_out, float *align_out, int32_t *n_frames, int *steps_run, float *s, cudaStream_t st);
 
 int check_dims(const gvx_dims *d) {
     GVX_CHECK(d != nullptr, "dims is null");
@@ -23,12 +37,17 @@ int check_dims(const gvx_dims *d) {
     GVX_CHECK(d->loc_kernel % 2 == 1, "attention_location_kernel_size must be odd");
     GVX_CHECK(d->p_att_dropout >= 0.f && d->p_att_dropout < 1.f && d->p_dec_dropout >= 0.f && d->p_dec_dropout < 1.f,
               "dropout probabilities must be in [0, 1)");
+    GVX_CHECK(d->precision == GVX_FP32 || d->precision == GVX_BF16, "precision must be GVX_FP32 or GVX_BF16");
+    if (d->precision == GVX_BF16)
+        GVX_CHECK(d->n_mels % 8 == 0 && d->enc_dim % 8 == 0 && d->att_rnn_dim % 32 == 0 && d->dec_rnn_dim % 32 == 0 &&
+                      d->prenet_dim % 8 == 0 && d->att_dim % 8 == 0,
+                  "bf16 mode: feature dims must be multiples of 8 and the rnn dims multiples of 32");
     return 0;
 }
 
 // Prenet.forward over `rows` = F*B rows (tacotron2.py:140-144)
 int run_prenet(const Dims &d, const gvx_weights *w, const float *frames, int frames_ld, int rows, int B, uint64_t seed,
-               int t0, int row_offset, float *pre1, float *pre2, cudaStream_t st) {
+               int t0, int row_offset, float *pre1, float *pre2, cudaStream_t st, const BfDsts *bf = nullptr) {
     for (int layer = 0; layer < 2; ++layer) {
         GemmIn g = gemm_in(layer == 0 ? w->prenet_w0 : w->prenet_w1, layer == 0 ? d.M : d.P, d.P, rows);
         if (layer == 0) add_seg(g, frames, d.M, frames_ld);
@@ -43,6 +62,7 @@ int run_prenet(const Dims &d, const gvx_weights *w, const float *frames, int fra
         e.t0 = t0;
         e.rows_per_frame = B;
         e.row_offset = row_offset;
+        if (layer == 1 && bf) e.bf = *bf;
         GVX_TRY((launch_gemm<32, EpiStore>(g, e, st)));
     }
     return 0;
@@ -110,7 +130,7 @@ int run_attention(const Dims &d, const gvx_weights *w, const float *packed, cons
     AttnFwdArgs a;
     memset(&a, 0, sizeof(a));
     a.s = AttnShape{B, N, d.D, d.E, d.F, d.KS};
-    a.q = q; a.pm = pm; a.memory = memory;
+    a.q = src_plain(q, d.D); a.pm = pm; a.memory = memory;
     a.wlc = w->loc_conv_w; a.wldT = packed + PL.wldT; a.v = w->v_w;
     a.lengths = lengths;
     a.w_prev = w_prev; a.cum = cum;
@@ -176,6 +196,7 @@ const char *gvx_profile_slot_name(int slot) { return prof_slot_name(slot); }
 
 size_t gvx_dec_packed_bytes(const gvx_dims *d) {
     if (check_dims(d)) return 0;
+    if (d->precision == GVX_BF16) return packed_total_bf16(Dims(*d)) * sizeof(float);
     return PackedL(Dims(*d)).total * sizeof(float);
 }
 
@@ -200,19 +221,23 @@ int gvx_dec_pack_weights(const gvx_dims *dd, const gvx_weights *w, void *packed_
     k_transpose<<<grid_for((size_t)d.D * d.F), 256, 0, st>>>(w->loc_dense_w, d.D, d.F, p + PL.wldT);
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
+    if (dd->precision == GVX_BF16) return pack_weights_bf16(d, w, p, st);
     return 0;
 }
 
 size_t gvx_dec_stash_bytes(const gvx_dims *d, int B, int N, int T) {
     if (check_dims(d) || B <= 0 || N <= 0 || T <= 0) return 0;
+    if (d->precision == GVX_BF16) return stash_total_bf16(Dims(*d), B, N, T) * sizeof(float);
     return StashL(Dims(*d), B, N, T).total * sizeof(float);
 }
 size_t gvx_dec_bwd_workspace_bytes(const gvx_dims *d, int B, int N, int T) {
     if (check_dims(d) || B <= 0 || N <= 0 || T <= 0) return 0;
+    if (d->precision == GVX_BF16) return bwd_total_bf16(Dims(*d), B, N, T) * sizeof(float);
     return BwdL(Dims(*d), B, N, T).total * sizeof(float);
 }
 size_t gvx_dec_infer_workspace_bytes(const gvx_dims *d, int B, int N, int max_steps) {
     if (check_dims(d) || B <= 0 || N <= 0 || max_steps <= 0) return 0;
+    if (d->precision == GVX_BF16) return infer_total_bf16(Dims(*d), B, N, max_steps) * sizeof(float);
     return InferL(Dims(*d), B, N, max_steps).total * sizeof(float);
 }
 
@@ -223,6 +248,9 @@ int gvx_dec_train_fwd(const gvx_dims *dd, const gvx_weights *w, const void *pack
     GVX_CHECK(w && packed_ && memory && mel_in && mel_out && gate_out && align_out && stash_, "null argument");
     GVX_CHECK(B > 0 && N > 0 && T > 0, "B, N, T must be positive");
     const Dims d(*dd);
+    if (dd->precision == GVX_BF16)
+        return train_fwd_bf16(d, w, (const float *)packed_, memory, mel_in, mem_lengths, B, N, T, seed, training, row_offset, mel_out,
+                              gate_out, align_out, (float *)stash_, (cudaStream_t)stream);
     const StashL S(d, B, N, T);
     const float *packed = (const float *)packed_;
     float *s = (float *)stash_;
@@ -289,6 +317,10 @@ int gvx_dec_infer(const gvx_dims *dd, const gvx_weights *w, const void *packed_,
               "null argument");
     GVX_CHECK(B > 0 && N > 0 && max_steps > 0, "B, N, max_steps must be positive");
     const Dims d(*dd);
+    if (dd->precision == GVX_BF16)
+        return infer_bf16(d, w, (const float *)packed_, memory, mem_lengths, B, N, max_steps, gate_threshold, ignore_gate, seed,
+                          training, row_offset, mel_out, gate_out, align_out, n_frames, steps_run, (float *)workspace,
+                          (cudaStream_t)stream);
     const InferL L(d, B, N, max_steps);
     const float *packed = (const float *)packed_;
     float *s = (float *)workspace;
@@ -436,3 +468,4 @@ int gvx_attention_step(const gvx_dims *dd, const gvx_weights *w, const void *pac
 
 // backward through time (gvx_dec_train_bwd) lives in its own file, same translation unit
 #include "gvx_bwd.cuh"
+#include "gvx_bf16_api.cuh"

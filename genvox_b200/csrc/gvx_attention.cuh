@@ -11,6 +11,7 @@
 // saving the [N, D] activations (1168*N bytes per sample-step in the reference).
 #pragma once
 #include "gvx_common.cuh"
+#include "gvx_io.cuh"
 
 namespace gvx {
 
@@ -41,7 +42,7 @@ struct AttnSmem {
 
 struct AttnFwdArgs {
     AttnShape s;
-    const float *q;          // [B, D]
+    SrcSum q;                // [B, D] processed query (possibly split-K partials)
     const float *pm;         // [B, N, D]
     const float *memory;     // [B, N, E]
     const float *wlc;        // [F, 2, KS]
@@ -53,8 +54,9 @@ struct AttnFwdArgs {
     float *align_out;        // row b at align_out + b * align_bstride
     long long align_bstride;
     float *cum_stash;        // cum before the update, same addressing as align_out; or null
-    float *ctx_out;          // [B, ctx_ld]
+    float *ctx_out;          // [B, ctx_ld] fp32, or null
     int ctx_ld;
+    BfDsts ctx_bf;           // bf16 copies of the context (bf16 mode)
     float *th_stash;         // [B, N, D] tanh(q + loc + pm) for the backward pass, or null
     float *conv_stash;       // [B, N, F] location-conv output for the backward pass, or null
 };
@@ -62,7 +64,7 @@ struct AttnFwdArgs {
 // stage w_{t-1} / cum_{t-1} (zero halo), the small weights and q into shared memory
 __device__ __forceinline__ void attn_stage_inputs(const AttnShape &s, const AttnSmem &L, float *sm, const float *wprev_row,
                                                   const float *cum_row, const float *wlc, const float *wldT, const float *v,
-                                                  const float *q_row) {
+                                                  const SrcSum &q, int b) {
     const int pad = (s.KS - 1) / 2, NP = s.N + s.KS - 1;
     for (int i = threadIdx.x; i < 2 * NP; i += blockDim.x) {
         const int c = i / NP, j = i - c * NP, n = j - pad;
@@ -74,7 +76,7 @@ __device__ __forceinline__ void attn_stage_inputs(const AttnShape &s, const Attn
     for (int i = threadIdx.x; i < s.F * s.D; i += blockDim.x) sm[L.wldT + i] = wldT[i];
     for (int i = threadIdx.x; i < s.D; i += blockDim.x) {
         sm[L.v + i] = v[i];
-        sm[L.q + i] = q_row[i];
+        sm[L.q + i] = src_get(q, b, i);
     }
 }
 
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_fwd(const AttnFwdA
     const int len = a.lengths ? (int)a.lengths[b] : s.N;
     float *wprev_row = a.w_prev + (size_t)b * s.N, *cum_row = a.cum + (size_t)b * s.N;
 
-    attn_stage_inputs(s, L, sm, wprev_row, cum_row, a.wlc, a.wldT, a.v, a.q + (size_t)b * s.D);
+    attn_stage_inputs(s, L, sm, wprev_row, cum_row, a.wlc, a.wldT, a.v, a.q, b);
     __syncthreads();
     attn_conv(s, L, sm);
     __syncthreads();
@@ -178,7 +180,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_fwd(const AttnFwdA
             c3 = fmaf(sm[L.w + n + 3], mem_b[(size_t)(n + 3) * s.E + e], c3);
         }
         for (; n < len; ++n) c0 = fmaf(sm[L.w + n], mem_b[(size_t)n * s.E + e], c0);
-        a.ctx_out[(size_t)b * a.ctx_ld + e] = (c0 + c1) + (c2 + c3);
+        const float cx = (c0 + c1) + (c2 + c3);
+        if (a.ctx_out) a.ctx_out[(size_t)b * a.ctx_ld + e] = cx;
+        if (a.ctx_bf.n) bf_store1(a.ctx_bf, b, e, cx);
     }
 }
 
@@ -231,16 +235,15 @@ struct AttnBwdArgs {
     const float *w_t;          // alignments of this step; row b at w_t + b * w_bstride
     long long w_bstride;
     const float *th;           // [B, N, D] stashed tanh
-    const float *dctx1; int ld1;   // d ctx_t contributions (2 and 3 may be null)
-    const float *dctx2; int ld2;
-    const float *dctx3; int ld3;
+    SrcSum dctx1, dctx2, dctx3;    // d ctx_t contributions (2 and 3 may be empty)
     const float *d_align;      // upstream d alignments of this step (row stride da_bstride) or null
     long long da_bstride;
     float *dw_carry;           // [B, N] in: d w_t from step t+1's conv channel 0; out: d w_{t-1}
     float *dcum_carry;         // [B, N] in: d cum_t; out: d cum_{t-1}
     float *dctx_out;           // [B, E] total d ctx_t
     float *de_out;             // [B, N] d energies
-    float *dq_out;             // [B, D] d processed query
+    float *dq_out;             // [B, D] d processed query (fp32) or null
+    BfDsts dq_bf;              // bf16 copies of d q (bf16 mode)
     float *dconv_out;          // [B, N, F] d conv output
 };
 
@@ -253,9 +256,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_bwd(const AttnBwdA
     const int pad = (s.KS - 1) / 2, NP = s.N + s.KS - 1;
 
     for (int e = tid; e < s.E; e += blockDim.x) {
-        float x = a.dctx1[(size_t)b * a.ld1 + e];
-        if (a.dctx2) x += a.dctx2[(size_t)b * a.ld2 + e];
-        if (a.dctx3) x += a.dctx3[(size_t)b * a.ld3 + e];
+        float x = src_get(a.dctx1, b, e);
+        if (a.dctx2.nsplit) x += src_get(a.dctx2, b, e);
+        if (a.dctx3.nsplit) x += src_get(a.dctx3, b, e);
         sm[L.dctx + e] = x;
         a.dctx_out[(size_t)b * s.E + e] = x;
     }
@@ -348,7 +351,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_bwd(const AttnBwdA
     for (int i = tid; i < s.D; i += blockDim.x) {
         float q = 0.f;
         for (int w = 0; w < nwarp; ++w) q += sm[L.dsbuf + w * s.D + i];
-        a.dq_out[(size_t)b * s.D + i] = q;
+        if (a.dq_out) a.dq_out[(size_t)b * s.D + i] = q;
+        if (a.dq_bf.n) bf_store1(a.dq_bf, b, i, q);
     }
 
     // d wcat[c, m] = sum_{f,k} Wlc[f,c,k] * d conv[m - k + pad, f]

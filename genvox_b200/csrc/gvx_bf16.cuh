@@ -1,0 +1,160 @@
+// genvox_b200 — bf16 mode glue around the tcgen05 gate-GEMM engine (gvx_tc.cuh).
+//
+// In bf16 mode (BASELINE configs[2]/[4]) the four big per-step contractions — both nn.LSTMCell gate
+// GEMMs (/root/reference/models/tts/tacotron2.py:340,:357) and their BPTT transposes — plus the query
+// (:98) and mel/gate projections (:361-362, inference) run on tcgen05 with bf16 operands and fp32
+// accumulation.  Everything pointwise stays fp32: the engine leaves split-K fp32 partials in L2 and the
+// kernels below add them (fixed order), apply the LSTM cell / its backward, and emit the next GEMM's
+// operand directly in the engine's shared-memory image ([K/8][NPAD][8] bf16, 16-byte vector stores)
+// and, for the time-batched weight-gradient GEMMs, as row-major bf16 rows.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "gvx_common.cuh"
+#include "gvx_gemm.cuh"
+#include "gvx_io.cuh"
+#include "gvx_tc.cuh"
+
+namespace gvx {
+
+// ------------------------------------------------------------------ LSTM cell forward from split-K partials
+// partial column of (unit, gate): (unit / 32) * 128 + gate * 32 + unit % 32   (k_tc_pack_w mode 1)
+struct BfLstmFwd {
+    const float *P;            // [KS][B][ldp]
+    int KS, ldp;
+    const float *bias;         // [4*HID] unit-major (b_ih + b_hh)
+    const float *c_prev;       // [B, HID]
+    float *c_out;              // [B, HID]
+    float *gates_out;          // [B, 4*HID] unit-major activations or null
+    BfDsts h_dst;              // dropped hidden state, bf16
+    DropCfg drop;
+    uint32_t site, t;
+    int row_offset, B, HID;
+};
+__global__ void __launch_bounds__(256) k_bf_lstm_fwd(const BfLstmFwd a) {
+    const int noct = a.HID >> 3;
+    const int total = a.B * noct;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int b = idx / noct, u0 = (idx - b * noct) << 3;
+        const int colbase = (u0 >> 5) * 128 + (u0 & 31);
+        float pre[4][8];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pre[g][j] = 0.f;
+        for (int s = 0; s < a.KS; ++s) {
+            const float *row = a.P + ((size_t)s * a.B + b) * a.ldp + colbase;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const float4 x0 = *reinterpret_cast<const float4 *>(row + g * 32);
+                const float4 x1 = *reinterpret_cast<const float4 *>(row + g * 32 + 4);
+                pre[g][0] += x0.x; pre[g][1] += x0.y; pre[g][2] += x0.z; pre[g][3] += x0.w;
+                pre[g][4] += x1.x; pre[g][5] += x1.y; pre[g][6] += x1.z; pre[g][7] += x1.w;
+            }
+        }
+        float h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int u = u0 + j;
+            const float4 bi = *reinterpret_cast<const float4 *>(a.bias + 4 * u);
+            const float gi = sigmoidf_(pre[0][j] + bi.x), gf = sigmoidf_(pre[1][j] + bi.y);
+            const float gg = tanhf(pre[2][j] + bi.z), go = sigmoidf_(pre[3][j] + bi.w);
+            const float cn = gf * a.c_prev[(size_t)b * a.HID + u] + gi * gg;
+            a.c_out[(size_t)b * a.HID + u] = cn;
+            h[j] = go * tanhf(cn) * drop_mult(a.drop, a.site, a.t, (uint32_t)(b + a.row_offset), (uint32_t)u);
+            if (a.gates_out) *reinterpret_cast<float4 *>(a.gates_out + (size_t)b * 4 * a.HID + 4 * u) = make_float4(gi, gf, gg, go);
+        }
+        uint4 v;
+        v.x = pack_bf2(h[0], h[1]); v.y = pack_bf2(h[2], h[3]); v.z = pack_bf2(h[4], h[5]); v.w = pack_bf2(h[6], h[7]);
+        bf_store8(a.h_dst, b, u0, v);
+    }
+}
+
+// ------------------------------------------------------------------ LSTM cell backward -> d(pre-activations) in bf16
+// d h_dropped[b, u] = s0 + s1 + s2 ; outputs d gates (unit-major k = 4u + g) as engine image + row-major rows.
+// Blocks past `main_blocks` compute the prenet gradient mask for frame t+1 instead:
+//   dz2[b, p] = 2 * [pre2 > 0] * sum_s dpre_src[b, p]            (tacotron2.py:143)
+struct BfLstmBwd {
+    SrcSum s0, s1, s2;
+    DropCfg drop;
+    uint32_t site, t;
+    int row_offset, B, HID;
+    const float *gates;        // [B, 4*HID]
+    const float *c_prev;       // [B, HID]
+    const float *c_new;        // [B, HID]
+    float *dc;                 // [B, HID] carried, in/out
+    BfDsts dg_dst;             // d gates, bf16, columns 4u+g
+    int main_blocks;
+    SrcSum dpre_src;           // optional
+    const float *pre2;         // [B, P] prenet output of that frame
+    float *dz2;                // [B, P]
+    int P;
+};
+__global__ void __launch_bounds__(256) k_bf_lstm_bwd(const BfLstmBwd a) {
+    if ((int)blockIdx.x >= a.main_blocks) {
+        const int total = a.B * a.P;
+        for (int idx = (blockIdx.x - a.main_blocks) * blockDim.x + threadIdx.x; idx < total;
+             idx += (gridDim.x - a.main_blocks) * blockDim.x) {
+            const int b = idx / a.P, p = idx - b * a.P;
+            a.dz2[idx] = a.pre2[idx] > 0.f ? 2.f * src_get(a.dpre_src, b, p) : 0.f;
+        }
+        return;
+    }
+    const int npair = a.HID >> 1;
+    const int total = a.B * npair;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += a.main_blocks * blockDim.x) {
+        const int b = idx / npair, u0 = (idx - b * npair) << 1;
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int u = u0 + j;
+            float dh = src_get(a.s0, b, u);
+            if (a.s1.nsplit) dh += src_get(a.s1, b, u);
+            if (a.s2.nsplit) dh += src_get(a.s2, b, u);
+            const float mult = drop_mult(a.drop, a.site, a.t, (uint32_t)(b + a.row_offset), (uint32_t)u);
+            const float4 ga = *reinterpret_cast<const float4 *>(a.gates + (size_t)b * 4 * a.HID + 4 * u);
+            const size_t ci = (size_t)b * a.HID + u;
+            float dcp;
+            const float4 dp = lstm_bwd_point(dh, mult, ga, a.c_prev[ci], a.c_new[ci], a.dc[ci], dcp);
+            a.dc[ci] = dcp;
+            w[2 * j] = pack_bf2(dp.x, dp.y);
+            w[2 * j + 1] = pack_bf2(dp.z, dp.w);
+        }
+        bf_store8(a.dg_dst, b, 4 * u0, make_uint4(w[0], w[1], w[2], w[3]));
+    }
+}
+
+// out[b, m] = sum_s P[s][b][m] + bias[m]   (inference projection epilogue)
+__global__ void k_bf_finalize(const float *__restrict__ P, int KS, int B, int ldp, int M, const float *__restrict__ bias,
+                              float *__restrict__ out, int ldo) {
+    const int total = B * M;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int b = i / M, m = i - b * M;
+        float s = bias ? bias[m] : 0.f;
+        for (int k = 0; k < KS; ++k) s += P[((size_t)k * B + b) * ldp + m];
+        out[(size_t)b * ldo + m] = s;
+    }
+}
+
+// fp32 -> bf16 copy of a row-major matrix (rows x cols, ld_in -> ld_out)
+__global__ void k_to_bf16(const float *__restrict__ x, int ld_in, size_t rows, int cols, __nv_bfloat16 *__restrict__ y, int ld_out) {
+    const size_t total = rows * cols;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / cols;
+        const int c = (int)(i - r * cols);
+        y[r * ld_out + c] = __float2bfloat16(x[r * ld_in + c]);
+    }
+}
+
+// column sums of a row-major bf16 matrix [rows, cols]: two deterministic stages
+__global__ void k_colsum_bf16_part(const __nv_bfloat16 *__restrict__ x, size_t rows, int cols, int nchunk, float *__restrict__ part) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunk = blockIdx.y;
+    if (c >= cols) return;
+    const size_t r0 = rows * chunk / nchunk, r1 = rows * (chunk + 1) / nchunk;
+    float s = 0.f;
+    for (size_t r = r0; r < r1; ++r) s += __bfloat162float(x[r * cols + c]);
+    part[(size_t)chunk * cols + c] = s;
+}
+
+}  // namespace gvx

@@ -1,0 +1,639 @@
+// genvox_b200 — bf16 mode drivers: packed operand images, teacher-forced forward, BPTT, inference.
+// Same entry points as fp32 mode (gvx_api.cu dispatches on gvx_dims.precision); see gvx_bf16.cuh /
+// gvx_tc.cuh for the kernels.  Reference lines: Decoder.forward tacotron2.py:365-388, decode :333-363,
+// inference :390-414, BPTT = loss.backward() :520.
+#pragma once
+#include <cublas_v2.h>
+
+#include "gvx_attention.cuh"
+#include "gvx_bf16.cuh"
+#include "gvx_blas.cuh"
+#include "gvx_layout.cuh"
+#include "gvx_misc.cuh"
+
+namespace gvx {
+
+typedef __nv_bfloat16 bf16;
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct BfGeom {
+    int Kpa, Kpd, Kpq, Kpp, Dp;        // padded K of: att gates, dec gates, query (A), projection (Kp), S4 (D)
+    int Ta, Td, Tq, Tp;                // forward row tiles: att, dec gates, query, projection
+    int TaT, TdT, TqT;                 // backward row tiles: rows = Ka, Kd, A
+    int G4A, G4H;                      // 4A, 4H (already multiples of 128 when A, H % 32 == 0)
+    explicit BfGeom(const Dims &d)
+        : Kpa(round_up(d.Ka, 64)), Kpd(round_up(d.Kd, 64)), Kpq(round_up(d.A, 64)), Kpp(round_up(d.Kp, 64)), Dp(round_up(d.D, 64)),
+          Ta(d.A / 32), Td(d.H / 32), Tq((d.D + 127) / 128), Tp((d.M + 1 + 127) / 128),
+          TaT((d.Ka + 127) / 128), TdT((d.Kd + 127) / 128), TqT((d.A + 127) / 128), G4A(round_up(4 * d.A, 64)), G4H(round_up(4 * d.H, 64)) {}
+};
+
+inline int check_bf16_dims(const Dims &d, int B) {
+    GVX_CHECK(d.M % 8 == 0 && d.E % 8 == 0 && d.A % 32 == 0 && d.H % 32 == 0 && d.P % 8 == 0 && d.D % 8 == 0,
+              "bf16 mode: feature dims must be multiples of 8 and the rnn dims multiples of 32");
+    GVX_CHECK(B <= 128, "bf16 mode: at most 128 rows per call");
+    return 0;
+}
+
+inline int tc_pick_ks(int mtiles, int nkb) {
+    int ks = 148 / (mtiles > 0 ? mtiles : 1);
+    if (ks > 16) ks = 16;
+    if (ks > nkb) ks = nkb;
+    if (ks < 1) ks = 1;
+    return ks;
+}
+
+// ---- bf16 part of the packed weights, appended after the fp32 PackedL block (offsets in floats) ----
+struct PackedBfL {
+    size_t WaI, WdI, WaTI, WdTI, WqI, WqTI, WpgI, WpgRM, total;
+    PackedBfL(const Dims &d, size_t base) {
+        const BfGeom g(d);
+        Carver c;
+        c.o = base;
+        auto img = [&](int tiles, int kpad) { return c.take(((size_t)tiles * TC_M * kpad + 1) / 2); };
+        WaI = img(g.Ta, g.Kpa); WdI = img(g.Td, g.Kpd);
+        WaTI = img(g.TaT, g.G4A); WdTI = img(g.TdT, g.G4H);
+        WqI = img(g.Tq, g.Kpq); WqTI = img(g.TqT, g.Dp);
+        WpgI = img(g.Tp, g.Kpp);
+        WpgRM = c.take(((size_t)(d.M + 1) * d.Kp + 1) / 2);
+        total = c.o;
+    }
+};
+
+int pack_weights_bf16(const Dims &d, const gvx_weights *w, float *packed, cudaStream_t st) {
+    const BfGeom g(d);
+    const PackedL PL(d);
+    const PackedBfL BL(d, PL.total);
+    auto pack = [&](int mode, const float *s0, const float *s1, int Mtot, int K, int ld, int HID, int Kih, int tiles, int kpad,
+                    size_t off) {
+        TcPackW p;
+        memset(&p, 0, sizeof(p));
+        p.s0 = s0; p.s1 = s1; p.mode = mode; p.Mtot = Mtot; p.K = K; p.ld = ld; p.HID = HID; p.Kih = Kih;
+        k_tc_pack_w<<<grid_for((size_t)tiles * TC_M * kpad), 256, 0, st>>>(p, tiles, kpad, (bf16 *)(packed + off));
+        GVX_LAUNCHED(1);
+    };
+    pack(1, w->att_w_ih, w->att_w_hh, 4 * d.A, d.Ka, 0, d.A, d.P + d.E, g.Ta, g.Kpa, BL.WaI);
+    pack(1, w->dec_w_ih, w->dec_w_hh, 4 * d.H, d.Kd, 0, d.H, d.A + d.E, g.Td, g.Kpd, BL.WdI);
+    pack(2, w->att_w_ih, w->att_w_hh, d.Ka, 4 * d.A, 0, d.A, d.P + d.E, g.TaT, g.G4A, BL.WaTI);
+    pack(2, w->dec_w_ih, w->dec_w_hh, d.Kd, 4 * d.H, 0, d.H, d.A + d.E, g.TdT, g.G4H, BL.WdTI);
+    pack(0, w->query_w, nullptr, d.D, d.A, d.A, 0, 0, g.Tq, g.Kpq, BL.WqI);
+    pack(3, w->query_w, nullptr, d.A, d.D, d.A, 0, 0, g.TqT, g.Dp, BL.WqTI);
+    pack(0, packed + PL.Wpg, nullptr, d.M + 1, d.Kp, d.Kp, 0, 0, g.Tp, g.Kpp, BL.WpgI);
+    k_to_bf16<<<grid_for((size_t)(d.M + 1) * d.Kp), 256, 0, st>>>(packed + PL.Wpg, d.Kp, (size_t)(d.M + 1), d.Kp,
+                                                               (bf16 *)(packed + BL.WpgRM), d.Kp);
+    GVX_LAUNCHED(1);
+    GVX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- bf16 training stash -----------------------------------------------------------------------------
+struct StashBfL {
+    size_t FR, PRE1, PRE2, PM, CA, GA, CD, GD, ALIGN, CUMS, TH, CONVS, OUT, WPREV, CUM, XAI, XDI, XARM, XDRM, HCRM, PA, PD, PQ, ERR,
+        total;
+    size_t xai_stride, xdi_stride;     // bf16 elements per frame image
+    int NPAD, KSa, KSd, KSq;
+    StashBfL(const Dims &d, int B, int N, int T) {
+        const BfGeom g(d);
+        NPAD = tc_npad(B);
+        KSa = tc_pick_ks(g.Ta, g.Kpa / TC_KB); KSd = tc_pick_ks(g.Td, g.Kpd / TC_KB); KSq = tc_pick_ks(g.Tq, g.Kpq / TC_KB);
+        Carver c;
+        const size_t TB = (size_t)T * B, T1B = (size_t)(T + 1) * B;
+        FR = c.take(TB * d.M); PRE1 = c.take(TB * d.P); PRE2 = c.take(TB * d.P);
+        PM = c.take((size_t)B * N * d.D);
+        CA = c.take(T1B * d.A); GA = c.take(TB * 4 * d.A);
+        CD = c.take(T1B * d.H); GD = c.take(TB * 4 * d.H);
+        ALIGN = c.take((size_t)B * T * N); CUMS = c.take((size_t)B * T * N);
+        TH = c.take(TB * N * d.D); CONVS = c.take(TB * N * d.F);
+        OUT = c.take(TB * d.OL);
+        WPREV = c.take((size_t)B * N); CUM = c.take((size_t)B * N);
+        xai_stride = (size_t)g.Kpa * NPAD; xdi_stride = (size_t)g.Kpd * NPAD;
+        XAI = c.take((size_t)T * xai_stride / 2); XDI = c.take((size_t)T * xdi_stride / 2);
+        XARM = c.take(TB * d.Ka / 2 + 8); XDRM = c.take(TB * d.Kd / 2 + 8); HCRM = c.take(TB * d.Kp / 2 + 8);
+        PA = c.take((size_t)KSa * B * g.Ta * TC_M); PD = c.take((size_t)KSd * B * g.Td * TC_M);
+        PQ = c.take((size_t)KSq * B * g.Tq * TC_M);
+        ERR = c.take(64);
+        total = c.o;
+    }
+};
+
+struct BwdBfL {
+    size_t DOUT, DOUTB, DHC, GDI, GAI, DQI, DGDRM, DGARM, DQRM, PDXD, PDXA, PS4, DCD, DCA, DCTX, DE, DCONV, DZ2, DZ1, DPM, DW, DCUM,
+        DWA, DWD, DBIAS, PART1, PART2, ONES, TMP, COLP, ERR, total;
+    size_t pdxd_stride, pdxa_stride;   // floats per ping-pong half
+    int NPAD, KSdT, KSaT, KSs4, post_blocks, colchunks;
+    BwdBfL(const Dims &d, int B, int N, int T) {
+        const BfGeom g(d);
+        NPAD = tc_npad(B);
+        KSdT = tc_pick_ks(g.TdT, g.G4H / TC_KB); KSaT = tc_pick_ks(g.TaT, g.G4A / TC_KB); KSs4 = tc_pick_ks(g.TqT, g.Dp / TC_KB);
+        post_blocks = 148 * 4;
+        colchunks = 64;
+        Carver c;
+        const size_t TB = (size_t)T * B;
+        DOUT = c.take(TB * d.OL); DOUTB = c.take(TB * d.OL / 2 + 8);
+        DHC = c.take(TB * d.Kp);
+        GDI = c.take((size_t)g.G4H * NPAD / 2); GAI = c.take((size_t)g.G4A * NPAD / 2); DQI = c.take((size_t)g.Dp * NPAD / 2);
+        DGDRM = c.take(TB * 4 * d.H / 2 + 8); DGARM = c.take(TB * 4 * d.A / 2 + 8); DQRM = c.take(TB * d.D / 2 + 8);
+        pdxd_stride = (size_t)KSdT * B * g.TdT * TC_M; pdxa_stride = (size_t)KSaT * B * g.TaT * TC_M;
+        PDXD = c.take(2 * pdxd_stride); PDXA = c.take(2 * pdxa_stride);
+        PS4 = c.take((size_t)KSs4 * B * g.TqT * TC_M);
+        DCD = c.take((size_t)B * d.H); DCA = c.take((size_t)B * d.A);
+        DCTX = c.take(TB * d.E);
+        DE = c.take(TB * N); DCONV = c.take(TB * N * d.F);
+        DZ2 = c.take(TB * d.P); DZ1 = c.take(TB * d.P);
+        DPM = c.take((size_t)B * N * d.D);
+        DW = c.take((size_t)B * N); DCUM = c.take((size_t)B * N);
+        DWA = c.take((size_t)4 * d.A * d.Ka); DWD = c.take((size_t)4 * d.H * d.Kd);
+        DBIAS = c.take((size_t)4 * (d.A > d.H ? d.A : d.H));
+        PART1 = c.take((size_t)post_blocks * (d.D * d.F + d.D));
+        PART2 = c.take((size_t)post_blocks * d.F * 2 * d.KS);
+        ONES = c.take(TB);
+        TMP = c.take((size_t)(d.M + 1) * d.Kp + 64);
+        COLP = c.take((size_t)colchunks * 4 * (d.A > d.H ? d.A : d.H));
+        ERR = c.take(64);
+        total = c.o;
+    }
+};
+
+struct InferBfL {
+    size_t PM, PRE1, PRE2, CA, CD, Q, WPREV, CUM, OUT, ZERO, FLAGS, XAI, XDI, XPI, PA, PD, PQ, PP, ERR, total;
+    size_t xai_stride, xdi_stride;
+    int NPAD, KSa, KSd, KSq, KSp;
+    InferBfL(const Dims &d, int B, int N, int steps) {
+        const BfGeom g(d);
+        NPAD = tc_npad(B);
+        KSa = tc_pick_ks(g.Ta, g.Kpa / TC_KB); KSd = tc_pick_ks(g.Td, g.Kpd / TC_KB); KSq = tc_pick_ks(g.Tq, g.Kpq / TC_KB);
+        KSp = tc_pick_ks(g.Tp, g.Kpp / TC_KB);
+        Carver c;
+        PM = c.take((size_t)B * N * d.D);
+        PRE1 = c.take((size_t)B * d.P); PRE2 = c.take((size_t)B * d.P);
+        CA = c.take((size_t)B * d.A); CD = c.take((size_t)B * d.H);
+        Q = c.take((size_t)B * d.D);
+        WPREV = c.take((size_t)B * N); CUM = c.take((size_t)B * N);
+        OUT = c.take((size_t)steps * B * d.OL);
+        ZERO = c.take((size_t)B * d.OL);
+        FLAGS = c.take(64);
+        xai_stride = (size_t)g.Kpa * NPAD; xdi_stride = (size_t)g.Kpd * NPAD;
+        XAI = c.take(2 * xai_stride / 2); XDI = c.take(2 * xdi_stride / 2);
+        XPI = c.take((size_t)g.Kpp * NPAD / 2);
+        PA = c.take((size_t)KSa * B * g.Ta * TC_M); PD = c.take((size_t)KSd * B * g.Td * TC_M);
+        PQ = c.take((size_t)KSq * B * g.Tq * TC_M); PP = c.take((size_t)KSp * B * g.Tp * TC_M);
+        ERR = c.take(64);
+        total = c.o;
+    }
+};
+
+// one tcgen05 gate GEMM: P[KS][B][tiles*128] = Wimg . Ximg
+inline int run_tc(const bf16 *Wimg, const bf16 *Ximg, float *P, int tiles, int kpad, int KS, int B, int *err, cudaStream_t st) {
+    TcGemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.Wimg = Wimg; a.Ximg = Ximg; a.P = P; a.Kpad = kpad; a.B = B; a.ldp = tiles * TC_M; a.KS = KS; a.err = err;
+    return launch_tc_gemm(a, tiles, st);
+}
+
+inline int run_bf_lstm_fwd(const Dims &d, const float *packed, int which, const float *P, int KS, int tiles, const float *c_prev,
+                           float *c_out, float *gates_out, const BfDsts &h_dst, int B, uint64_t seed, int t, int training,
+                           int row_offset, cudaStream_t st) {
+    const PackedL PL(d);
+    BfLstmFwd a;
+    memset(&a, 0, sizeof(a));
+    a.P = P; a.KS = KS; a.ldp = tiles * TC_M;
+    a.bias = packed + (which == 0 ? PL.ba : PL.bd);
+    a.c_prev = c_prev; a.c_out = c_out; a.gates_out = gates_out; a.h_dst = h_dst;
+    a.drop = make_drop(seed, which == 0 ? d.p_att : d.p_dec, training);
+    a.site = which == 0 ? SITE_ATT : SITE_DEC;
+    a.t = (uint32_t)t; a.row_offset = row_offset; a.B = B; a.HID = which == 0 ? d.A : d.H;
+    k_bf_lstm_fwd<<<grid_for((size_t)B * a.HID / 8), 256, 0, st>>>(a);
+    GVX_LAUNCHED(1);
+    GVX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+inline int check_tc_err(int *err_dev, cudaStream_t st, const char *what) {
+    int h = 0;
+    GVX_CUDA(cudaMemcpyAsync(&h, err_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GVX_CUDA(cudaStreamSynchronize(st));
+    if (h) {
+        snprintf(g_err, sizeof(g_err), "%s: tcgen05 pipeline timeout (code %d)", what, h);
+        return 1;
+    }
+    return 0;
+}
+
+// bf16 x bf16 -> fp32 time-batched GEMMs (plain library GEMMs): row-major C[M,N] = op(A) . op(B)
+inline int gemm_tn_bf16(cudaStream_t st, int M, int N, int K, const bf16 *A, int lda, const bf16 *Bm, int ldb, float *Cm, int ldc) {
+    cublasHandle_t h;
+    GVX_TRY(blas(&h, st));
+    const float alpha = 1.f, beta = 0.f;
+    cublasStatus_t s = cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, N, M, K, &alpha, Bm, CUDA_R_16BF, ldb, A, CUDA_R_16BF, lda, &beta, Cm,
+                                    CUDA_R_32F, ldc, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
+    if (s != CUBLAS_STATUS_SUCCESS) { snprintf(g_err, sizeof(g_err), "cublasGemmEx(TN bf16) failed: %d", (int)s); return 1; }
+    return 0;
+}
+// C[M,N] = A[M,K] . W[N,K]^T
+inline int gemm_nt_bf16(cudaStream_t st, int M, int N, int K, const bf16 *A, int lda, const bf16 *Wm, int ldw, float *Cm, int ldc) {
+    cublasHandle_t h;
+    GVX_TRY(blas(&h, st));
+    const float alpha = 1.f, beta = 0.f;
+    cublasStatus_t s = cublasGemmEx(h, CUBLAS_OP_T, CUBLAS_OP_N, N, M, K, &alpha, Wm, CUDA_R_16BF, ldw, A, CUDA_R_16BF, lda, &beta, Cm,
+                                    CUDA_R_32F, ldc, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
+    if (s != CUBLAS_STATUS_SUCCESS) { snprintf(g_err, sizeof(g_err), "cublasGemmEx(NT bf16) failed: %d", (int)s); return 1; }
+    return 0;
+}
+
+__global__ void k_add_bias_rows(float *x, size_t rows, int cols, int ld, const float *__restrict__ bias) {
+    const size_t total = rows * cols;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / cols;
+        const int c = (int)(i - r * cols);
+        x[r * ld + c] += bias[c];
+    }
+}
+
+// ======================================================================================= forward (training)
+int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, const float *memory, const float *mel_in,
+                          const int64_t *mem_lengths, int B, int N, int T, uint64_t seed, int training, int row_offset,
+                          float *mel_out, float *gate_out, float *align_out, float *s, cudaStream_t st) {
+    GVX_TRY(check_bf16_dims(d, B));
+    const BfGeom g(d);
+    const PackedL PL(d);
+    const PackedBfL BL(d, PL.total);
+    const StashBfL S(d, B, N, T);
+    const int NPAD = S.NPAD;
+    const size_t BA = (size_t)B * d.A, BH = (size_t)B * d.H;
+    bf16 *XAI = (bf16 *)(s + S.XAI), *XDI = (bf16 *)(s + S.XDI), *XARM = (bf16 *)(s + S.XARM), *XDRM = (bf16 *)(s + S.XDRM),
+         *HCRM = (bf16 *)(s + S.HCRM);
+    int *err = (int *)(s + S.ERR);
+    const bf16 *WaI = (const bf16 *)(packed + BL.WaI), *WdI = (const bf16 *)(packed + BL.WdI), *WqI = (const bf16 *)(packed + BL.WqI);
+
+    ProfScope *ps_setup = new ProfScope(PS_SETUP, st);
+    GVX_CUDA(cudaMemsetAsync(err, 0, 64 * sizeof(float), st));
+    // operand images start as zeros: K padding, ctx_{-1} = h_{-1} = 0 (tacotron2.py:303-315)
+    GVX_CUDA(cudaMemsetAsync(XAI, 0, (size_t)T * S.xai_stride * sizeof(bf16), st));
+    GVX_CUDA(cudaMemsetAsync(XDI, 0, (size_t)T * S.xdi_stride * sizeof(bf16), st));
+    GVX_CUDA(cudaMemsetAsync(XARM, 0, (size_t)B * d.Ka * sizeof(bf16), st));
+    GVX_CUDA(cudaMemsetAsync(XDRM, 0, (size_t)B * d.Kd * sizeof(bf16), st));
+    GVX_CUDA(cudaMemsetAsync(s + S.CA, 0, BA * sizeof(float), st));
+    GVX_CUDA(cudaMemsetAsync(s + S.CD, 0, BH * sizeof(float), st));
+    GVX_CUDA(cudaMemsetAsync(s + S.WPREV, 0, (size_t)B * N * sizeof(float), st));
+    GVX_CUDA(cudaMemsetAsync(s + S.CUM, 0, (size_t)B * N * sizeof(float), st));
+    k_pack_frames<<<grid_for((size_t)T * B * d.M), 256, 0, st>>>(mel_in, B, d.M, T, s + S.FR);
+    GVX_LAUNCHED(1);
+    GVX_CUDA(cudaGetLastError());
+    {
+        BfDsts bf;
+        memset(&bf, 0, sizeof(bf));
+        bf.d[bf.n++] = BfDst{XAI, 1, 0, NPAD, (long long)S.xai_stride};
+        bf.d[bf.n++] = BfDst{XARM, 2, 0, d.Ka, (long long)B * d.Ka};
+        GVX_TRY(run_prenet(d, w, s + S.FR, d.M, T * B, B, seed, 0, row_offset, s + S.PRE1, s + S.PRE2, st, &bf));
+    }
+    GVX_TRY(run_processed_memory(d, w, memory, B, N, s + S.PM, st));
+    delete ps_setup;
+
+    for (int t = 0; t < T; ++t) {
+        const bool more = t + 1 < T;
+        bf16 *xa = XAI + (size_t)t * S.xai_stride, *xd = XDI + (size_t)t * S.xdi_stride;
+        bf16 *xa_n = more ? XAI + (size_t)(t + 1) * S.xai_stride : nullptr, *xd_n = more ? XDI + (size_t)(t + 1) * S.xdi_stride : nullptr;
+        bf16 *xarm_n = more ? XARM + (size_t)(t + 1) * B * d.Ka : nullptr, *xdrm = XDRM + (size_t)t * B * d.Kd;
+        bf16 *xdrm_n = more ? XDRM + (size_t)(t + 1) * B * d.Kd : nullptr, *hcrm = HCRM + (size_t)t * B * d.Kp;
+        {   // attention LSTM (tacotron2.py:338-341)
+            ProfScope ps(PS_ATT_LSTM, st);
+            GVX_TRY(run_tc(WaI, xa, s + S.PA, g.Ta, g.Kpa, S.KSa, B, err, st));
+            BfDsts h;
+            memset(&h, 0, sizeof(h));
+            add_img(h, xd, 0, NPAD); add_rm(h, xdrm, 0, d.Kd);
+            add_img(h, xa_n, d.P + d.E, NPAD); add_rm(h, xarm_n, d.P + d.E, d.Ka);
+            GVX_TRY(run_bf_lstm_fwd(d, packed, 0, s + S.PA, S.KSa, g.Ta, s + S.CA + t * BA, s + S.CA + (t + 1) * BA,
+                                    s + S.GA + (size_t)t * 4 * BA, h, B, seed, t, training, row_offset, st));
+        }
+        {   // query projection (:98): X = the h_att prefix of the decoder-LSTM operand image
+            ProfScope ps(PS_QUERY, st);
+            GVX_TRY(run_tc(WqI, xd, s + S.PQ, g.Tq, g.Kpq, S.KSq, B, err, st));
+        }
+        {   // attention (:344-353)
+            ProfScope ps(PS_ATTENTION, st);
+            AttnFwdArgs a;
+            memset(&a, 0, sizeof(a));
+            a.s = AttnShape{B, N, d.D, d.E, d.F, d.KS};
+            a.q = src_split(s + S.PQ, g.Tq * TC_M, S.KSq, (long long)B * g.Tq * TC_M);
+            a.pm = s + S.PM; a.memory = memory;
+            a.wlc = w->loc_conv_w; a.wldT = packed + PL.wldT; a.v = w->v_w; a.lengths = mem_lengths;
+            a.w_prev = s + S.WPREV; a.cum = s + S.CUM;
+            a.align_out = s + S.ALIGN + (size_t)t * N; a.align_bstride = (long long)T * N;
+            a.cum_stash = s + S.CUMS + (size_t)t * N;
+            a.ctx_out = nullptr; a.ctx_ld = d.E;
+            add_img(a.ctx_bf, xd, d.A, NPAD); add_rm(a.ctx_bf, xdrm, d.A, d.Kd);
+            add_img(a.ctx_bf, xa_n, d.P, NPAD); add_rm(a.ctx_bf, xarm_n, d.P, d.Ka);
+            add_rm(a.ctx_bf, hcrm, d.H, d.Kp);
+            a.th_stash = s + S.TH + (size_t)t * B * N * d.D;
+            a.conv_stash = s + S.CONVS + (size_t)t * B * N * d.F;
+            GVX_TRY(launch_attention_fwd(a, st));
+        }
+        {   // decoder LSTM (:355-358)
+            ProfScope ps(PS_DEC_LSTM, st);
+            GVX_TRY(run_tc(WdI, xd, s + S.PD, g.Td, g.Kpd, S.KSd, B, err, st));
+            BfDsts h;
+            memset(&h, 0, sizeof(h));
+            add_rm(h, hcrm, 0, d.Kp);
+            add_img(h, xd_n, d.A + d.E, NPAD); add_rm(h, xdrm_n, d.A + d.E, d.Kd);
+            GVX_TRY(run_bf_lstm_fwd(d, packed, 1, s + S.PD, S.KSd, g.Td, s + S.CD + t * BH, s + S.CD + (t + 1) * BH,
+                                    s + S.GD + (size_t)t * 4 * BH, h, B, seed, t, training, row_offset, st));
+        }
+    }
+    ProfScope ps_out(PS_OUTPUT, st);
+    // mel / gate projections for all frames (:360-362): [T*B, H+E] bf16 . Wpg^T
+    GVX_TRY(gemm_nt_bf16(st, T * B, d.M + 1, d.Kp, HCRM, d.Kp, (const bf16 *)(packed + BL.WpgRM), d.Kp, s + S.OUT, d.OL));
+    k_add_bias_rows<<<grid_for((size_t)T * B * (d.M + 1)), 256, 0, st>>>(s + S.OUT, (size_t)T * B, d.M + 1, d.OL, packed + PL.bpg);
+    GVX_LAUNCHED(1);
+    k_unpack_out<<<grid_for((size_t)B * (d.M + 1) * T), 256, 0, st>>>(s + S.OUT, B, d.M, d.OL, T, T, mel_out, gate_out);
+    GVX_LAUNCHED(1);
+    GVX_CUDA(cudaGetLastError());
+    GVX_CUDA(cudaMemcpyAsync(align_out, s + S.ALIGN, (size_t)B * T * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+inline int run_bf_lstm_bwd(const Dims &d, int which, const SrcSum &s0, const SrcSum &s1, const SrcSum &s2, const float *gates,
+                           const float *c_prev, const float *c_new, float *dc, const BfDsts &dg, int B, uint64_t seed, int t,
+                           int training, int row_offset, const SrcSum *dpre_src, const float *pre2, float *dz2, cudaStream_t st) {
+    BfLstmBwd a;
+    memset(&a, 0, sizeof(a));
+    a.s0 = s0; a.s1 = s1; a.s2 = s2;
+    a.drop = make_drop(seed, which == 0 ? d.p_att : d.p_dec, training);
+    a.site = which == 0 ? SITE_ATT : SITE_DEC;
+    a.t = (uint32_t)t; a.row_offset = row_offset; a.B = B; a.HID = which == 0 ? d.A : d.H;
+    a.gates = gates; a.c_prev = c_prev; a.c_new = c_new; a.dc = dc; a.dg_dst = dg;
+    a.main_blocks = grid_for((size_t)B * a.HID / 2);
+    int extra = 0;
+    if (dpre_src) {
+        a.dpre_src = *dpre_src; a.pre2 = pre2; a.dz2 = dz2; a.P = d.P;
+        extra = grid_for((size_t)B * d.P);
+    }
+    k_bf_lstm_bwd<<<a.main_blocks + extra, 256, 0, st>>>(a);
+    GVX_LAUNCHED(1);
+    GVX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ======================================================================================= backward (BPTT)
+int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, const float *memory, const int64_t *mem_lengths,
+                   int B, int N, int T, uint64_t seed, int training, int row_offset, const float *d_mel, const float *d_gate,
+                   const float *d_align, const float *s, float *x, const gvx_grads *g, float *d_memory, cudaStream_t st) {
+    GVX_TRY(check_bf16_dims(d, B));
+    const BfGeom gm(d);
+    const PackedL PL(d);
+    const PackedBfL BL(d, PL.total);
+    const StashBfL S(d, B, N, T);
+    const BwdBfL W(d, B, N, T);
+    const int NPAD = W.NPAD, TB = T * B;
+    const size_t BA = (size_t)B * d.A, BH = (size_t)B * d.H, BE = (size_t)B * d.E;
+    const bf16 *WaTI = (const bf16 *)(packed + BL.WaTI), *WdTI = (const bf16 *)(packed + BL.WdTI), *WqTI = (const bf16 *)(packed + BL.WqTI);
+    const bf16 *XARM = (const bf16 *)(s + S.XARM), *XDRM = (const bf16 *)(s + S.XDRM), *HCRM = (const bf16 *)(s + S.HCRM);
+    bf16 *GDI = (bf16 *)(x + W.GDI), *GAI = (bf16 *)(x + W.GAI), *DQI = (bf16 *)(x + W.DQI);
+    bf16 *DGDRM = (bf16 *)(x + W.DGDRM), *DGARM = (bf16 *)(x + W.DGARM), *DQRM = (bf16 *)(x + W.DQRM), *DOUTB = (bf16 *)(x + W.DOUTB);
+    int *err = (int *)(x + W.ERR);
+    const int ldd = gm.TdT * TC_M, lda = gm.TaT * TC_M, lds4 = gm.TqT * TC_M;
+
+    GVX_CUDA(cudaMemsetAsync(err, 0, 64 * sizeof(float), st));
+    GVX_CUDA(cudaMemsetAsync(x + W.DW, 0, (size_t)B * N * sizeof(float), st));
+    GVX_CUDA(cudaMemsetAsync(x + W.DCUM, 0, (size_t)B * N * sizeof(float), st));
+    GVX_CUDA(cudaMemsetAsync(x + W.DCD, 0, BH * sizeof(float), st));
+    GVX_CUDA(cudaMemsetAsync(x + W.DCA, 0, BA * sizeof(float), st));
+    GVX_CUDA(cudaMemsetAsync(GDI, 0, (size_t)gm.G4H * NPAD * sizeof(bf16), st));     // K / row padding of the operand images
+    GVX_CUDA(cudaMemsetAsync(GAI, 0, (size_t)gm.G4A * NPAD * sizeof(bf16), st));
+    GVX_CUDA(cudaMemsetAsync(DQI, 0, (size_t)gm.Dp * NPAD * sizeof(bf16), st));
+    k_fill_f32<<<grid_for((size_t)TB), 256, 0, st>>>(x + W.ONES, (size_t)TB, 1.f);
+    GVX_LAUNCHED(1);
+    k_pack_dout<<<grid_for((size_t)TB * d.OL), 256, 0, st>>>(d_mel, d_gate, B, d.M, d.OL, T, x + W.DOUT);
+    GVX_LAUNCHED(1);
+    k_to_bf16<<<grid_for((size_t)TB * d.OL), 256, 0, st>>>(x + W.DOUT, d.OL, (size_t)TB, d.OL, DOUTB, d.OL);
+    GVX_LAUNCHED(1);
+    GVX_CUDA(cudaGetLastError());
+    GVX_TRY(gemm_nn(st, TB, d.Kp, d.M + 1, x + W.DOUT, d.OL, packed + PL.Wpg, d.Kp, x + W.DHC, d.Kp, 0.f));
+
+    for (int t = T - 1; t >= 0; --t) {
+        const bool last = t == T - 1;
+        float *pdxd = x + W.PDXD + (size_t)(t & 1) * W.pdxd_stride, *pdxd_n = x + W.PDXD + (size_t)((t + 1) & 1) * W.pdxd_stride;
+        float *pdxa = x + W.PDXA + (size_t)(t & 1) * W.pdxa_stride, *pdxa_n = x + W.PDXA + (size_t)((t + 1) & 1) * W.pdxa_stride;
+        const long long sd = (long long)B * ldd, sa = (long long)B * lda;
+        {   // S1: decoder-LSTM pointwise backward
+            ProfScope ps(PS_BWD_DEC_POINT, st);
+            BfDsts dg;
+            memset(&dg, 0, sizeof(dg));
+            add_img(dg, GDI, 0, NPAD); add_rm(dg, DGDRM + (size_t)t * B * 4 * d.H, 0, 4 * d.H);
+            GVX_TRY(run_bf_lstm_bwd(d, 1, src_plain(x + W.DHC + (size_t)t * B * d.Kp, d.Kp),
+                                    last ? src_none() : src_split(pdxd_n + d.A + d.E, ldd, W.KSdT, sd), src_none(),
+                                    s + S.GD + (size_t)t * 4 * BH, s + S.CD + t * BH, s + S.CD + (t + 1) * BH, x + W.DCD, dg, B, seed,
+                                    t, training, row_offset, nullptr, nullptr, nullptr, st));
+        }
+        {   // S2: d x_dec = d gates_dec . W_dec
+            ProfScope ps(PS_BWD_DEC_GEMM, st);
+            GVX_TRY(run_tc(WdTI, GDI, pdxd, gm.TdT, gm.G4H, W.KSdT, B, err, st));
+        }
+        {   // S3: attention backward
+            ProfScope ps(PS_BWD_ATTENTION, st);
+            AttnBwdArgs a;
+            memset(&a, 0, sizeof(a));
+            a.s = AttnShape{B, N, d.D, d.E, d.F, d.KS};
+            a.memory = memory; a.wlc = w->loc_conv_w; a.wld = w->loc_dense_w; a.v = w->v_w; a.lengths = mem_lengths;
+            a.w_t = s + S.ALIGN + (size_t)t * N; a.w_bstride = (long long)T * N;
+            a.th = s + S.TH + (size_t)t * B * N * d.D;
+            a.dctx1 = src_plain(x + W.DHC + (size_t)t * B * d.Kp + d.H, d.Kp);
+            a.dctx2 = src_split(pdxd + d.A, ldd, W.KSdT, sd);
+            a.dctx3 = last ? src_none() : src_split(pdxa_n + d.P, lda, W.KSaT, sa);
+            a.d_align = d_align ? d_align + (size_t)t * N : nullptr; a.da_bstride = (long long)T * N;
+            a.dw_carry = x + W.DW; a.dcum_carry = x + W.DCUM;
+            a.dctx_out = x + W.DCTX + t * BE;
+            a.de_out = x + W.DE + (size_t)t * B * N;
+            a.dq_out = nullptr;
+            add_img(a.dq_bf, DQI, 0, NPAD); add_rm(a.dq_bf, DQRM + (size_t)t * B * d.D, 0, d.D);
+            a.dconv_out = x + W.DCONV + (size_t)t * B * N * d.F;
+            GVX_TRY(launch_attention_bwd(a, st));
+        }
+        {   // S4: d h_att = d q . W_query + (from decoder-LSTM input) + (from step t+1), attention-LSTM pointwise backward
+            ProfScope ps(PS_BWD_ATT_POINT, st);
+            GVX_TRY(run_tc(WqTI, DQI, x + W.PS4, gm.TqT, gm.Dp, W.KSs4, B, err, st));
+            BfDsts dg;
+            memset(&dg, 0, sizeof(dg));
+            add_img(dg, GAI, 0, NPAD); add_rm(dg, DGARM + (size_t)t * B * 4 * d.A, 0, 4 * d.A);
+            SrcSum dpre = last ? src_none() : src_split(pdxa_n, lda, W.KSaT, sa);
+            GVX_TRY(run_bf_lstm_bwd(d, 0, src_split(x + W.PS4, lds4, W.KSs4, (long long)B * lds4), src_split(pdxd, ldd, W.KSdT, sd),
+                                    last ? src_none() : src_split(pdxa_n + d.P + d.E, lda, W.KSaT, sa),
+                                    s + S.GA + (size_t)t * 4 * BA, s + S.CA + t * BA, s + S.CA + (t + 1) * BA, x + W.DCA, dg, B, seed,
+                                    t, training, row_offset, last ? nullptr : &dpre, last ? nullptr : s + S.PRE2 + (size_t)(t + 1) * B * d.P,
+                                    last ? nullptr : x + W.DZ2 + (size_t)(t + 1) * B * d.P, st));
+        }
+        {   // S5: d x_att = d gates_att . W_att
+            ProfScope ps(PS_BWD_ATT_GEMM, st);
+            GVX_TRY(run_tc(WaTI, GAI, pdxa, gm.TaT, gm.G4A, W.KSaT, B, err, st));
+        }
+    }
+    ProfScope ps_batched(PS_BWD_BATCHED, st);
+    {   // prenet gradient of frame 0 from the last d x_att partials (ping-pong half 0)
+        const int total = B * d.P;
+        BfLstmBwd a;
+        memset(&a, 0, sizeof(a));
+        a.main_blocks = 0; a.B = B; a.P = d.P;
+        a.dpre_src = src_split(x + W.PDXA, lda, W.KSaT, (long long)B * lda);
+        a.pre2 = s + S.PRE2; a.dz2 = x + W.DZ2;
+        k_bf_lstm_bwd<<<grid_for((size_t)total), 256, 0, st>>>(a);
+        GVX_LAUNCHED(1);
+        GVX_CUDA(cudaGetLastError());
+    }
+    // projections: d Wpg = DOUT^T . [h_dec | ctx];  biases = column sums
+    float *tmp = x + W.TMP;
+    GVX_TRY(gemm_tn_bf16(st, d.M + 1, d.Kp, TB, DOUTB, d.OL, HCRM, d.Kp, tmp, d.Kp));
+    GVX_CUDA(cudaMemcpyAsync(g->proj_w, tmp, (size_t)d.M * d.Kp * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    GVX_CUDA(cudaMemcpyAsync(g->gate_w, tmp + (size_t)d.M * d.Kp, (size_t)d.Kp * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    GVX_TRY(colsum(st, x + W.DOUT, TB, d.M + 1, d.OL, x + W.ONES, x + W.DBIAS));
+    GVX_CUDA(cudaMemcpyAsync(g->proj_b, x + W.DBIAS, (size_t)d.M * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    GVX_CUDA(cudaMemcpyAsync(g->gate_b, x + W.DBIAS + d.M, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // LSTM weights (unit-major rows, [W_ih | W_hh] columns) and biases
+    auto colsum_bf = [&](const bf16 *m, int cols, float *out) -> int {
+        dim3 grid((cols + 255) / 256, W.colchunks);
+        k_colsum_bf16_part<<<grid, 256, 0, st>>>(m, (size_t)TB, cols, W.colchunks, x + W.COLP);
+        GVX_LAUNCHED(1);
+        k_reduce_partials<<<grid_for((size_t)cols), 256, 0, st>>>(x + W.COLP, W.colchunks, cols, 0, cols, out);
+        GVX_LAUNCHED(1);
+        GVX_CUDA(cudaGetLastError());
+        return 0;
+    };
+    GVX_TRY(gemm_tn_bf16(st, 4 * d.H, d.Kd, TB, DGDRM, 4 * d.H, XDRM, d.Kd, x + W.DWD, d.Kd));
+    k_unpack_lstm_grad<<<grid_for((size_t)4 * d.H * d.Kd), 256, 0, st>>>(x + W.DWD, d.H, d.A + d.E, g->dec_w_ih, g->dec_w_hh);
+    GVX_LAUNCHED(1);
+    GVX_TRY(colsum_bf(DGDRM, 4 * d.H, x + W.DBIAS));
+    k_unpack_bias_grad<<<grid_for((size_t)4 * d.H), 256, 0, st>>>(x + W.DBIAS, d.H, g->dec_b_ih, g->dec_b_hh);
+    GVX_LAUNCHED(1);
+    GVX_TRY(gemm_tn_bf16(st, 4 * d.A, d.Ka, TB, DGARM, 4 * d.A, XARM, d.Ka, x + W.DWA, d.Ka));
+    k_unpack_lstm_grad<<<grid_for((size_t)4 * d.A * d.Ka), 256, 0, st>>>(x + W.DWA, d.A, d.P + d.E, g->att_w_ih, g->att_w_hh);
+    GVX_LAUNCHED(1);
+    GVX_TRY(colsum_bf(DGARM, 4 * d.A, x + W.DBIAS));
+    k_unpack_bias_grad<<<grid_for((size_t)4 * d.A), 256, 0, st>>>(x + W.DBIAS, d.A, g->att_b_ih, g->att_b_hh);
+    GVX_LAUNCHED(1);
+    GVX_CUDA(cudaGetLastError());
+    // query layer: d Wq [D, A] = DQ^T . h_att   (h_att_t = first A columns of the decoder-LSTM input rows)
+    GVX_TRY(gemm_tn_bf16(st, d.D, d.A, TB, DQRM, d.D, XDRM, d.Kd, g->query_w, d.A));
+
+    BwdPostArgs pa;
+    pa.TH = s + S.TH; pa.DE = x + W.DE; pa.CONVS = s + S.CONVS; pa.DCONV = x + W.DCONV; pa.ALIGN = s + S.ALIGN;
+    pa.CUMS = s + S.CUMS; pa.DCTX = x + W.DCTX; pa.PRE1 = s + S.PRE1; pa.FR = s + S.FR;
+    pa.DPM = x + W.DPM; pa.PART1 = x + W.PART1; pa.PART2 = x + W.PART2; pa.DZ2 = x + W.DZ2; pa.DZ1 = x + W.DZ1;
+    pa.post_blocks = W.post_blocks;
+    return bwd_post_common(d, w, memory, B, N, T, pa, g, d_memory, st);
+}
+
+// ======================================================================================= inference
+int infer_bf16(const Dims &d, const gvx_weights *w, const float *packed, const float *memory, const int64_t *mem_lengths,
+                      int B, int N, int max_steps, float gate_threshold, int ignore_gate, uint64_t seed, int training,
+                      int row_offset, float *mel_out, float *gate_out, float *align_out, int32_t *n_frames, int *steps_run, float *s,
+                      cudaStream_t st) {
+    GVX_TRY(check_bf16_dims(d, B));
+    const BfGeom g(d);
+    const PackedL PL(d);
+    const PackedBfL BL(d, PL.total);
+    const InferBfL L(d, B, N, max_steps);
+    const int NPAD = L.NPAD;
+    bf16 *XAI = (bf16 *)(s + L.XAI), *XDI = (bf16 *)(s + L.XDI), *XPI = (bf16 *)(s + L.XPI);
+    int *err = (int *)(s + L.ERR), *flags = (int *)(s + L.FLAGS);
+    const bf16 *WaI = (const bf16 *)(packed + BL.WaI), *WdI = (const bf16 *)(packed + BL.WdI), *WqI = (const bf16 *)(packed + BL.WqI),
+               *WpgI = (const bf16 *)(packed + BL.WpgI);
+
+    GVX_TRY(run_processed_memory(d, w, memory, B, N, s + L.PM, st));
+    GVX_CUDA(cudaMemsetAsync(err, 0, 64 * sizeof(float), st));
+    GVX_CUDA(cudaMemsetAsync(flags, 0, 64 * sizeof(int), st));
+    GVX_CUDA(cudaMemsetAsync(XAI, 0, 2 * L.xai_stride * sizeof(bf16), st));
+    GVX_CUDA(cudaMemsetAsync(XDI, 0, 2 * L.xdi_stride * sizeof(bf16), st));
+    GVX_CUDA(cudaMemsetAsync(XPI, 0, (size_t)g.Kpp * NPAD * sizeof(bf16), st));
+    GVX_CUDA(cudaMemsetAsync(s + L.CA, 0, (size_t)B * d.A * sizeof(float), st));
+    GVX_CUDA(cudaMemsetAsync(s + L.CD, 0, (size_t)B * d.H * sizeof(float), st));
+    GVX_CUDA(cudaMemsetAsync(s + L.WPREV, 0, (size_t)B * N * sizeof(float), st));
+    GVX_CUDA(cudaMemsetAsync(s + L.CUM, 0, (size_t)B * N * sizeof(float), st));
+    GVX_CUDA(cudaMemsetAsync(s + L.ZERO, 0, (size_t)B * d.OL * sizeof(float), st));
+    k_fill_i32<<<grid_for(B), 256, 0, st>>>(n_frames, B, ignore_gate ? max_steps : -1, 0);
+    GVX_LAUNCHED(1);
+    GVX_CUDA(cudaGetLastError());
+
+    int t = 0, host_running = B;
+    for (; t < max_steps; ++t) {
+        bf16 *xa = XAI + (size_t)(t & 1) * L.xai_stride, *xa_n = XAI + (size_t)((t + 1) & 1) * L.xai_stride;
+        bf16 *xd = XDI + (size_t)(t & 1) * L.xdi_stride, *xd_n = XDI + (size_t)((t + 1) & 1) * L.xdi_stride;
+        {   // prenet on the previous mel frame (tacotron2.py:398), output straight into the attention-LSTM operand image
+            ProfScope ps(PS_PRENET, st);
+            const float *prev = t == 0 ? s + L.ZERO : s + L.OUT + (size_t)(t - 1) * B * d.OL;
+            BfDsts bf;
+            memset(&bf, 0, sizeof(bf));
+            add_img(bf, xa, 0, NPAD);
+            GVX_TRY(run_prenet(d, w, prev, d.OL, B, B, seed, t, row_offset, s + L.PRE1, s + L.PRE2, st, &bf));
+        }
+        {
+            ProfScope ps(PS_ATT_LSTM, st);
+            GVX_TRY(run_tc(WaI, xa, s + L.PA, g.Ta, g.Kpa, L.KSa, B, err, st));
+            BfDsts h;
+            memset(&h, 0, sizeof(h));
+            add_img(h, xd, 0, NPAD); add_img(h, xa_n, d.P + d.E, NPAD);
+            GVX_TRY(run_bf_lstm_fwd(d, packed, 0, s + L.PA, L.KSa, g.Ta, s + L.CA, s + L.CA, nullptr, h, B, seed, t, training,
+                                    row_offset, st));
+        }
+        {
+            ProfScope ps(PS_QUERY, st);
+            GVX_TRY(run_tc(WqI, xd, s + L.PQ, g.Tq, g.Kpq, L.KSq, B, err, st));
+        }
+        {
+            ProfScope ps(PS_ATTENTION, st);
+            AttnFwdArgs a;
+            memset(&a, 0, sizeof(a));
+            a.s = AttnShape{B, N, d.D, d.E, d.F, d.KS};
+            a.q = src_split(s + L.PQ, g.Tq * TC_M, L.KSq, (long long)B * g.Tq * TC_M);
+            a.pm = s + L.PM; a.memory = memory;
+            a.wlc = w->loc_conv_w; a.wldT = packed + PL.wldT; a.v = w->v_w; a.lengths = mem_lengths;
+            a.w_prev = s + L.WPREV; a.cum = s + L.CUM;
+            a.align_out = align_out + (size_t)t * N; a.align_bstride = (long long)max_steps * N;
+            a.ctx_ld = d.E;
+            add_img(a.ctx_bf, xd, d.A, NPAD); add_img(a.ctx_bf, xa_n, d.P, NPAD); add_img(a.ctx_bf, XPI, d.H, NPAD);
+            GVX_TRY(launch_attention_fwd(a, st));
+        }
+        {
+            ProfScope ps(PS_DEC_LSTM, st);
+            GVX_TRY(run_tc(WdI, xd, s + L.PD, g.Td, g.Kpd, L.KSd, B, err, st));
+            BfDsts h;
+            memset(&h, 0, sizeof(h));
+            add_img(h, XPI, 0, NPAD); add_img(h, xd_n, d.A + d.E, NPAD);
+            GVX_TRY(run_bf_lstm_fwd(d, packed, 1, s + L.PD, L.KSd, g.Td, s + L.CD, s + L.CD, nullptr, h, B, seed, t, training,
+                                    row_offset, st));
+        }
+        float *out_t = s + L.OUT + (size_t)t * B * d.OL;
+        {
+            ProfScope ps(PS_PROJ, st);
+            GVX_TRY(run_tc(WpgI, XPI, s + L.PP, g.Tp, g.Kpp, L.KSp, B, err, st));
+            k_bf_finalize<<<grid_for((size_t)B * (d.M + 1)), 256, 0, st>>>(s + L.PP, L.KSp, B, g.Tp * TC_M, d.M + 1, packed + PL.bpg,
+                                                                          out_t, d.OL);
+            GVX_LAUNCHED(1);
+            GVX_CUDA(cudaGetLastError());
+        }
+        if (!ignore_gate) {
+            k_gate_check<<<1, 128, 0, st>>>(out_t, B, d.M, d.OL, gate_threshold, t, n_frames, flags);
+            GVX_LAUNCHED(1);
+            GVX_CUDA(cudaGetLastError());
+            if ((t + 1) % GVX_STOP_POLL == 0 || t + 1 == max_steps) {
+                GVX_CUDA(cudaMemcpyAsync(&host_running, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+                GVX_CUDA(cudaStreamSynchronize(st));
+                if (host_running == 0) { ++t; break; }
+            }
+        }
+    }
+    const int steps = t < max_steps ? t : max_steps;
+    if (!ignore_gate) {
+        k_fill_i32<<<grid_for(B), 256, 0, st>>>(n_frames, B, steps, 1);
+        GVX_LAUNCHED(1);
+    }
+    k_unpack_out<<<grid_for((size_t)B * (d.M + 1) * steps), 256, 0, st>>>(s + L.OUT, B, d.M, d.OL, steps, max_steps, mel_out, gate_out);
+    GVX_LAUNCHED(1);
+    GVX_CUDA(cudaGetLastError());
+    *steps_run = steps;
+    return check_tc_err(err, st, "gvx_dec_infer");
+}
+
+size_t packed_total_bf16(const Dims &d) { return PackedBfL(d, PackedL(d).total).total; }
+size_t stash_total_bf16(const Dims &d, int B, int N, int T) { return StashBfL(d, B, N, T).total; }
+size_t bwd_total_bf16(const Dims &d, int B, int N, int T) { return BwdBfL(d, B, N, T).total; }
+size_t infer_total_bf16(const Dims &d, int B, int N, int steps) { return InferBfL(d, B, N, steps).total; }
+
+}  // namespace gvx

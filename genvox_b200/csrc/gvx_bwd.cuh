@@ -18,6 +18,7 @@
 
 #include "../../include/genvox_b200.h"
 #include "gvx_attention.cuh"
+#include "gvx_blas.cuh"
 #include "gvx_common.cuh"
 #include "gvx_gemm.cuh"
 #include "gvx_layout.cuh"
@@ -25,54 +26,6 @@
 
 namespace gvx {
 int check_dims(const gvx_dims *d);
-
-#define GVX_CUBLAS(expr)                                                                             \
-    do {                                                                                             \
-        cublasStatus_t s__ = (expr);                                                                 \
-        if (s__ != CUBLAS_STATUS_SUCCESS) {                                                          \
-            snprintf(gvx::g_err, sizeof(gvx::g_err), "%s:%d: %s -> cublas status %d", __FILE__, __LINE__, #expr, (int)s__); \
-            return 1;                                                                                \
-        }                                                                                            \
-    } while (0)
-
-static int blas(cublasHandle_t *out, cudaStream_t st) {
-    static thread_local cublasHandle_t h = nullptr;
-    if (!h) {
-        GVX_CUBLAS(cublasCreate(&h));
-        GVX_CUBLAS(cublasSetMathMode(h, CUBLAS_DEFAULT_MATH));    // true fp32 sgemm (no TF32), like torch's default
-    }
-    GVX_CUBLAS(cublasSetStream(h, st));
-    *out = h;
-    return 0;
-}
-
-// row-major helpers: C[M,N] (ldc) = alpha * op(A) . op(B) + beta * C
-// NN: A [M,K] (lda), B [K,N] (ldb)
-static int gemm_nn(cudaStream_t st, int M, int N, int K, const float *A, int lda, const float *B, int ldb, float *C, int ldc,
-                   float beta) {
-    cublasHandle_t h;
-    GVX_TRY(blas(&h, st));
-    const float alpha = 1.f;
-    GVX_CUBLAS(cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, N, M, K, &alpha, B, ldb, A, lda, &beta, C, ldc));
-    return 0;
-}
-// TN: A [K,M] (lda), B [K,N] (ldb):  C = A^T . B   (weight gradients: sum over the K = T*B rows)
-static int gemm_tn(cudaStream_t st, int M, int N, int K, const float *A, int lda, const float *B, int ldb, float *C, int ldc,
-                   float beta) {
-    cublasHandle_t h;
-    GVX_TRY(blas(&h, st));
-    const float alpha = 1.f;
-    GVX_CUBLAS(cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, N, M, K, &alpha, B, ldb, A, lda, &beta, C, ldc));
-    return 0;
-}
-// column sums of a row-major X [rows, ncols] (ld): out[c] = sum_r X[r, c]
-static int colsum(cudaStream_t st, const float *X, int rows, int ncols, int ld, const float *ones, float *out) {
-    cublasHandle_t h;
-    GVX_TRY(blas(&h, st));
-    const float alpha = 1.f, beta = 0.f;
-    GVX_CUBLAS(cublasSgemv(h, CUBLAS_OP_N, ncols, rows, &alpha, X, ld, ones, 1, &beta, out, 1));
-    return 0;
-}
 
 // S1: decoder-LSTM pointwise backward.  d h_dropped = dh1 (+ dh2)
 __global__ void k_lstm_bwd_pointwise(const float *__restrict__ dh1, int ld1, const float *__restrict__ dh2, int ld2,
@@ -213,6 +166,73 @@ __global__ void k_reduce_partials(const float *__restrict__ part, int nblk, int 
     }
 }
 
+// Everything after the reverse-time chain that does not depend on the precision mode:
+// attention parameters (sums over t, b, n), memory layer, d memory, prenet.  DZ2 must already hold
+// d z2 = 2 [PRE2 > 0] d PRE2.
+struct BwdPostArgs {
+    const float *TH, *DE, *CONVS, *DCONV, *ALIGN, *CUMS, *DCTX, *PRE1, *FR;
+    float *DPM, *PART1, *PART2, *DZ2, *DZ1;
+    int post_blocks;
+};
+inline int bwd_post_common(const Dims &d, const gvx_weights *w, const float *memory, int B, int N, int T, const BwdPostArgs &p,
+                           const gvx_grads *g, float *d_memory, cudaStream_t st) {
+    const int TB = T * B;
+    {
+        const int nblk = p.post_blocks;
+        const int threads = (d.D + 31) & ~31;
+        GVX_CHECK(threads <= 512, "att_dim too large");
+        if (d.F <= 32) {
+            k_attn_post_dense<32><<<nblk, threads, 0, st>>>(p.TH, p.DE, p.CONVS, w->v_w, T, B, N, d.D, d.F, p.DPM, p.PART1);
+        } else {
+            k_attn_post_dense<64><<<nblk, threads, 0, st>>>(p.TH, p.DE, p.CONVS, w->v_w, T, B, N, d.D, d.F, p.DPM, p.PART1);
+        }
+        GVX_LAUNCHED(1);
+        GVX_CUDA(cudaGetLastError());
+        const int stride = d.D * d.F + d.D;
+        k_reduce_partials<<<grid_for((size_t)d.D * d.F), 256, 0, st>>>(p.PART1, nblk, stride, 0, d.D * d.F, g->loc_dense_w);
+        GVX_LAUNCHED(1);
+        k_reduce_partials<<<grid_for((size_t)d.D), 256, 0, st>>>(p.PART1, nblk, stride, d.D * d.F, d.D, g->v_w);
+        GVX_LAUNCHED(1);
+        const size_t smem = ((size_t)2 * (N + d.KS - 1) + (size_t)N * (d.F + 1)) * sizeof(float);
+        GVX_CHECK(smem <= 200 * 1024, "token count too large for the conv-gradient kernel");
+        static size_t configured = 0;
+        if (smem > configured) {
+            GVX_CUDA(cudaFuncSetAttribute(k_attn_post_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        k_attn_post_conv<<<nblk, 512, smem, st>>>(p.DCONV, p.ALIGN, p.CUMS, T, B, N, d.F, d.KS, p.PART2);
+        GVX_LAUNCHED(1);
+        GVX_CUDA(cudaGetLastError());
+        k_reduce_partials<<<grid_for((size_t)d.F * 2 * d.KS), 256, 0, st>>>(p.PART2, nblk, d.F * 2 * d.KS, 0, d.F * 2 * d.KS,
+                                                                           g->loc_conv_w);
+        GVX_LAUNCHED(1);
+        GVX_CUDA(cudaGetLastError());
+    }
+    // memory layer and d memory:  d Wm = DPM^T . memory;  d memory = DPM . Wm + align^T . d ctx (per row)
+    GVX_TRY(gemm_tn(st, d.D, d.E, B * N, p.DPM, d.D, memory, d.E, g->memory_w, d.E, 0.f));
+    GVX_TRY(gemm_nn(st, B * N, d.E, d.D, p.DPM, d.D, w->memory_w, d.E, d_memory, d.E, 0.f));
+    {
+        cublasHandle_t h;
+        GVX_TRY(blas(&h, st));
+        const float alpha = 1.f, beta = 1.f;
+        // row-major per b: C[N, E] += A[T, N]^T . Bm[T, E];  A = ALIGN[b] (lda N), Bm = DCTX[:, b, :] (ldb B*E)
+        GVX_CUBLAS(cublasSgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_T, d.E, N, T, &alpha, p.DCTX, B * d.E, (long long)d.E,
+                                             p.ALIGN, N, (long long)T * N, &beta, d_memory, d.E, (long long)N * d.E, B));
+    }
+    // prenet (tacotron2.py:140-144): d W1 = d z2^T . PRE1;  d PRE1 = d z2 . W1;  d z1 = 2 [PRE1 > 0] d PRE1;  d W0 = d z1^T . frames
+    GVX_TRY(gemm_tn(st, d.P, d.P, TB, p.DZ2, d.P, p.PRE1, d.P, g->prenet_w1, d.P, 0.f));
+    GVX_TRY(gemm_nn(st, TB, d.P, d.P, p.DZ2, d.P, w->prenet_w1, d.P, p.DZ1, d.P, 0.f));
+    k_prenet_bwd_mask<<<grid_for((size_t)TB * d.P), 256, 0, st>>>(p.DZ1, d.P, p.PRE1, TB, d.P, p.DZ1);
+    GVX_LAUNCHED(1);
+    GVX_CUDA(cudaGetLastError());
+    GVX_TRY(gemm_tn(st, d.P, d.M, TB, p.DZ1, d.P, p.FR, d.M, g->prenet_w0, d.M, 0.f));
+    return 0;
+}
+
+int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, const float *memory, const int64_t *mem_lengths,
+                   int B, int N, int T, uint64_t seed, int training, int row_offset, const float *d_mel, const float *d_gate,
+                   const float *d_align, const float *s, float *x, const gvx_grads *g, float *d_memory, cudaStream_t st);
+
 }  // namespace gvx
 
 using namespace gvx;
@@ -226,6 +246,9 @@ extern "C" int gvx_dec_train_bwd(const gvx_dims *dd, const gvx_weights *w, const
     GVX_CHECK(B > 0 && N > 0 && T > 0, "B, N, T must be positive");
     const Dims d(*dd);
     GVX_CHECK(d.F <= 64 && d.D <= 512, "backward supports loc_filters <= 64 and att_dim <= 512");
+    if (dd->precision == GVX_BF16)
+        return train_bwd_bf16(d, w, (const float *)packed_, memory, mem_lengths, B, N, T, seed, training, row_offset, d_mel, d_gate,
+                              d_align, (const float *)stash_, (float *)workspace, g, d_memory, (cudaStream_t)stream);
     GVX_CHECK(d.F * 2 * d.KS <= 8 * 512, "location conv too large for the backward reduction kernel");
     const StashL S(d, B, N, T);
     const BwdL W(d, B, N, T);
@@ -287,9 +310,9 @@ extern "C" int gvx_dec_train_bwd(const gvx_dims *dd, const gvx_weights *w, const
             a.memory = memory; a.wlc = w->loc_conv_w; a.wld = w->loc_dense_w; a.v = w->v_w; a.lengths = mem_lengths;
             a.w_t = s + S.ALIGN + (size_t)t * N; a.w_bstride = (long long)T * N;
             a.th = s + S.TH + (size_t)t * B * N * d.D;
-            a.dctx1 = x + W.DHC + (size_t)t * B * d.Kp + d.H; a.ld1 = d.Kp;
-            a.dctx2 = dxd + d.A; a.ld2 = d.Kd;
-            a.dctx3 = last ? nullptr : dxa_next + d.P; a.ld3 = d.Ka;
+            a.dctx1 = src_plain(x + W.DHC + (size_t)t * B * d.Kp + d.H, d.Kp);
+            a.dctx2 = src_plain(dxd + d.A, d.Kd);
+            a.dctx3 = last ? src_none() : src_plain(dxa_next + d.P, d.Ka);
             a.d_align = d_align ? d_align + (size_t)t * N : nullptr; a.da_bstride = (long long)T * N;
             a.dw_carry = x + W.DW; a.dcum_carry = x + W.DCUM;
             a.dctx_out = x + W.DCTX + t * BE;
@@ -359,61 +382,15 @@ extern "C" int gvx_dec_train_bwd(const gvx_dims *dd, const gvx_weights *w, const
     // query layer: d Wq [D, A] = DQ^T . HA[1:]
     GVX_TRY(gemm_tn(st, d.D, d.A, TB, x + W.DQ, d.D, s + S.HA + BA, d.A, g->query_w, d.A, 0.f));
 
-    // attention parameters that sum over (t, b, n)
-    {
-        const int nblk = W.post_blocks;
-        const int threads = (d.D + 31) & ~31;
-        GVX_CHECK(threads <= 512, "att_dim too large");
-        if (d.F <= 32) {
-            k_attn_post_dense<32><<<nblk, threads, 0, st>>>(s + S.TH, x + W.DE, s + S.CONVS, w->v_w, T, B, N, d.D, d.F,
-                                                           x + W.DPM, x + W.PART1);
-        } else {
-            k_attn_post_dense<64><<<nblk, threads, 0, st>>>(s + S.TH, x + W.DE, s + S.CONVS, w->v_w, T, B, N, d.D, d.F,
-                                                           x + W.DPM, x + W.PART1);
-        }
-        GVX_LAUNCHED(1);
-        GVX_CUDA(cudaGetLastError());
-        const int stride = d.D * d.F + d.D;
-        k_reduce_partials<<<grid_for((size_t)d.D * d.F), 256, 0, st>>>(x + W.PART1, nblk, stride, 0, d.D * d.F, g->loc_dense_w);
-    GVX_LAUNCHED(1);
-        k_reduce_partials<<<grid_for((size_t)d.D), 256, 0, st>>>(x + W.PART1, nblk, stride, d.D * d.F, d.D, g->v_w);
-    GVX_LAUNCHED(1);
-        const size_t smem = ((size_t)2 * (N + d.KS - 1) + (size_t)N * (d.F + 1)) * sizeof(float);
-        GVX_CHECK(smem <= 200 * 1024, "token count too large for the conv-gradient kernel");
-        static size_t configured = 0;
-        if (smem > configured) {
-            GVX_CUDA(cudaFuncSetAttribute(k_attn_post_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
-        k_attn_post_conv<<<nblk, 512, smem, st>>>(x + W.DCONV, s + S.ALIGN, s + S.CUMS, T, B, N, d.F, d.KS, x + W.PART2);
-    GVX_LAUNCHED(1);
-        GVX_CUDA(cudaGetLastError());
-        k_reduce_partials<<<grid_for((size_t)d.F * 2 * d.KS), 256, 0, st>>>(x + W.PART2, nblk, d.F * 2 * d.KS, 0,
-                                                                           d.F * 2 * d.KS, g->loc_conv_w);
-    GVX_LAUNCHED(1);
-        GVX_CUDA(cudaGetLastError());
-    }
-    // memory layer and d memory:  d Wm = DPM^T . memory;  d memory = DPM . Wm + align^T . d ctx (per row)
-    GVX_TRY(gemm_tn(st, d.D, d.E, B * N, x + W.DPM, d.D, memory, d.E, g->memory_w, d.E, 0.f));
-    GVX_TRY(gemm_nn(st, B * N, d.E, d.D, x + W.DPM, d.D, w->memory_w, d.E, d_memory, d.E, 0.f));
-    {
-        cublasHandle_t h;
-        GVX_TRY(blas(&h, st));
-        const float alpha = 1.f, beta = 1.f;
-        // row-major per b: C[N, E] += A[T, N]^T . Bm[T, E];  A = ALIGN[b] (lda N), Bm = DCTX[:, b, :] (ldb B*E)
-        GVX_CUBLAS(cublasSgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_T, d.E, N, T, &alpha, x + W.DCTX, B * d.E,
-                                             (long long)d.E, s + S.ALIGN, N, (long long)T * N, &beta, d_memory, d.E,
-                                             (long long)N * d.E, B));
-    }
-    // prenet (tacotron2.py:140-144): d z2 = d PRE2 * 2 [PRE2 > 0];  d W1 = d z2^T . PRE1;  d PRE1 = d z2 . W1; ...
+    // prenet mask, then everything that does not depend on the precision mode
     k_prenet_bwd_mask<<<grid_for((size_t)TB * d.P), 256, 0, st>>>(x + W.DXA, d.Ka, s + S.PRE2, TB, d.P, x + W.DZ2);
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
-    GVX_TRY(gemm_tn(st, d.P, d.P, TB, x + W.DZ2, d.P, s + S.PRE1, d.P, g->prenet_w1, d.P, 0.f));
-    GVX_TRY(gemm_nn(st, TB, d.P, d.P, x + W.DZ2, d.P, w->prenet_w1, d.P, x + W.DZ1, d.P, 0.f));
-    k_prenet_bwd_mask<<<grid_for((size_t)TB * d.P), 256, 0, st>>>(x + W.DZ1, d.P, s + S.PRE1, TB, d.P, x + W.DZ1);
-    GVX_LAUNCHED(1);
-    GVX_CUDA(cudaGetLastError());
-    GVX_TRY(gemm_tn(st, d.P, d.M, TB, x + W.DZ1, d.P, s + S.FR, d.M, g->prenet_w0, d.M, 0.f));
-    return 0;
+    BwdPostArgs pa;
+    pa.TH = s + S.TH; pa.DE = x + W.DE; pa.CONVS = s + S.CONVS; pa.DCONV = x + W.DCONV; pa.ALIGN = s + S.ALIGN;
+    pa.CUMS = s + S.CUMS; pa.DCTX = x + W.DCTX; pa.PRE1 = s + S.PRE1; pa.FR = s + S.FR;
+    pa.DPM = x + W.DPM; pa.PART1 = x + W.PART1; pa.PART2 = x + W.PART2; pa.DZ2 = x + W.DZ2; pa.DZ1 = x + W.DZ1;
+    pa.post_blocks = W.post_blocks;
+    return bwd_post_common(d, w, memory, B, N, T, pa, g, d_memory, st);
 }
+

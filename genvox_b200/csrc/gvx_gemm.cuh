@@ -16,6 +16,7 @@
 //   EpiLstmBwd   backward of the same pointwise (BPTT, tacotron2.py:520)
 #pragma once
 #include "gvx_common.cuh"
+#include "gvx_io.cuh"
 
 namespace gvx {
 
@@ -66,6 +67,7 @@ struct EpiStore {
     int t0;                // Philox t of the first frame
     int rows_per_frame;    // rows of X per frame (B); row m -> frame m / B, batch row m % B
     int row_offset;
+    BfDsts bf;             // optional bf16 copies (bf16 mode), addressed by (frame, batch row, column)
 
     template <int BT, int R>
     __device__ __forceinline__ void run(const float *tile, int m0, int r0, int M, int Rtot) const {
@@ -83,6 +85,10 @@ struct EpiStore {
                 v = fmaxf(v, 0.f) * drop_mult(drop, site, (uint32_t)(t0 + f), (uint32_t)(brow + row_offset), (uint32_t)rr);
             }
             out[(size_t)m * ldo + rr] = v;
+            if (bf.n) {
+                const int f = m / rows_per_frame;
+                bf_store1_t(bf, f, m - f * rows_per_frame, rr, v);
+            }
         }
     }
 };

@@ -1,0 +1,82 @@
+// genvox_b200 — small I/O descriptors shared by the bf16-mode kernels and the attention kernels:
+// SrcSum reads a value that may still be split-K partial sums, BfDsts scatters a bf16 activation to the
+// tcgen05 operand image(s) and/or row-major rows.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "gvx_common.cuh"
+
+namespace gvx {
+
+// value(b, col) = sum_s p[s * split_stride + b * ld + col]   (split-K partials or a plain matrix)
+struct SrcSum {
+    const float *p;
+    int ld;
+    int nsplit;
+    long long split_stride;
+};
+__device__ __forceinline__ float src_get(const SrcSum &s, int b, int col) {
+    float v = 0.f;
+    const float *q = s.p + (size_t)b * s.ld + col;
+    for (int i = 0; i < s.nsplit; ++i) v += q[(size_t)i * s.split_stride];
+    return v;
+}
+inline SrcSum src_plain(const float *p, int ld) { return SrcSum{p, ld, p ? 1 : 0, 0}; }
+inline SrcSum src_split(const float *p, int ld, int nsplit, long long stride) { return SrcSum{p, ld, p ? nsplit : 0, stride}; }
+inline SrcSum src_none() { return SrcSum{nullptr, 0, 0, 0}; }
+
+// destination of a bf16 activation vector: engine image or row-major rows
+struct BfDst {
+    __nv_bfloat16 *p;
+    int kind;    // 0 none, 1 image [K/8][npad][8] starting at element column `koff`, 2 row-major (ld) starting at column `koff`
+    int koff;    // multiple of 8
+    int ld;      // image: NPAD; row-major: row stride in elements
+    long long tstride;   // elements between consecutive frames (bf_store1_t only)
+};
+constexpr int BF_MAXDST = 5;
+struct BfDsts {
+    BfDst d[BF_MAXDST];
+    int n;
+};
+inline void add_img(BfDsts &s, __nv_bfloat16 *p, int koff, int npad) {
+    if (p) s.d[s.n++] = BfDst{p, 1, koff, npad, 0};
+}
+inline void add_rm(BfDsts &s, __nv_bfloat16 *p, int koff, int ld) {
+    if (p) s.d[s.n++] = BfDst{p, 2, koff, ld, 0};
+}
+// 8 consecutive columns k..k+7 (k multiple of 8) of row b
+__device__ __forceinline__ void bf_store8(const BfDsts &s, int b, int k, uint4 v) {
+    for (int i = 0; i < s.n; ++i) {
+        const BfDst &d = s.d[i];
+        const int kk = d.koff + k;
+        if (d.kind == 1) *reinterpret_cast<uint4 *>(d.p + ((size_t)(kk >> 3) * d.ld + b) * 8) = v;
+        else *reinterpret_cast<uint4 *>(d.p + (size_t)b * d.ld + kk) = v;
+    }
+}
+// one column k of row b
+__device__ __forceinline__ void bf_store1(const BfDsts &s, int b, int k, float x) {
+    const __nv_bfloat16 h = __float2bfloat16(x);
+    for (int i = 0; i < s.n; ++i) {
+        const BfDst &d = s.d[i];
+        const int kk = d.koff + k;
+        if (d.kind == 1) d.p[((size_t)(kk >> 3) * d.ld + b) * 8 + (kk & 7)] = h;
+        else d.p[(size_t)b * d.ld + kk] = h;
+    }
+}
+// one column k of row b of frame t (time-batched producers: prenet over all frames)
+__device__ __forceinline__ void bf_store1_t(const BfDsts &s, int t, int b, int k, float x) {
+    const __nv_bfloat16 h = __float2bfloat16(x);
+    for (int i = 0; i < s.n; ++i) {
+        const BfDst &d = s.d[i];
+        const int kk = d.koff + k;
+        __nv_bfloat16 *base = d.p + (size_t)t * d.tstride;
+        if (d.kind == 1) base[((size_t)(kk >> 3) * d.ld + b) * 8 + (kk & 7)] = h;
+        else base[(size_t)b * d.ld + kk] = h;
+    }
+}
+__device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&v);
+}
+
+}  // namespace gvx

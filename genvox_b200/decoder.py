@@ -114,6 +114,8 @@ class Decoder(nn.Module):
         self.linear_projection = LinearParams(decoder_rnn_dim + encoder_embedding_dim, n_mels)
         self.gate_layer = LinearParams(decoder_rnn_dim + encoder_embedding_dim, 1, bias=True, w_init_gain="sigmoid")
 
+        # arithmetic of the recurrent GEMMs: "fp32" (FFMA, parity mode) or "bf16" (tcgen05, fp32 accumulate)
+        self.precision = "fp32"
         # dropout stream control (the reference draws from torch's global RNG, tacotron2.py:143,341,358)
         self.dropout_row_offset = 0        # data parallel: first row of this rank in the global batch
         self._forced_seed = None
@@ -143,7 +145,8 @@ class Decoder(nn.Module):
         return _native.GvxDims(self.n_mel_channels, self.encoder_embedding_dim, self.attention_rnn_dim,
                                self.decoder_rnn_dim, self.prenet_dim, self.attention_dim,
                                self.attention_location_n_filters, self.attention_location_kernel_size,
-                               float(self.p_attention_dropout), float(self.p_decoder_dropout))
+                               float(self.p_attention_dropout), float(self.p_decoder_dropout),
+                               {"fp32": 0, "bf16": 1}[self.precision])
 
     @staticmethod
     def _weights_struct(params):
@@ -157,7 +160,7 @@ class Decoder(nn.Module):
                 raise RuntimeError("genvox_b200: decoder parameters must be contiguous float32 CUDA tensors")
         dims = self._dims()
         weights = self._weights_struct(params)
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        key = (self.precision,) + tuple((p.data_ptr(), p._version) for p in params)
         if key != self._pack_key:
             nbytes = lib.gvx_dec_packed_bytes(C.byref(dims))
             if nbytes == 0:
@@ -228,11 +231,12 @@ def decoder_kwargs_from(ref_decoder):
         attention_location_n_filters=conv.out_channels, attention_location_kernel_size=conv.kernel_size[0])
 
 
-def install(model):
+def install(model, precision="fp32"):
     """Swap `model.decoder` (a reference Tacotron2, tacotron2.py:416-448) for the B200-native Decoder,
     keeping its parameters.  Tacotron2.forward/inference, the Trainer and the Synthesizer are untouched."""
     ref = model.decoder
     new = Decoder(**decoder_kwargs_from(ref))
+    new.precision = precision
     new.load_state_dict(ref.state_dict(), strict=True)
     p = next(ref.parameters())
     new.to(device=p.device, dtype=p.dtype)

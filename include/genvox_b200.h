@@ -45,7 +45,13 @@ typedef struct gvx_dims {
     int32_t loc_kernel;        /* attention_location_kernel_size, 31 (odd) */
     float p_att_dropout;       /* 0.1 */
     float p_dec_dropout;       /* 0.1 */
+    int32_t precision;         /* GVX_FP32: fp32 FFMA everywhere (parity mode, BASELINE configs[0],[1]);
+                                  GVX_BF16: gate / query / projection GEMMs on tcgen05 with bf16 operands and fp32
+                                  accumulation, pointwise math, cell state and attention in fp32 (configs[2],[4]);
+                                  needs dims % 8 == 0, rnn dims % 32 == 0 and at most 128 rows per call */
 } gvx_dims;
+#define GVX_FP32 0
+#define GVX_BF16 1
 
 /* Decoder parameters in state_dict layout, row-major [out, in]:
  * names are the reference's `decoder.*` keys. */

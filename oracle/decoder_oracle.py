@@ -25,6 +25,51 @@ import torch.nn.functional as F
 from . import philox
 
 
+# ---- optional bf16 semantics of the product's bf16 mode (gate / query / projection GEMM operands rounded to
+# bf16, gradients of those GEMM outputs rounded to bf16 in backward; everything else in the working dtype)
+_BF16 = False
+
+
+class bf16_semantics:
+    """with O.bf16_semantics(): ...  — the oracle then mirrors genvox_b200's bf16 mode rounding points."""
+
+    def __enter__(self):
+        global _BF16
+        self.prev, _BF16 = _BF16, True
+
+    def __exit__(self, *exc):
+        global _BF16
+        _BF16 = self.prev
+
+
+class _RoundFwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def _rf(x):
+    return _RoundFwd.apply(x) if _BF16 else x
+
+
+def _rb(x):
+    return _RoundBwd.apply(x) if (_BF16 and x.requires_grad) else x
+
+
 def _t(x, dtype):
     if isinstance(x, torch.Tensor):
         return x.to(dtype) if x.is_floating_point() else x
@@ -73,7 +118,7 @@ def prenet(P, frames: torch.Tensor, seed: int, t0: int = 0, row_offset: int = 0)
 
 def lstm_cell(x, h, c, w_ih, w_hh, b_ih, b_hh):
     """nn.LSTMCell (tacotron2.py:286,294,340,357): gate row order i, f, g, o."""
-    gates = F.linear(x, w_ih, b_ih) + F.linear(h, w_hh, b_hh)
+    gates = _rb(F.linear(_rf(x), _rf(w_ih), b_ih) + F.linear(_rf(h), _rf(w_hh), b_hh))
     i, f, g, o = gates.chunk(4, dim=1)
     i, f, g, o = torch.sigmoid(i), torch.sigmoid(f), torch.tanh(g), torch.sigmoid(o)
     c_new = f * c + i * g
@@ -91,7 +136,7 @@ def location_features(P, w_prev, w_cum):
 
 def attention(P, h_att, memory, processed_memory, w_prev, w_cum, mask):
     """Attention.forward + get_alignment_energies, tacotron2.py:89-129."""
-    q = F.linear(h_att, P["attention_layer.query_layer.linear_layer.weight"]).unsqueeze(1)   # :98
+    q = _rb(F.linear(_rf(h_att), _rf(P["attention_layer.query_layer.linear_layer.weight"]))).unsqueeze(1)   # :98
     loc = location_features(P, w_prev, w_cum)                                                # :99
     e = F.linear(torch.tanh(q + loc + processed_memory),
                  P["attention_layer.v.linear_layer.weight"]).squeeze(-1)                     # :102-103
@@ -131,8 +176,8 @@ def decode_step(P, S: DecoderState, prenet_out, t: int, training: bool, p_att: f
                                  P["decoder_rnn.bias_ih"], P["decoder_rnn.bias_hh"])        # :357
     S.h_dec = philox_dropout(S.h_dec, p_dec, training, seed, philox.SITE_DEC, t, row_offset)  # :358 (carried)
     hc = torch.cat((S.h_dec, S.ctx), dim=1)                                                 # :360
-    mel = F.linear(hc, P["linear_projection.linear_layer.weight"], P["linear_projection.linear_layer.bias"])  # :361
-    gate = F.linear(hc, P["gate_layer.linear_layer.weight"], P["gate_layer.linear_layer.bias"])               # :362
+    mel = F.linear(_rf(hc), _rf(P["linear_projection.linear_layer.weight"]), P["linear_projection.linear_layer.bias"])  # :361
+    gate = F.linear(_rf(hc), _rf(P["gate_layer.linear_layer.weight"]), P["gate_layer.linear_layer.bias"])               # :362
     return mel, gate.squeeze(1), S.w
 
 
