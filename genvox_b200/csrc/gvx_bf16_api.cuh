@@ -5,7 +5,7 @@
 #pragma once
 #include <cublas_v2.h>
 
-#include "gvx_attention.cuh"
+#include "gvx_attention_fast.cuh"
 #include "gvx_bf16.cuh"
 #include "gvx_blas.cuh"
 #include "gvx_layout.cuh"
@@ -125,7 +125,7 @@ struct BwdBfL {
         const BfGeom g(d);
         NPAD = tc_npad(B);
         KSdT = tc_pick_ks(g.TdT, g.G4H / TC_KB); KSaT = tc_pick_ks(g.TaT, g.G4A / TC_KB); KSs4 = tc_pick_ks(g.TqT, g.Dp / TC_KB);
-        post_blocks = 148 * 4;
+        post_blocks = 148 * 8;
         colchunks = 64;
         Carver c;
         const size_t TB = (size_t)T * B;
@@ -326,7 +326,7 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
             add_rm(a.ctx_bf, hcrm, d.H, d.Kp);
             a.th_stash = s + S.TH + (size_t)t * B * N * d.D;
             a.conv_stash = s + S.CONVS + (size_t)t * B * N * d.F;
-            GVX_TRY(launch_attention_fwd(a, st));
+            GVX_TRY(launch_attention_fwd_any(a, st));
         }
         {   // decoder LSTM (:355-358)
             ProfScope ps(PS_DEC_LSTM, st);
@@ -446,7 +446,7 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
             a.dq_out = nullptr;
             add_img(a.dq_bf, DQI, 0, NPAD); add_rm(a.dq_bf, DQRM + (size_t)t * B * d.D, 0, d.D);
             a.dconv_out = x + W.DCONV + (size_t)t * B * N * d.F;
-            GVX_TRY(launch_attention_bwd(a, st));
+            GVX_TRY(launch_attention_bwd_any(a, st));
         }
         {   // S4: d h_att = d q . W_query + (from decoder-LSTM input) + (from step t+1), attention-LSTM pointwise backward
             ProfScope ps(PS_BWD_ATT_POINT, st);
@@ -588,7 +588,7 @@ int infer_bf16(const Dims &d, const gvx_weights *w, const float *packed, const f
             a.align_out = align_out + (size_t)t * N; a.align_bstride = (long long)max_steps * N;
             a.ctx_ld = d.E;
             add_img(a.ctx_bf, xd, d.A, NPAD); add_img(a.ctx_bf, xa_n, d.P, NPAD); add_img(a.ctx_bf, XPI, d.H, NPAD);
-            GVX_TRY(launch_attention_fwd(a, st));
+            GVX_TRY(launch_attention_fwd_any(a, st));
         }
         {
             ProfScope ps(PS_DEC_LSTM, st);

@@ -17,7 +17,7 @@
 #include <cublas_v2.h>
 
 #include "../../include/genvox_b200.h"
-#include "gvx_attention.cuh"
+#include "gvx_attention_fast.cuh"
 #include "gvx_blas.cuh"
 #include "gvx_common.cuh"
 #include "gvx_gemm.cuh"
@@ -68,11 +68,14 @@ __global__ void k_unpack_bias_grad(const float *__restrict__ db, int HID, float 
 
 // Post-pass 1: for every token (b, n), over all t:  d s = d e * v * (1 - th^2)
 //   d pm[b,n,d] = sum_t d s;  d v[d] += sum d e * th;  d Wld[d,f] += sum d s * conv[f]
-// blockDim = D threads (thread = d); per-block partials of d Wld / d v are reduced by k_reduce_partials.
+// blockDim = D threads (thread = d), 8 resident blocks per SM and a 4-deep unrolled time loop keep enough
+// loads in flight to stream the [T,B,N,D] tanh stash near HBM speed; per-block partials of d Wld / d v are
+// reduced in a fixed order by k_reduce_partials.
 template <int FMAX>
-__global__ void k_attn_post_dense(const float *__restrict__ TH, const float *__restrict__ DE, const float *__restrict__ CONVS,
-                                  const float *__restrict__ v, int T, int B, int N, int D, int F, float *__restrict__ DPM,
-                                  float *__restrict__ part /* [grid][D*F + D] */) {
+__global__ void __launch_bounds__(512, (FMAX <= 32 ? 2 : 1)) k_attn_post_dense(const float *__restrict__ TH, const float *__restrict__ DE,
+                                                             const float *__restrict__ CONVS, const float *__restrict__ v, int T,
+                                                             int B, int N, int D, int F, float *__restrict__ DPM,
+                                                             float *__restrict__ part /* [grid][D*F + D] */) {
     const int d = threadIdx.x;
     float wacc[FMAX];
 #pragma unroll
@@ -82,18 +85,48 @@ __global__ void k_attn_post_dense(const float *__restrict__ TH, const float *__r
     const size_t tok_stride = (size_t)B * N;
     for (int tok = blockIdx.x; tok < B * N; tok += gridDim.x) {
         float pacc = 0.f;
-        for (int t = 0; t < T; ++t) {
+        int t = 0;
+        for (; t + 4 <= T; t += 4) {
+            float de[4], th[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const size_t row = (size_t)(t + i) * tok_stride + tok;
+                de[i] = DE[row];
+                th[i] = d < D ? TH[row * D + d] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const size_t row = (size_t)(t + i) * tok_stride + tok;
+                const float ds = de[i] * vd * (1.f - th[i] * th[i]);
+                pacc += ds;
+                vacc = fmaf(de[i], th[i], vacc);
+                const float4 *cv = reinterpret_cast<const float4 *>(CONVS + row * F);
+                if (FMAX % 4 == 0 && F == FMAX) {
+#pragma unroll
+                    for (int f4 = 0; f4 < FMAX / 4; ++f4) {
+                        const float4 c = cv[f4];
+                        wacc[4 * f4] = fmaf(ds, c.x, wacc[4 * f4]); wacc[4 * f4 + 1] = fmaf(ds, c.y, wacc[4 * f4 + 1]);
+                        wacc[4 * f4 + 2] = fmaf(ds, c.z, wacc[4 * f4 + 2]); wacc[4 * f4 + 3] = fmaf(ds, c.w, wacc[4 * f4 + 3]);
+                    }
+                } else {
+                    const float *cs = CONVS + row * F;
+#pragma unroll
+                    for (int f = 0; f < FMAX; ++f)
+                        if (f < F) wacc[f] = fmaf(ds, cs[f], wacc[f]);
+                }
+            }
+        }
+        for (; t < T; ++t) {
             const size_t row = (size_t)t * tok_stride + tok;
             const float de = DE[row];
-            if (de == 0.f) continue;      // masked tokens contribute exactly zero
             const float th = d < D ? TH[row * D + d] : 0.f;
             const float ds = de * vd * (1.f - th * th);
             pacc += ds;
             vacc = fmaf(de, th, vacc);
-            const float *cv = CONVS + row * F;
+            const float *cs = CONVS + row * F;
 #pragma unroll
             for (int f = 0; f < FMAX; ++f)
-                if (f < F) wacc[f] = fmaf(ds, cv[f], wacc[f]);
+                if (f < F) wacc[f] = fmaf(ds, cs[f], wacc[f]);
         }
         if (d < D) DPM[(size_t)tok * D + d] = pacc;
     }
@@ -108,52 +141,62 @@ __global__ void k_attn_post_dense(const float *__restrict__ TH, const float *__r
 
 // Post-pass 2: d Wlc[f,c,k] = sum_{t,b,n} d conv[t,b,n,f] * wcat[t,b,c,n+k-pad]
 //   wcat channel 0 = alignments of step t-1 (zeros at t = 0), channel 1 = cum before step t.
-__global__ void k_attn_post_conv(const float *__restrict__ DCONV, const float *__restrict__ ALIGN,
-                                 const float *__restrict__ CUMS, int T, int B, int N, int F, int KS,
-                                 float *__restrict__ part /* [grid][F*2*KS] */) {
+// One thread = (filter f, channel c, block of 8 taps); the 8-tap window slides over the tokens in registers
+// (6 LDS.128 per 64 FMAs).  Per-block partials [grid][F*2*KS], reduced afterwards in a fixed order.
+__global__ void __launch_bounds__(1024, 1) k_attn_post_conv(const float *__restrict__ DCONV, const float *__restrict__ ALIGN,
+                                                              const float *__restrict__ CUMS, int T, int B, int N, int F, int KS,
+                                                              float *__restrict__ part /* [grid][F*2*KS] */) {
     extern __shared__ __align__(16) float sm[];
-    const int pad = (KS - 1) / 2, NP = N + KS - 1;
-    float *wcat = sm;                       // [2][NP]
-    float *dcv = sm + 2 * NP;               // [N][F+1]
-    const int nout = F * 2 * KS;
-    // each thread owns outputs o = tid, tid + blockDim, ... (at most 8)
+    const int pad = (KS - 1) / 2, KB = (KS + 7) / 8;
+    const int NCS = (N + 7) & ~7, NPS = NCS + 8 * KB + 8;
+    float *wc = sm;                         // [2][NPS], index = token + pad
+    float *dT = sm + 2 * NPS;               // [F][NCS]
+    const int ntask = F * 2 * KB;
+    const int task = threadIdx.x;
+    const int f = task / (2 * KB), c = (task / KB) & 1, k0 = (task % KB) * 8;
     float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     for (int item = blockIdx.x; item < T * B; item += gridDim.x) {
         const int t = item / B, b = item - t * B;
         __syncthreads();
-        for (int i = threadIdx.x; i < 2 * NP; i += blockDim.x) {
-            const int c = i / NP, n = i - c * NP - pad;
+        for (int i = threadIdx.x; i < 2 * NPS; i += blockDim.x) {
+            const int cc = i / NPS, n = i - cc * NPS - pad;
             float x = 0.f;
             if (n >= 0 && n < N) {
-                if (c == 0) x = t > 0 ? ALIGN[((size_t)b * T + (t - 1)) * N + n] : 0.f;
+                if (cc == 0) x = t > 0 ? ALIGN[((size_t)b * T + (t - 1)) * N + n] : 0.f;
                 else x = CUMS[((size_t)b * T + t) * N + n];
             }
-            wcat[i] = x;
+            wc[i] = x;
         }
         const float *src = DCONV + ((size_t)t * B + b) * N * F;
-        for (int i = threadIdx.x; i < N * F; i += blockDim.x) {
-            const int n = i / F, f = i - n * F;
-            dcv[n * (F + 1) + f] = src[i];
+        for (int i = threadIdx.x; i < NCS * F; i += blockDim.x) {
+            const int n = i / F, ff = i - n * F;
+            dT[ff * NCS + n] = n < N ? src[i] : 0.f;
         }
         __syncthreads();
+        if (task < ntask) {
+            const float *dr = dT + f * NCS, *xr = wc + c * NPS + k0;
+            for (int n0 = 0; n0 < NCS; n0 += 8) {
+                const float4 d0 = *reinterpret_cast<const float4 *>(dr + n0), d1 = *reinterpret_cast<const float4 *>(dr + n0 + 4);
+                const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+                float x[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int o = threadIdx.x + i * blockDim.x;
-            if (o < nout) {
-                const int f = o / (2 * KS), ck = o - f * 2 * KS, c = ck / KS, k = ck - c * KS;
-                const float *x = wcat + c * NP + k;
-                float a = acc[i];
-                for (int n = 0; n < N; ++n) a = fmaf(dcv[n * (F + 1) + f], x[n], a);
-                acc[i] = a;
+                for (int i = 0; i < 4; ++i) {
+                    const float4 t4 = *reinterpret_cast<const float4 *>(xr + n0 + 4 * i);
+                    x[4 * i] = t4.x; x[4 * i + 1] = t4.y; x[4 * i + 2] = t4.z; x[4 * i + 3] = t4.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(dd[i], x[i + j], acc[j]);
             }
         }
     }
+    if (task < ntask) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int o = threadIdx.x + i * blockDim.x;
-        if (o < nout) part[(size_t)blockIdx.x * nout + o] = acc[i];
+        for (int j = 0; j < 8; ++j)
+            if (k0 + j < KS) part[(size_t)blockIdx.x * (F * 2 * KS) + (f * 2 + c) * KS + k0 + j] = acc[j];
     }
 }
 
@@ -193,14 +236,17 @@ inline int bwd_post_common(const Dims &d, const gvx_weights *w, const float *mem
         GVX_LAUNCHED(1);
         k_reduce_partials<<<grid_for((size_t)d.D), 256, 0, st>>>(p.PART1, nblk, stride, d.D * d.F, d.D, g->v_w);
         GVX_LAUNCHED(1);
-        const size_t smem = ((size_t)2 * (N + d.KS - 1) + (size_t)N * (d.F + 1)) * sizeof(float);
+        const int KB = (d.KS + 7) / 8, NCS = (N + 7) & ~7, NPS = NCS + 8 * KB + 8;
+        const int cthreads = (d.F * 2 * KB + 31) & ~31;
+        GVX_CHECK(cthreads <= 1024, "location conv too large for the conv-gradient kernel");
+        const size_t smem = ((size_t)2 * NPS + (size_t)d.F * NCS) * sizeof(float);
         GVX_CHECK(smem <= 200 * 1024, "token count too large for the conv-gradient kernel");
         static size_t configured = 0;
         if (smem > configured) {
             GVX_CUDA(cudaFuncSetAttribute(k_attn_post_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = smem;
         }
-        k_attn_post_conv<<<nblk, 512, smem, st>>>(p.DCONV, p.ALIGN, p.CUMS, T, B, N, d.F, d.KS, p.PART2);
+        k_attn_post_conv<<<nblk, cthreads < 64 ? 64 : cthreads, smem, st>>>(p.DCONV, p.ALIGN, p.CUMS, T, B, N, d.F, d.KS, p.PART2);
         GVX_LAUNCHED(1);
         GVX_CUDA(cudaGetLastError());
         k_reduce_partials<<<grid_for((size_t)d.F * 2 * d.KS), 256, 0, st>>>(p.PART2, nblk, d.F * 2 * d.KS, 0, d.F * 2 * d.KS,
@@ -319,7 +365,7 @@ extern "C" int gvx_dec_train_bwd(const gvx_dims *dd, const gvx_weights *w, const
             a.de_out = x + W.DE + (size_t)t * B * N;
             a.dq_out = x + W.DQ + (size_t)t * B * d.D;
             a.dconv_out = x + W.DCONV + (size_t)t * B * N * d.F;
-            GVX_TRY(launch_attention_bwd(a, st));
+            GVX_TRY(launch_attention_bwd_any(a, st));
         }
         // S4
         {

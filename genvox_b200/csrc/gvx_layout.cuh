@@ -70,7 +70,7 @@ struct BwdL {
     BwdL(const Dims &d, int B, int N, int T) {
         Carver c;
         const size_t TB = (size_t)T * B;
-        post_blocks = 148 * 4;
+        post_blocks = 148 * 8;
         DOUT = c.take(TB * d.OL);            // [T][B][OL]   d(mel|gate) time-major
         DHC = c.take(TB * d.Kp);             // [T][B][H+E]  DOUT . Wpg
         DGD = c.take(TB * 4 * d.H);          // d(pre-activations) decoder LSTM, packed gate order
