@@ -367,7 +367,7 @@ int gvx_dec_infer(const gvx_dims *dd, const gvx_weights *w, const void *packed_,
         float *out_t = s + L.OUT + (size_t)t * B * d.OL;
         { ProfScope ps(PS_PROJ, st); GVX_TRY(run_projection(d, packed, s + L.HD + nxt * BH, d.H, s + L.CTX, d.E, B, out_t, st, true)); }
         if (!ignore_gate) {
-            k_gate_check<<<1, 128, 0, st>>>(out_t, B, d.M, d.OL, gate_threshold, t, n_frames, flags);
+            GVX_CUDA(launch_pdl(k_gate_check, dim3(1), dim3(128), 0, st, (const float *)out_t, B, d.M, d.OL, gate_threshold, t, n_frames, flags));
     GVX_LAUNCHED(1);
             GVX_CUDA(cudaGetLastError());
             if ((t + 1) % GVX_STOP_POLL == 0 || t + 1 == max_steps) {

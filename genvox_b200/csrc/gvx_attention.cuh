@@ -95,6 +95,8 @@ __device__ __forceinline__ void attn_conv(const AttnShape &s, const AttnSmem &L,
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_fwd(const AttnFwdArgs a) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) float sm[];
     const AttnShape s = a.s;
     const AttnSmem L(s);
@@ -196,7 +198,7 @@ inline int launch_attention_fwd(const AttnFwdArgs &a, cudaStream_t stream) {
         GVX_CUDA(cudaFuncSetAttribute(k_attention_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         configured = bytes;
     }
-    k_attention_fwd<<<a.s.B, ATT_THREADS, bytes, stream>>>(a);
+    GVX_CUDA(launch_pdl(k_attention_fwd, dim3(a.s.B), dim3(ATT_THREADS), bytes, stream, a));
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     return 0;
@@ -248,6 +250,8 @@ struct AttnBwdArgs {
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_bwd(const AttnBwdArgs a) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) float sm[];
     const AttnShape s = a.s;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
@@ -379,7 +383,7 @@ inline int launch_attention_bwd(const AttnBwdArgs &a, cudaStream_t stream) {
         GVX_CUDA(cudaFuncSetAttribute(k_attention_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         configured = bytes;
     }
-    k_attention_bwd<<<a.s.B, ATT_THREADS, bytes, stream>>>(a);
+    GVX_CUDA(launch_pdl(k_attention_bwd, dim3(a.s.B), dim3(ATT_THREADS), bytes, stream, a));
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     return 0;

@@ -57,20 +57,21 @@ __global__ void __launch_bounds__(AF_THREADS, 1) k_attention_fwd_fast(const Attn
     const int len = a.lengths ? (int)a.lengths[b] : N;
     float *wprev_row = a.w_prev + (size_t)b * N, *cum_row = a.cum + (size_t)b * N;
 
-    // ---- stage inputs: (w_{t-1}, cum_{t-1}) with zero halo, small weights, q
+    // ---- stage the small weights while the previous kernel of the chain is still running (PDL) ...
+    pdl_trigger();
+    for (int i = tid; i < AF_F * 2 * AF_KS; i += AF_THREADS) sm[L.wlc + i] = a.wlc[i];
+    for (int i = tid; i < AF_F * AF_D / 4; i += AF_THREADS)
+        reinterpret_cast<float4 *>(sm + L.wldT)[i] = reinterpret_cast<const float4 *>(a.wldT)[i];
+    if (tid < AF_D) sm[L.v + tid] = a.v[tid];
+    pdl_wait();
+    // ---- ... then what it produced: (w_{t-1}, cum_{t-1}) with zero halo, q
     for (int i = tid; i < 2 * L.NPS; i += AF_THREADS) {
         const int c = i / L.NPS, n = i - c * L.NPS - AF_PAD;
         float x = 0.f;
         if (n >= 0 && n < N) x = c == 0 ? wprev_row[n] : cum_row[n];
         sm[L.wcat + i] = x;
     }
-    for (int i = tid; i < AF_F * 2 * AF_KS; i += AF_THREADS) sm[L.wlc + i] = a.wlc[i];
-    for (int i = tid; i < AF_F * AF_D / 4; i += AF_THREADS)
-        reinterpret_cast<float4 *>(sm + L.wldT)[i] = reinterpret_cast<const float4 *>(a.wldT)[i];
-    if (tid < AF_D) {
-        sm[L.v + tid] = a.v[tid];
-        sm[L.q + tid] = src_get(a.q, b, tid);
-    }
+    if (tid < AF_D) sm[L.q + tid] = src_get(a.q, b, tid);
     __syncthreads();
 
     // ---- location conv: task = (filter f, block of 8 tokens); sliding window in registers
@@ -242,6 +243,15 @@ __global__ void __launch_bounds__(AF_THREADS, 1) k_attention_bwd_fast(const Attn
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int len = a.lengths ? (int)a.lengths[b] : N;
 
+    pdl_trigger();                                             // weights first (PDL prologue), then dependent data
+    if (tid < AF_D) sm[L.v + tid] = a.v[tid];
+    for (int i = tid; i < AF_D * AF_F; i += AF_THREADS) {      // wld [D, F] -> [D/4][F][4]
+        const int d = i >> 5, f = i & 31;
+        sm[L.wld4 + ((d >> 2) * AF_F + f) * 4 + (d & 3)] = a.wld[i];
+    }
+    for (int i = tid; i < AF_F * 2 * AF_KS; i += AF_THREADS) sm[L.wlc + i] = a.wlc[i];
+    for (int i = tid; i < AF_F * L.NDS; i += AF_THREADS) sm[L.dconvT + i] = 0.f;
+    pdl_wait();
     for (int e = tid; e < E; e += AF_THREADS) {
         float x = src_get(a.dctx1, b, e);
         if (a.dctx2.nsplit) x += src_get(a.dctx2, b, e);
@@ -250,13 +260,6 @@ __global__ void __launch_bounds__(AF_THREADS, 1) k_attention_bwd_fast(const Attn
         a.dctx_out[(size_t)b * E + e] = x;
     }
     for (int n = tid; n < L.NCS; n += AF_THREADS) sm[L.w + n] = n < N ? a.w_t[(size_t)b * a.w_bstride + n] : 0.f;
-    if (tid < AF_D) sm[L.v + tid] = a.v[tid];
-    for (int i = tid; i < AF_D * AF_F; i += AF_THREADS) {      // wld [D, F] -> [D/4][F][4]
-        const int d = i >> 5, f = i & 31;
-        sm[L.wld4 + ((d >> 2) * AF_F + f) * 4 + (d & 3)] = a.wld[i];
-    }
-    for (int i = tid; i < AF_F * 2 * AF_KS; i += AF_THREADS) sm[L.wlc + i] = a.wlc[i];
-    for (int i = tid; i < AF_F * L.NDS; i += AF_THREADS) sm[L.dconvT + i] = 0.f;
     __syncthreads();
 
     // ---- d w[n] = <d ctx, memory[n]> + carried terms
@@ -411,7 +414,7 @@ inline int launch_attention_fwd_any(const AttnFwdArgs &a, cudaStream_t stream) {
         GVX_CUDA(cudaFuncSetAttribute(k_attention_fwd_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         configured = bytes;
     }
-    k_attention_fwd_fast<<<a.s.B, AF_THREADS, bytes, stream>>>(a);
+    GVX_CUDA(launch_pdl(k_attention_fwd_fast, dim3(a.s.B), dim3(AF_THREADS), bytes, stream, a));
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     return 0;
@@ -426,7 +429,7 @@ inline int launch_attention_bwd_any(const AttnBwdArgs &a, cudaStream_t stream) {
         GVX_CUDA(cudaFuncSetAttribute(k_attention_bwd_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         configured = bytes;
     }
-    k_attention_bwd_fast<<<a.s.B, AF_THREADS, bytes, stream>>>(a);
+    GVX_CUDA(launch_pdl(k_attention_bwd_fast, dim3(a.s.B), dim3(AF_THREADS), bytes, stream, a));
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     return 0;

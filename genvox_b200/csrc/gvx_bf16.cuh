@@ -32,6 +32,8 @@ struct BfLstmFwd {
     int row_offset, B, HID;
 };
 __global__ void __launch_bounds__(256) k_bf_lstm_fwd(const BfLstmFwd a) {
+    pdl_trigger();
+    pdl_wait();
     const int noct = a.HID >> 3;
     const int total = a.B * noct;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -91,6 +93,8 @@ struct BfLstmBwd {
     int P;
 };
 __global__ void __launch_bounds__(256) k_bf_lstm_bwd(const BfLstmBwd a) {
+    pdl_trigger();
+    pdl_wait();
     if ((int)blockIdx.x >= a.main_blocks) {
         const int total = a.B * a.P;
         for (int idx = (blockIdx.x - a.main_blocks) * blockDim.x + threadIdx.x; idx < total;
@@ -127,6 +131,8 @@ __global__ void __launch_bounds__(256) k_bf_lstm_bwd(const BfLstmBwd a) {
 // out[b, m] = sum_s P[s][b][m] + bias[m]   (inference projection epilogue)
 __global__ void k_bf_finalize(const float *__restrict__ P, int KS, int B, int ldp, int M, const float *__restrict__ bias,
                               float *__restrict__ out, int ldo) {
+    pdl_trigger();
+    pdl_wait();
     const int total = B * M;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int b = i / M, m = i - b * M;

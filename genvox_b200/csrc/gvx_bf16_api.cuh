@@ -202,7 +202,7 @@ inline int run_bf_lstm_fwd(const Dims &d, const float *packed, int which, const 
     a.drop = make_drop(seed, which == 0 ? d.p_att : d.p_dec, training);
     a.site = which == 0 ? SITE_ATT : SITE_DEC;
     a.t = (uint32_t)t; a.row_offset = row_offset; a.B = B; a.HID = which == 0 ? d.A : d.H;
-    k_bf_lstm_fwd<<<grid_for((size_t)B * a.HID / 8), 256, 0, st>>>(a);
+    GVX_CUDA(launch_pdl(k_bf_lstm_fwd, dim3(grid_for((size_t)B * a.HID / 8)), dim3(256), 0, st, a));
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     return 0;
@@ -367,7 +367,7 @@ inline int run_bf_lstm_bwd(const Dims &d, int which, const SrcSum &s0, const Src
         a.dpre_src = *dpre_src; a.pre2 = pre2; a.dz2 = dz2; a.P = d.P;
         extra = grid_for((size_t)B * d.P);
     }
-    k_bf_lstm_bwd<<<a.main_blocks + extra, 256, 0, st>>>(a);
+    GVX_CUDA(launch_pdl(k_bf_lstm_bwd, dim3(a.main_blocks + extra), dim3(256), 0, st, a));
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     return 0;
@@ -603,13 +603,13 @@ int infer_bf16(const Dims &d, const gvx_weights *w, const float *packed, const f
         {
             ProfScope ps(PS_PROJ, st);
             GVX_TRY(run_tc(WpgI, XPI, s + L.PP, g.Tp, g.Kpp, L.KSp, B, err, st));
-            k_bf_finalize<<<grid_for((size_t)B * (d.M + 1)), 256, 0, st>>>(s + L.PP, L.KSp, B, g.Tp * TC_M, d.M + 1, packed + PL.bpg,
-                                                                          out_t, d.OL);
+            GVX_CUDA(launch_pdl(k_bf_finalize, dim3(grid_for((size_t)B * (d.M + 1))), dim3(256), 0, st, (const float *)(s + L.PP), L.KSp,
+                                B, g.Tp * TC_M, d.M + 1, (const float *)(packed + PL.bpg), out_t, d.OL));
             GVX_LAUNCHED(1);
             GVX_CUDA(cudaGetLastError());
         }
         if (!ignore_gate) {
-            k_gate_check<<<1, 128, 0, st>>>(out_t, B, d.M, d.OL, gate_threshold, t, n_frames, flags);
+            GVX_CUDA(launch_pdl(k_gate_check, dim3(1), dim3(128), 0, st, (const float *)out_t, B, d.M, d.OL, gate_threshold, t, n_frames, flags));
             GVX_LAUNCHED(1);
             GVX_CUDA(cudaGetLastError());
             if ((t + 1) % GVX_STOP_POLL == 0 || t + 1 == max_steps) {

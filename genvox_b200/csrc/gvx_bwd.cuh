@@ -33,6 +33,8 @@ __global__ void k_lstm_bwd_pointwise(const float *__restrict__ dh1, int ld1, con
                                      const float *__restrict__ gates, const float *__restrict__ c_prev,
                                      const float *__restrict__ c_new, float *__restrict__ dc, float *__restrict__ dgates,
                                      int B, int HID) {
+    pdl_trigger();
+    pdl_wait();
     const int total = B * HID;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int b = i / HID, u = i - b * HID;
@@ -329,10 +331,10 @@ extern "C" int gvx_dec_train_bwd(const gvx_dims *dd, const gvx_weights *w, const
         // S1
         {
         ProfScope ps(PS_BWD_DEC_POINT, st);
-        k_lstm_bwd_pointwise<<<grid_for(BH), 256, 0, st>>>(
+        GVX_CUDA(launch_pdl(k_lstm_bwd_pointwise, dim3(grid_for(BH)), dim3(256), 0, st,
             x + W.DHC + (size_t)t * B * d.Kp, d.Kp, last ? nullptr : dxd_next + d.A + d.E, d.Kd, drop_dec, SITE_DEC,
             (uint32_t)t, row_offset, s + S.GD + (size_t)t * 4 * BH, s + S.CD + t * BH, s + S.CD + (t + 1) * BH, x + W.DCD,
-            x + W.DGD + (size_t)t * 4 * BH, B, d.H);
+            x + W.DGD + (size_t)t * 4 * BH, B, d.H));
         GVX_LAUNCHED(1);
         }
         GVX_CUDA(cudaGetLastError());

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -96,6 +97,39 @@ struct ProfScope {
         if (active) { cudaEventRecord(r.b, st); g_prof.recs.push_back(r); }
     }
 };
+
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of the per-step chain is launched with cudaLaunchAttributeProgrammaticStreamSerialization:
+// it signals `launch_dependents` at once, so the next kernel's CTAs become resident early and run their
+// prologue (barrier init, TMEM allocation, weight prefetch — nothing the previous kernel writes), then block
+// in `griddepcontrol.wait` until the previous grid has completed and flushed.  GVX_NO_PDL=1 disables it.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("GVX_NO_PDL");
+        on = (e && e[0] == '1') ? 0 : 1;
+    }
+    return on == 1;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 // ---------------------------------------------------------------- Philox4x32-10
 enum : uint32_t { SITE_PRENET0 = 0, SITE_PRENET1 = 1, SITE_ATT = 2, SITE_DEC = 3 };

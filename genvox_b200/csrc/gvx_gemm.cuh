@@ -192,6 +192,8 @@ struct EpiLstmBwd {
 // ------------------------------------------------------------------ kernel
 template <int BT, int R, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm(const GemmIn g, const Epi epi) {
+    pdl_trigger();
+    pdl_wait();
     using C = GemmCfg<BT, R>;
     constexpr int TB = C::TB, RJ = C::RJ, SS = GEMM_SS, KC = GEMM_KC;
     extern __shared__ __align__(16) float smem[];
@@ -304,7 +306,7 @@ inline int launch_gemm_t(const GemmIn &g, const Epi &epi, cudaStream_t stream) {
         configured = true;
     }
     dim3 grid((g.Rtot + R - 1) / R, (g.M + BT - 1) / BT);
-    k_gemm<BT, R, Epi><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(g, epi);
+    GVX_CUDA(launch_pdl(k_gemm<BT, R, Epi>, grid, dim3(GEMM_THREADS), C::SMEM_BYTES, stream, g, epi));
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     return 0;

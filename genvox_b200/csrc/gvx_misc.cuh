@@ -99,6 +99,8 @@ __global__ void k_pack_dout(const float *__restrict__ d_mel, const float *__rest
 // flags[0] = number of rows still running after this step.  One block.
 __global__ void k_gate_check(const float *__restrict__ out_t, int B, int M, int OL, float thr, int t,
                              int32_t *__restrict__ n_frames, int *__restrict__ flags) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ int running;
     if (threadIdx.x == 0) running = 0;
     __syncthreads();

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(const TcGemmArgs a) {
     uint64_t *tmem_full = empty + TC_STAGES;
     uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
 
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x, ks = blockIdx.y;
     const int nkb_all = a.Kpad / TC_KB;
@@ -176,10 +177,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(const TcGemmArgs a) {
         if (elect_one()) {
             const uint8_t *wsrc = (const uint8_t *)a.Wimg + ((size_t)tile * nkb_all + kb0) * C::WB;
             const uint8_t *xsrc = (const uint8_t *)a.Ximg + (size_t)kb0 * C::XB;
-            for (int i = 0; i < nkb; ++i) {
+            // PDL prologue: the weight images do not depend on the previous kernel of the chain, so the first
+            // ring of stages is filled with weights before griddepcontrol.wait; activations follow after it.
+            const int npre = nkb < TC_STAGES ? nkb : TC_STAGES;
+            for (int i = 0; i < npre; ++i) {
+                mbar_expect_tx(full + i, (uint32_t)C::SB);
+                tma_bulk_g2s(smem + (size_t)i * C::SB, wsrc + (size_t)i * C::WB, (uint32_t)C::WB, full + i);
+            }
+            pdl_wait();
+            for (int i = 0; i < npre; ++i)
+                tma_bulk_g2s(smem + (size_t)i * C::SB + C::WB, xsrc + (size_t)i * C::XB, (uint32_t)C::XB, full + i);
+            for (int i = npre; i < nkb; ++i) {
                 const int s = i % TC_STAGES;
                 const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
-                if (i >= TC_STAGES && !mbar_wait(empty + s, ph ^ 1u, a.err, 1)) break;
+                if (!mbar_wait(empty + s, ph ^ 1u, a.err, 1)) break;
                 mbar_expect_tx(full + s, (uint32_t)C::SB);
                 tma_bulk_g2s(smem + (size_t)s * C::SB, wsrc + (size_t)i * C::WB, (uint32_t)C::WB, full + s);
                 tma_bulk_g2s(smem + (size_t)s * C::SB + C::WB, xsrc + (size_t)i * C::XB, (uint32_t)C::XB, full + s);
@@ -243,7 +254,7 @@ inline int launch_tc_gemm_t(const TcGemmArgs &a, int Mtiles, cudaStream_t st) {
         configured = true;
     }
     dim3 grid(Mtiles, a.KS);
-    k_tc_gemm<NPAD><<<grid, TC_THREADS, C::SMEM, st>>>(a);
+    GVX_CUDA(launch_pdl(k_tc_gemm<NPAD>, grid, dim3(TC_THREADS), C::SMEM, st, a));
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     return 0;
