@@ -2,7 +2,7 @@
 // and the single-phase hooks used by the parity tests.  See include/genvox_b200.h for the
 // contract and the reference file:line each entry point replaces.
 #include "../../include/genvox_b200.h"
-#include "gvx_attention_fast.cuh"
+#include "gvx_attention_c2.cuh"
 #include "gvx_common.cuh"
 #include "gvx_gemm.cuh"
 #include "gvx_layout.cuh"
@@ -137,7 +137,7 @@ int run_attention(const Dims &d, const gvx_weights *w, const float *packed, cons
     a.align_out = align_out; a.align_bstride = align_bstride; a.cum_stash = cum_stash;
     a.ctx_out = ctx_out; a.ctx_ld = d.E;
     a.th_stash = th_stash; a.conv_stash = conv_stash;
-    return launch_attention_fwd_any(a, st);
+    return launch_attention_fwd_best(a, st);
 }
 
 // [mel | gate] = [h_dec, ctx] . Wpg^T + bpg   (tacotron2.py:360-362) over `rows` rows

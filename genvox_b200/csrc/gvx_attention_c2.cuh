@@ -1,0 +1,496 @@
+// genvox_b200 — attention step split over a 2-CTA thread-block cluster per batch row.
+//
+// With B = 64 rows one CTA per row leaves 84 of the 148 SMs idle and the kernel is latency-bound (ncu:
+// issue slots 30 % busy, long-scoreboard and barrier stalls dominate).  Here the two CTAs of a cluster
+// split the tokens of a row in halves and exchange, through distributed shared memory, only
+//   forward : the softmax max and sum (2 floats) and the partial context (E floats),
+//   backward: <w, dw> (1 float), the partial d q (D floats) and a 15-token halo of d conv.
+// Maths and I/O contract are those of k_attention_fwd_fast / k_attention_bwd_fast (gvx_attention_fast.cuh);
+// reference: tacotron2.py:48-53, :89-129, :344-353.  Reductions across the pair are always rank 0 + rank 1, so
+// both CTAs hold bit-identical values and results do not depend on scheduling.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "gvx_attention_fast.cuh"
+
+namespace gvx {
+
+namespace cg = cooperative_groups;
+
+struct AttnC2Geom {
+    int NH;        // tokens per CTA (multiple of 8)
+    int nblk;      // NH / 8
+    int NPS;       // local wcat row length
+    int NDS;       // local d conv row length (backward)
+    __host__ __device__ explicit AttnC2Geom(int N) {
+        NH = (((N + 1) / 2) + 7) & ~7;
+        nblk = NH / 8;
+        NPS = NH + 40;
+        NDS = NH + 40;
+    }
+};
+
+struct AttnC2FwdSmem {
+    int wcat, convT, wldT, wlc, v, q, e, w, part, ctxp, xch, scratch, total;
+    __host__ __device__ AttnC2FwdSmem(int N, int E) {
+        const AttnC2Geom g(N);
+        int o = 0;
+        auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+        wcat = take(2 * g.NPS);
+        convT = take(AF_F * g.NH);
+        wldT = take(AF_F * AF_D);
+        wlc = take(AF_F * 2 * AF_KS);
+        v = take(AF_D);
+        q = take(AF_D);
+        e = take(g.NH);
+        w = take(g.NH);
+        part = take(4 * E);
+        ctxp = take(E);        // this CTA's partial context, read by the peer
+        xch = take(8);         // [0] local max, [1] local sum
+        scratch = take(64);
+        total = o;
+    }
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_attention_fwd_c2(const AttnFwdArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int N = a.s.N, E = a.s.E;
+    const AttnC2Geom G(N);
+    const AttnC2FwdSmem L(N, E);
+    const int rank = (int)cluster.block_rank(), peer = rank ^ 1;
+    const int b = blockIdx.x >> 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int len = a.lengths ? (int)a.lengths[b] : N;
+    const int n_lo = rank * G.NH;
+    const int n_own = max(0, min(N, n_lo + G.NH) - n_lo);      // valid own tokens: local index [0, n_own)
+    float *wprev_row = a.w_prev + (size_t)b * N, *cum_row = a.cum + (size_t)b * N;
+
+    pdl_trigger();
+    for (int i = tid; i < AF_F * 2 * AF_KS; i += AF_THREADS) sm[L.wlc + i] = a.wlc[i];
+    for (int i = tid; i < AF_F * AF_D / 4; i += AF_THREADS)
+        reinterpret_cast<float4 *>(sm + L.wldT)[i] = reinterpret_cast<const float4 *>(a.wldT)[i];
+    if (tid < AF_D) sm[L.v + tid] = a.v[tid];
+    pdl_wait();
+    // local window of (w_{t-1}, cum_{t-1}): index i <-> token n_lo + i - 15, zero outside [0, N)
+    for (int i = tid; i < 2 * G.NPS; i += AF_THREADS) {
+        const int c = i / G.NPS, n = n_lo + (i - c * G.NPS) - AF_PAD;
+        float x = 0.f;
+        if (n >= 0 && n < N) x = c == 0 ? wprev_row[n] : cum_row[n];
+        sm[L.wcat + i] = x;
+    }
+    if (tid < AF_D) sm[L.q + tid] = src_get(a.q, b, tid);
+    __syncthreads();
+
+    // ---- location conv for the own tokens
+    for (int task = tid; task < AF_F * G.nblk; task += AF_THREADS) {
+        const int f = task / G.nblk, n0 = (task - f * G.nblk) * 8;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            float x[40];
+            const float4 *xr = reinterpret_cast<const float4 *>(sm + L.wcat + c * G.NPS + n0);
+#pragma unroll
+            for (int i = 0; i < 10; ++i) {
+                const float4 t4 = xr[i];
+                x[4 * i] = t4.x; x[4 * i + 1] = t4.y; x[4 * i + 2] = t4.z; x[4 * i + 3] = t4.w;
+            }
+            const float *wr = sm + L.wlc + (f * 2 + c) * AF_KS;
+#pragma unroll
+            for (int k = 0; k < AF_KS; ++k) {
+                const float wk = wr[k];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(wk, x[j + k], acc[j]);
+            }
+        }
+        float4 *dst = reinterpret_cast<float4 *>(sm + L.convT + f * G.NH + n0);
+        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    __syncthreads();
+    if (a.conv_stash) {
+        float *cs = a.conv_stash + ((size_t)b * N + n_lo) * AF_F;
+        for (int i = tid; i < n_own * AF_F; i += AF_THREADS) {
+            const int n = i >> 5, f = i & 31;
+            cs[i] = sm[L.convT + f * G.NH + n];
+        }
+    }
+
+    // ---- energies of the own tokens (4 tokens per warp pass, 4 attention dims per lane)
+    {
+        const float4 q4 = *reinterpret_cast<const float4 *>(sm + L.q + lane * 4);
+        const float4 v4 = *reinterpret_cast<const float4 *>(sm + L.v + lane * 4);
+        const float *pm_b = a.pm + ((size_t)b * N + n_lo) * AF_D;
+        const int ngrp = (n_own + 3) / 4;
+        for (int grp = wid; grp < ngrp; grp += AF_WARPS) {
+            const int n0 = grp * 4;
+            float4 p[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)        // issue the processed-memory loads before the dense layer hides them
+                p[j] = n0 + j < n_own ? *reinterpret_cast<const float4 *>(pm_b + (size_t)(n0 + j) * AF_D + lane * 4)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            float acc[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+#pragma unroll 8
+            for (int f = 0; f < AF_F; ++f) {
+                const float4 wd = *reinterpret_cast<const float4 *>(sm + L.wldT + f * AF_D + lane * 4);
+                const float4 c4 = *reinterpret_cast<const float4 *>(sm + L.convT + f * G.NH + n0);
+                const float cj[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[j][0] = fmaf(cj[j], wd.x, acc[j][0]);
+                    acc[j][1] = fmaf(cj[j], wd.y, acc[j][1]);
+                    acc[j][2] = fmaf(cj[j], wd.z, acc[j][2]);
+                    acc[j][3] = fmaf(cj[j], wd.w, acc[j][3]);
+                }
+            }
+            float part[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                part[j] = 0.f;
+                if (n0 + j < n_own) {
+                    float4 th;
+                    th.x = tanh_fast((q4.x + acc[j][0]) + p[j].x);
+                    th.y = tanh_fast((q4.y + acc[j][1]) + p[j].y);
+                    th.z = tanh_fast((q4.z + acc[j][2]) + p[j].z);
+                    th.w = tanh_fast((q4.w + acc[j][3]) + p[j].w);
+                    if (a.th_stash)
+                        *reinterpret_cast<float4 *>(a.th_stash + ((size_t)b * N + n_lo + n0 + j) * AF_D + lane * 4) = th;
+                    part[j] = fmaf(v4.x, th.x, fmaf(v4.y, th.y, fmaf(v4.z, th.z, v4.w * th.w)));
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) part[j] += __shfl_xor_sync(0xffffffffu, part[j], o);
+            }
+            if (lane < 4) {
+                const int nl = n0 + lane;
+                const float pv = lane == 0 ? part[0] : (lane == 1 ? part[1] : (lane == 2 ? part[2] : part[3]));
+                if (nl < n_own) sm[L.e + nl] = (n_lo + nl) < len ? pv : -INFINITY;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- masked softmax over ALL tokens of the row: exchange max, then sum, with the peer CTA
+    float mx = -INFINITY;
+    for (int n = tid; n < n_own; n += AF_THREADS) mx = fmaxf(mx, sm[L.e + n]);
+    mx = block_max(mx, sm + L.scratch);
+    if (tid == 0) sm[L.xch + 0] = mx;
+    cluster.sync();
+    const float *peer_sm = cluster.map_shared_rank(sm, peer);
+    mx = fmaxf(mx, peer_sm[L.xch + 0]);
+    float sum = 0.f;
+    for (int n = tid; n < n_own; n += AF_THREADS) {
+        const float pexp = expf(sm[L.e + n] - mx);
+        sm[L.w + n] = pexp;
+        sum += pexp;
+    }
+    sum = block_sum(sum, sm + L.scratch);
+    if (tid == 0) sm[L.xch + 1] = sum;
+    cluster.sync();
+    {
+        const float other = peer_sm[L.xch + 1];
+        sum = rank == 0 ? sum + other : other + sum;       // always rank 0 + rank 1
+    }
+    for (int n = tid; n < n_own; n += AF_THREADS) {
+        const float w = sm[L.w + n] / sum;
+        sm[L.w + n] = w;
+        const int ng = n_lo + n;
+        const float c_old = cum_row[ng];
+        a.align_out[(size_t)b * a.align_bstride + ng] = w;
+        if (a.cum_stash) a.cum_stash[(size_t)b * a.align_bstride + ng] = c_old;
+        wprev_row[ng] = w;
+        cum_row[ng] = c_old + w;
+    }
+    __syncthreads();
+
+    // ---- partial context over the own tokens, then each CTA finalises half of the E columns
+    {
+        const float *mem_b = a.memory + ((size_t)b * N + n_lo) * E;
+        const int own_len = max(0, min(len, n_lo + n_own) - n_lo);
+        const int tg = tid >> 7, te = tid & 127;
+        for (int e4 = te * 4; e4 < E; e4 += 512) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int n = tg; n < own_len; n += 4) {
+                const float w = sm[L.w + n];
+                const float4 m = *reinterpret_cast<const float4 *>(mem_b + (size_t)n * E + e4);
+                acc.x = fmaf(w, m.x, acc.x); acc.y = fmaf(w, m.y, acc.y); acc.z = fmaf(w, m.z, acc.z); acc.w = fmaf(w, m.w, acc.w);
+            }
+            *reinterpret_cast<float4 *>(sm + L.part + tg * E + e4) = acc;
+        }
+        __syncthreads();
+        for (int e = tid; e < E; e += AF_THREADS)
+            sm[L.ctxp + e] = (sm[L.part + e] + sm[L.part + E + e]) + (sm[L.part + 2 * E + e] + sm[L.part + 3 * E + e]);
+        cluster.sync();
+        const int eh = E / 2;
+        for (int e = rank * eh + tid; e < (rank + 1) * eh; e += AF_THREADS) {
+            const float mine = sm[L.ctxp + e], other = peer_sm[L.ctxp + e];
+            const float cx = rank == 0 ? mine + other : other + mine;
+            if (a.ctx_out) a.ctx_out[(size_t)b * a.ctx_ld + e] = cx;
+            if (a.ctx_bf.n) bf_store1(a.ctx_bf, b, e, cx);
+        }
+    }
+    cluster.sync();      // the peer may still be reading this CTA's shared memory
+}
+
+// ------------------------------------------------------------------------------------ backward
+struct AttnC2BwdSmem {
+    int dctx, w, de, v, wld4, wlc, dsb, dconvT, dq, dqp, part, xch, scratch, total;
+    __host__ __device__ AttnC2BwdSmem(int N, int E) {
+        const AttnC2Geom g(N);
+        int o = 0;
+        auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+        dctx = take(E);
+        w = take(g.NH);
+        de = take(g.NH);
+        v = take(AF_D);
+        wld4 = take(AF_D * AF_F);
+        wlc = take(AF_F * 2 * AF_KS);
+        dsb = take(AF_WARPS * 4 * AF_D);
+        dconvT = take(AF_F * g.NDS);
+        dq = take(AF_WARPS * AF_D);
+        dqp = take(AF_D);       // this CTA's partial d q, read by rank 0
+        part = take(8 * 2 * g.NH);
+        xch = take(8);
+        scratch = take(64);
+        total = o;
+    }
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_attention_bwd_c2(const AttnBwdArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int N = a.s.N, E = a.s.E;
+    const AttnC2Geom G(N);
+    const AttnC2BwdSmem L(N, E);
+    const int rank = (int)cluster.block_rank(), peer = rank ^ 1;
+    const int b = blockIdx.x >> 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int len = a.lengths ? (int)a.lengths[b] : N;
+    const int n_lo = rank * G.NH;
+    const int n_own = max(0, min(N, n_lo + G.NH) - n_lo);
+    const int own_len = max(0, min(len, n_lo + n_own) - n_lo);     // unmasked own tokens
+
+    pdl_trigger();
+    if (tid < AF_D) sm[L.v + tid] = a.v[tid];
+    for (int i = tid; i < AF_D * AF_F; i += AF_THREADS) {
+        const int d = i >> 5, f = i & 31;
+        sm[L.wld4 + ((d >> 2) * AF_F + f) * 4 + (d & 3)] = a.wld[i];
+    }
+    for (int i = tid; i < AF_F * 2 * AF_KS; i += AF_THREADS) sm[L.wlc + i] = a.wlc[i];
+    for (int i = tid; i < AF_F * G.NDS; i += AF_THREADS) sm[L.dconvT + i] = 0.f;
+    pdl_wait();
+    for (int e = tid; e < E; e += AF_THREADS) {
+        float x = src_get(a.dctx1, b, e);
+        if (a.dctx2.nsplit) x += src_get(a.dctx2, b, e);
+        if (a.dctx3.nsplit) x += src_get(a.dctx3, b, e);
+        sm[L.dctx + e] = x;
+        if (rank == 0) a.dctx_out[(size_t)b * E + e] = x;
+    }
+    for (int n = tid; n < G.NH; n += AF_THREADS) sm[L.w + n] = n < n_own ? a.w_t[(size_t)b * a.w_bstride + n_lo + n] : 0.f;
+    __syncthreads();
+
+    // ---- d w of the own tokens
+    {
+        const float *mem_b = a.memory + ((size_t)b * N + n_lo) * E;
+        for (int n = wid; n < G.NH; n += AF_WARPS) {
+            float dw = 0.f;
+            if (n < own_len) {
+                float part = 0.f;
+                for (int e = lane * 4; e < E; e += 128) {
+                    const float4 m = *reinterpret_cast<const float4 *>(mem_b + (size_t)n * E + e);
+                    const float4 g4 = *reinterpret_cast<const float4 *>(sm + L.dctx + e);
+                    part = fmaf(m.x, g4.x, part); part = fmaf(m.y, g4.y, part);
+                    part = fmaf(m.z, g4.z, part); part = fmaf(m.w, g4.w, part);
+                }
+                part = warp_sum(part);
+                const size_t gi = (size_t)b * N + n_lo + n;
+                dw = part + a.dw_carry[gi] + a.dcum_carry[gi];
+                if (a.d_align) dw += a.d_align[(size_t)b * a.da_bstride + n_lo + n];
+            }
+            if (lane == 0) sm[L.de + n] = dw;
+        }
+    }
+    __syncthreads();
+    // ---- softmax backward: <w, dw> over the whole row = rank 0 part + rank 1 part
+    const float *peer_sm = cluster.map_shared_rank(sm, peer);
+    {
+        float part = 0.f;
+        for (int n = tid; n < n_own; n += AF_THREADS) part = fmaf(sm[L.w + n], sm[L.de + n], part);
+        part = block_sum(part, sm + L.scratch);
+        if (tid == 0) sm[L.xch + 0] = part;
+        cluster.sync();
+        const float other = peer_sm[L.xch + 0];
+        const float dot = rank == 0 ? part + other : other + part;
+        for (int n = tid; n < G.NH; n += AF_THREADS) {
+            const float de = n < n_own ? sm[L.w + n] * (sm[L.de + n] - dot) : 0.f;
+            sm[L.de + n] = de;
+            if (n < n_own) a.de_out[(size_t)b * N + n_lo + n] = de;
+        }
+    }
+    __syncthreads();
+
+    // ---- d s, partial d q, d conv of the own tokens
+    {
+        const float4 v4 = *reinterpret_cast<const float4 *>(sm + L.v + lane * 4);
+        float4 dqa = make_float4(0.f, 0.f, 0.f, 0.f);
+        float *dsb = sm + L.dsb + wid * 4 * AF_D;
+        const int ngrp = G.NH / 4;
+        for (int grp = wid; grp < ngrp; grp += AF_WARPS) {
+            const int n0 = grp * 4;
+            if (n0 >= own_len) {
+                for (int j = 0; j < 4; ++j)
+                    if (n0 + j < n_own) a.dconv_out[((size_t)b * N + n_lo + n0 + j) * AF_F + lane] = 0.f;
+                continue;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + j;
+                float4 ds = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n < own_len) {
+                    const float de = sm[L.de + n];
+                    const float4 th = *reinterpret_cast<const float4 *>(a.th + ((size_t)b * N + n_lo + n) * AF_D + lane * 4);
+                    ds.x = de * v4.x * (1.f - th.x * th.x);
+                    ds.y = de * v4.y * (1.f - th.y * th.y);
+                    ds.z = de * v4.z * (1.f - th.z * th.z);
+                    ds.w = de * v4.w * (1.f - th.w * th.w);
+                    dqa.x += ds.x; dqa.y += ds.y; dqa.z += ds.z; dqa.w += ds.w;
+                }
+                *reinterpret_cast<float4 *>(dsb + j * AF_D + lane * 4) = ds;
+            }
+            __syncwarp();
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+            for (int dq = 0; dq < AF_D / 4; ++dq) {
+                const float4 w4 = *reinterpret_cast<const float4 *>(sm + L.wld4 + (dq * AF_F + lane) * 4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 x = *reinterpret_cast<const float4 *>(dsb + j * AF_D + dq * 4);
+                    acc[j] = fmaf(x.x, w4.x, fmaf(x.y, w4.y, fmaf(x.z, w4.z, fmaf(x.w, w4.w, acc[j]))));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + j;
+                if (n < n_own) {
+                    sm[L.dconvT + lane * G.NDS + n + AF_PAD] = acc[j];       // local index = local token + 15
+                    a.dconv_out[((size_t)b * N + n_lo + n) * AF_F + lane] = acc[j];
+                }
+            }
+            __syncwarp();
+        }
+        *reinterpret_cast<float4 *>(sm + L.dq + wid * AF_D + lane * 4) = dqa;
+    }
+    __syncthreads();
+    if (tid < AF_D) {
+        float q = 0.f;
+#pragma unroll
+        for (int w = 0; w < AF_WARPS; ++w) q += sm[L.dq + w * AF_D + tid];
+        sm[L.dqp + tid] = q;
+    }
+    cluster.sync();          // both CTAs' d conv rows and partial d q are complete
+    if (rank == 0 && tid < AF_D) {
+        const float q = sm[L.dqp + tid] + peer_sm[L.dqp + tid];
+        if (a.dq_out) a.dq_out[(size_t)b * AF_D + tid] = q;
+        if (a.dq_bf.n) bf_store1(a.dq_bf, b, tid, q);
+    }
+    // ---- 15-token halo of d conv from the peer: rank 0 needs the peer's first tokens, rank 1 the peer's last
+    for (int i = tid; i < AF_F * AF_PAD; i += AF_THREADS) {
+        const int f = i / AF_PAD, h = i - f * AF_PAD;
+        if (rank == 0) sm[L.dconvT + f * G.NDS + G.NH + AF_PAD + h] = peer_sm[L.dconvT + f * G.NDS + AF_PAD + h];
+        else sm[L.dconvT + f * G.NDS + h] = peer_sm[L.dconvT + f * G.NDS + G.NH + h];
+    }
+    __syncthreads();
+
+    // ---- d wcat of the own tokens
+    {
+        const int ntask = 2 * G.nblk * 8;
+        for (int task = tid; task < ntask; task += AF_THREADS) {
+            const int fg = task & 7, rest = task >> 3;
+            const int c = rest / G.nblk, m0 = (rest - c * G.nblk) * 8;
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll 1
+            for (int ff = 0; ff < 4; ++ff) {
+                const int f = fg * 4 + ff;
+                float x[40];
+                const float4 *xr = reinterpret_cast<const float4 *>(sm + L.dconvT + f * G.NDS + m0);
+#pragma unroll
+                for (int i = 0; i < 10; ++i) {
+                    const float4 t4 = xr[i];
+                    x[4 * i] = t4.x; x[4 * i + 1] = t4.y; x[4 * i + 2] = t4.z; x[4 * i + 3] = t4.w;
+                }
+                const float *wr = sm + L.wlc + (f * 2 + c) * AF_KS;
+#pragma unroll
+                for (int k = 0; k < AF_KS; ++k) {
+                    const float wk = wr[k];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(wk, x[j - k + 30], acc[j]);
+                }
+            }
+            float4 *dst = reinterpret_cast<float4 *>(sm + L.part + (fg * 2 + c) * G.NH + m0);
+            dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 2 * n_own; idx += AF_THREADS) {
+        const int c = idx / n_own, m = idx - c * n_own;
+        float s = 0.f;
+#pragma unroll
+        for (int fg = 0; fg < 8; ++fg) s += sm[L.part + (fg * 2 + c) * G.NH + m];
+        const size_t gi = (size_t)b * N + n_lo + m;
+        if (c == 0) a.dw_carry[gi] = s;
+        else a.dcum_carry[gi] += s;
+    }
+    cluster.sync();
+}
+
+inline bool attention_c2_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("GVX_ATT_C2");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
+inline int launch_attention_fwd_best(const AttnFwdArgs &a, cudaStream_t stream) {
+    const AttnC2FwdSmem L(a.s.N, a.s.E);
+    const size_t bytes = (size_t)L.total * sizeof(float);
+    // the split pays when the rows alone cannot fill the machine
+    if (!attention_c2_enabled() || !attention_fast_ok(a.s) || a.s.B > 74 || a.s.N < 32 || a.s.E % 8 != 0 || bytes > 200 * 1024)
+        return launch_attention_fwd_any(a, stream);
+    static size_t configured = 0;
+    if (bytes > configured) {
+        GVX_CUDA(cudaFuncSetAttribute(k_attention_fwd_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured = bytes;
+    }
+    GVX_CUDA(launch_pdl(k_attention_fwd_c2, dim3(2 * a.s.B), dim3(AF_THREADS), bytes, stream, a));
+    GVX_LAUNCHED(1);
+    return 0;
+}
+
+inline int launch_attention_bwd_best(const AttnBwdArgs &a, cudaStream_t stream) {
+    const AttnC2BwdSmem L(a.s.N, a.s.E);
+    const size_t bytes = (size_t)L.total * sizeof(float);
+    if (!attention_c2_enabled() || !attention_fast_ok(a.s) || a.s.B > 74 || a.s.N < 32 || a.s.E % 8 != 0 || bytes > 200 * 1024)
+        return launch_attention_bwd_any(a, stream);
+    static size_t configured = 0;
+    if (bytes > configured) {
+        GVX_CUDA(cudaFuncSetAttribute(k_attention_bwd_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured = bytes;
+    }
+    GVX_CUDA(launch_pdl(k_attention_bwd_c2, dim3(2 * a.s.B), dim3(AF_THREADS), bytes, stream, a));
+    GVX_LAUNCHED(1);
+    return 0;
+}
+
+}  // namespace gvx

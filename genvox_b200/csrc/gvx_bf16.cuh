@@ -34,41 +34,26 @@ struct BfLstmFwd {
 __global__ void __launch_bounds__(256) k_bf_lstm_fwd(const BfLstmFwd a) {
     pdl_trigger();
     pdl_wait();
-    const int noct = a.HID >> 3;
-    const int total = a.B * noct;
+    // one thread per (row, hidden unit): B*HID threads keep every SM busy; a warp covers 32 consecutive units, so
+    // each partial read is one coalesced 128-byte line and the bf16 stores fill whole 16-byte image chunks
+    const int total = a.B * a.HID;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int b = idx / noct, u0 = (idx - b * noct) << 3;
-        const int colbase = (u0 >> 5) * 128 + (u0 & 31);
-        float pre[4][8];
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) pre[g][j] = 0.f;
+        const int b = idx / a.HID, u = idx - b * a.HID;
+        const int col = (u >> 5) * 128 + (u & 31);
+        float pre[4] = {0.f, 0.f, 0.f, 0.f};
         for (int s = 0; s < a.KS; ++s) {
-            const float *row = a.P + ((size_t)s * a.B + b) * a.ldp + colbase;
+            const float *row = a.P + ((size_t)s * a.B + b) * a.ldp + col;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const float4 x0 = *reinterpret_cast<const float4 *>(row + g * 32);
-                const float4 x1 = *reinterpret_cast<const float4 *>(row + g * 32 + 4);
-                pre[g][0] += x0.x; pre[g][1] += x0.y; pre[g][2] += x0.z; pre[g][3] += x0.w;
-                pre[g][4] += x1.x; pre[g][5] += x1.y; pre[g][6] += x1.z; pre[g][7] += x1.w;
-            }
+            for (int g = 0; g < 4; ++g) pre[g] += row[g * 32];
         }
-        float h[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int u = u0 + j;
-            const float4 bi = *reinterpret_cast<const float4 *>(a.bias + 4 * u);
-            const float gi = sigmoidf_(pre[0][j] + bi.x), gf = sigmoidf_(pre[1][j] + bi.y);
-            const float gg = tanhf(pre[2][j] + bi.z), go = sigmoidf_(pre[3][j] + bi.w);
-            const float cn = gf * a.c_prev[(size_t)b * a.HID + u] + gi * gg;
-            a.c_out[(size_t)b * a.HID + u] = cn;
-            h[j] = go * tanhf(cn) * drop_mult(a.drop, a.site, a.t, (uint32_t)(b + a.row_offset), (uint32_t)u);
-            if (a.gates_out) *reinterpret_cast<float4 *>(a.gates_out + (size_t)b * 4 * a.HID + 4 * u) = make_float4(gi, gf, gg, go);
-        }
-        uint4 v;
-        v.x = pack_bf2(h[0], h[1]); v.y = pack_bf2(h[2], h[3]); v.z = pack_bf2(h[4], h[5]); v.w = pack_bf2(h[6], h[7]);
-        bf_store8(a.h_dst, b, u0, v);
+        const float4 bi = *reinterpret_cast<const float4 *>(a.bias + 4 * u);
+        const float gi = sigmoidf_(pre[0] + bi.x), gf = sigmoidf_(pre[1] + bi.y);
+        const float gg = tanhf(pre[2] + bi.z), go = sigmoidf_(pre[3] + bi.w);
+        const float cn = gf * a.c_prev[idx] + gi * gg;
+        a.c_out[idx] = cn;
+        const float h = go * tanhf(cn) * drop_mult(a.drop, a.site, a.t, (uint32_t)(b + a.row_offset), (uint32_t)u);
+        if (a.gates_out) *reinterpret_cast<float4 *>(a.gates_out + (size_t)b * 4 * a.HID + 4 * u) = make_float4(gi, gf, gg, go);
+        bf_store1(a.h_dst, b, u, h);
     }
 }
 

@@ -5,7 +5,7 @@
 #pragma once
 #include <cublas_v2.h>
 
-#include "gvx_attention_fast.cuh"
+#include "gvx_attention_c2.cuh"
 #include "gvx_bf16.cuh"
 #include "gvx_blas.cuh"
 #include "gvx_layout.cuh"
@@ -202,7 +202,7 @@ inline int run_bf_lstm_fwd(const Dims &d, const float *packed, int which, const 
     a.drop = make_drop(seed, which == 0 ? d.p_att : d.p_dec, training);
     a.site = which == 0 ? SITE_ATT : SITE_DEC;
     a.t = (uint32_t)t; a.row_offset = row_offset; a.B = B; a.HID = which == 0 ? d.A : d.H;
-    GVX_CUDA(launch_pdl(k_bf_lstm_fwd, dim3(grid_for((size_t)B * a.HID / 8)), dim3(256), 0, st, a));
+    GVX_CUDA(launch_pdl(k_bf_lstm_fwd, dim3(grid_for((size_t)B * a.HID)), dim3(256), 0, st, a));
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     return 0;
@@ -326,7 +326,7 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
             add_rm(a.ctx_bf, hcrm, d.H, d.Kp);
             a.th_stash = s + S.TH + (size_t)t * B * N * d.D;
             a.conv_stash = s + S.CONVS + (size_t)t * B * N * d.F;
-            GVX_TRY(launch_attention_fwd_any(a, st));
+            GVX_TRY(launch_attention_fwd_best(a, st));
         }
         {   // decoder LSTM (:355-358)
             ProfScope ps(PS_DEC_LSTM, st);
@@ -446,7 +446,7 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
             a.dq_out = nullptr;
             add_img(a.dq_bf, DQI, 0, NPAD); add_rm(a.dq_bf, DQRM + (size_t)t * B * d.D, 0, d.D);
             a.dconv_out = x + W.DCONV + (size_t)t * B * N * d.F;
-            GVX_TRY(launch_attention_bwd_any(a, st));
+            GVX_TRY(launch_attention_bwd_best(a, st));
         }
         {   // S4: d h_att = d q . W_query + (from decoder-LSTM input) + (from step t+1), attention-LSTM pointwise backward
             ProfScope ps(PS_BWD_ATT_POINT, st);
@@ -491,7 +491,7 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
         dim3 grid((cols + 255) / 256, W.colchunks);
         k_colsum_bf16_part<<<grid, 256, 0, st>>>(m, (size_t)TB, cols, W.colchunks, x + W.COLP);
         GVX_LAUNCHED(1);
-        k_reduce_partials<<<grid_for((size_t)cols), 256, 0, st>>>(x + W.COLP, W.colchunks, cols, 0, cols, out);
+        k_reduce_partials<<<(cols + 31) / 32, dim3(32, 8), 0, st>>>(x + W.COLP, W.colchunks, cols, 0, cols, out);
         GVX_LAUNCHED(1);
         GVX_CUDA(cudaGetLastError());
         return 0;
@@ -588,7 +588,7 @@ int infer_bf16(const Dims &d, const gvx_weights *w, const float *packed, const f
             a.align_out = align_out + (size_t)t * N; a.align_bstride = (long long)max_steps * N;
             a.ctx_ld = d.E;
             add_img(a.ctx_bf, xd, d.A, NPAD); add_img(a.ctx_bf, xa_n, d.P, NPAD); add_img(a.ctx_bf, XPI, d.H, NPAD);
-            GVX_TRY(launch_attention_fwd_any(a, st));
+            GVX_TRY(launch_attention_fwd_best(a, st));
         }
         {
             ProfScope ps(PS_DEC_LSTM, st);

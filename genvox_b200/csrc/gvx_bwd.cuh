@@ -17,7 +17,7 @@
 #include <cublas_v2.h>
 
 #include "../../include/genvox_b200.h"
-#include "gvx_attention_fast.cuh"
+#include "gvx_attention_c2.cuh"
 #include "gvx_blas.cuh"
 #include "gvx_common.cuh"
 #include "gvx_gemm.cuh"
@@ -202,12 +202,22 @@ __global__ void __launch_bounds__(1024, 1) k_attn_post_conv(const float *__restr
     }
 }
 
-// out[i] = sum_blk part[blk * stride + off + i], fixed order
-__global__ void k_reduce_partials(const float *__restrict__ part, int nblk, int stride, int off, int n, float *__restrict__ out) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int k = 0; k < nblk; ++k) s += part[(size_t)k * stride + off + i];
-        out[i] = s;
+// out[i] = sum_blk part[blk * stride + off + i]: 8 interleaved groups of blocks per output (threadIdx.y), each
+// summed in order, then combined in a fixed order -> deterministic, 8x more loads in flight than a single loop
+__global__ void __launch_bounds__(256) k_reduce_partials(const float *__restrict__ part, int nblk, int stride, int off, int n,
+                                                          float *__restrict__ out) {
+    __shared__ float sh[8][32];
+    const int i = blockIdx.x * 32 + threadIdx.x, g = threadIdx.y;
+    float s = 0.f;
+    if (i < n)
+        for (int k = g; k < nblk; k += 8) s += part[(size_t)k * stride + off + i];
+    sh[g][threadIdx.x] = s;
+    __syncthreads();
+    if (g == 0 && i < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += sh[q][threadIdx.x];
+        out[i] = t;
     }
 }
 
@@ -234,9 +244,9 @@ inline int bwd_post_common(const Dims &d, const gvx_weights *w, const float *mem
         GVX_LAUNCHED(1);
         GVX_CUDA(cudaGetLastError());
         const int stride = d.D * d.F + d.D;
-        k_reduce_partials<<<grid_for((size_t)d.D * d.F), 256, 0, st>>>(p.PART1, nblk, stride, 0, d.D * d.F, g->loc_dense_w);
+        k_reduce_partials<<<(d.D * d.F + 31) / 32, dim3(32, 8), 0, st>>>(p.PART1, nblk, stride, 0, d.D * d.F, g->loc_dense_w);
         GVX_LAUNCHED(1);
-        k_reduce_partials<<<grid_for((size_t)d.D), 256, 0, st>>>(p.PART1, nblk, stride, d.D * d.F, d.D, g->v_w);
+        k_reduce_partials<<<(d.D + 31) / 32, dim3(32, 8), 0, st>>>(p.PART1, nblk, stride, d.D * d.F, d.D, g->v_w);
         GVX_LAUNCHED(1);
         const int KB = (d.KS + 7) / 8, NCS = (N + 7) & ~7, NPS = NCS + 8 * KB + 8;
         const int cthreads = (d.F * 2 * KB + 31) & ~31;
@@ -251,7 +261,7 @@ inline int bwd_post_common(const Dims &d, const gvx_weights *w, const float *mem
         k_attn_post_conv<<<nblk, cthreads < 64 ? 64 : cthreads, smem, st>>>(p.DCONV, p.ALIGN, p.CUMS, T, B, N, d.F, d.KS, p.PART2);
         GVX_LAUNCHED(1);
         GVX_CUDA(cudaGetLastError());
-        k_reduce_partials<<<grid_for((size_t)d.F * 2 * d.KS), 256, 0, st>>>(p.PART2, nblk, d.F * 2 * d.KS, 0, d.F * 2 * d.KS,
+        k_reduce_partials<<<(d.F * 2 * d.KS + 31) / 32, dim3(32, 8), 0, st>>>(p.PART2, nblk, d.F * 2 * d.KS, 0, d.F * 2 * d.KS,
                                                                            g->loc_conv_w);
         GVX_LAUNCHED(1);
         GVX_CUDA(cudaGetLastError());
@@ -367,7 +377,7 @@ extern "C" int gvx_dec_train_bwd(const gvx_dims *dd, const gvx_weights *w, const
             a.de_out = x + W.DE + (size_t)t * B * N;
             a.dq_out = x + W.DQ + (size_t)t * B * d.D;
             a.dconv_out = x + W.DCONV + (size_t)t * B * N * d.F;
-            GVX_TRY(launch_attention_bwd_any(a, st));
+            GVX_TRY(launch_attention_bwd_best(a, st));
         }
         // S4
         {

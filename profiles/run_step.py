@@ -1,5 +1,5 @@
-"""Short driver for ncu: one decoder train step (fwd + BPTT) at the bench batch shape with few frames,
-then a few inference steps.  Usage: python profiles/run_step.py [T] [infer_steps]"""
+"""Short driver for ncu: decoder train steps (fwd + BPTT) at the bench batch shape with few frames,
+then a few inference steps.  Usage: python profiles/run_step.py [T] [infer_steps] [bf16|fp32]"""
 import os
 import sys
 
@@ -13,9 +13,11 @@ from genvox_b200.training import decoder_train_step, make_optimizer  # noqa: E40
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+PREC = sys.argv[3] if len(sys.argv) > 3 else "bf16"
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 dec = genvox_b200.Decoder(**decoder_dims()).to(dev).train()
+dec.precision = PREC
 opt = make_optimizer(dec)
 memory, mel, gate, lengths = (t.to(dev) for t in synthetic_batch(torch, 64, 150, T))
 for _ in range(2):
