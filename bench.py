@@ -197,8 +197,8 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def step_resident():
-        return decoder_train_step(dec, opt, memory, mel, gate, lengths, group=group)
+    def step_resident(sync_gradients=True):
+        return decoder_train_step(dec, opt, memory, mel, gate, lengths, group=group, sync_gradients=sync_gradients)
 
     loss_h = torch.zeros(1).pin_memory()
 
@@ -222,8 +222,10 @@ def run_ours(args, rank, world, local_rank):
     launches0 = lib.gvx_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    host_t0 = time.perf_counter()
     for _ in range(K):
         loss, _ = step_resident()
+    host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / K      # host time to ENQUEUE a step (no sync inside)
     e1.record()
     barrier()
     launches = lib.gvx_launch_count() - launches0
@@ -253,15 +255,18 @@ def run_ours(args, rank, world, local_rank):
                                       if args.precision == "bf16" else "fp32 arithmetic"),
                        "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "per-step working set (stash + workspace, several GB) is far larger than the 126 MB L2"},
-            "e2e": e2e, "gpu_launches": int(launches), "final_loss": final_loss}
+            "e2e": e2e, "gpu_launches": int(launches), "final_loss": final_loss, "host_enqueue_ms_per_step": host_enqueue_ms}
     if clocks is not None:
         line["clocks"] = clocks
+    gs = (C.c_ulonglong * 4)()
+    lib.gvx_graph_stats(gs)
+    line["cuda_graphs"] = {"eager_calls": int(gs[0]), "captured": int(gs[1]), "replays": int(gs[2]), "failed_captures": int(gs[3])}
 
     if rank == 0:
         # ---- one extra, profiled step: per-phase device time from CUDA events around every launch
         lib.gvx_profile_reset()
         lib.gvx_profile_enable(1)
-        step_resident()
+        step_resident(sync_gradients=False)      # rank 0 alone: no collective in this extra step
         torch.cuda.synchronize()
         lib.gvx_profile_enable(0)
         phases, slot = {}, 0
@@ -347,7 +352,8 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
     try:
         run_ours(args, rank, world, local_rank)
     finally:

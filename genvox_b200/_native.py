@@ -56,6 +56,7 @@ _SIGNATURES = {
     "gvx_profile_reset": (C.c_int, []),
     "gvx_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "gvx_profile_slot_name": (C.c_char_p, [C.c_int]),
+    "gvx_graph_stats": (C.c_int, [C.POINTER(C.c_ulonglong)]),
     "gvx_dec_packed_bytes": (C.c_size_t, [C.POINTER(GvxDims)]),
     "gvx_dec_pack_weights": (C.c_int, [C.POINTER(GvxDims), C.POINTER(GvxWeights), _P, _P]),
     "gvx_dec_stash_bytes": (C.c_size_t, [C.POINTER(GvxDims), C.c_int, C.c_int, C.c_int]),

@@ -5,6 +5,7 @@
 #include "gvx_attention_c2.cuh"
 #include "gvx_common.cuh"
 #include "gvx_gemm.cuh"
+#include "gvx_graph.cuh"
 #include "gvx_layout.cuh"
 #include "gvx_misc.cuh"
 #include "gvx_tc.cuh"
@@ -18,6 +19,10 @@ size_t packed_total_bf16(const Dims &d);
 size_t stash_total_bf16(const Dims &d, int B, int N, int T);
 size_t bwd_total_bf16(const Dims &d, int B, int N, int T);
 size_t infer_total_bf16(const Dims &d, int B, int N, int steps);
+size_t stash_seed_off_bf16(const Dims &d, int B, int N, int T);
+size_t infer_flags_off_bf16(const Dims &d, int B, int N, int steps);
+size_t infer_err_off_bf16(const Dims &d, int B, int N, int steps);
+int check_tc_err_public(int *err_dev, cudaStream_t st, const char *what);
 int pack_weights_bf16(const Dims &d, const gvx_weights *w, float *packed, cudaStream_t st);
 int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, const float *memory, const float *mel_in,
                    const int64_t *mem_lengths, int B, int N, int T, uint64_t seed, int training, int row_offset, float *mel_out,
@@ -241,12 +246,9 @@ size_t gvx_dec_infer_workspace_bytes(const gvx_dims *d, int B, int N, int max_st
     return InferL(Dims(*d), B, N, max_steps).total * sizeof(float);
 }
 
-int gvx_dec_train_fwd(const gvx_dims *dd, const gvx_weights *w, const void *packed_, const float *memory,
-                      const float *mel_in, const int64_t *mem_lengths, int B, int N, int T, uint64_t seed, int training,
-                      int row_offset, float *mel_out, float *gate_out, float *align_out, void *stash_, void *stream) {
-    GVX_TRY(check_dims(dd));
-    GVX_CHECK(w && packed_ && memory && mel_in && mel_out && gate_out && align_out && stash_, "null argument");
-    GVX_CHECK(B > 0 && N > 0 && T > 0, "B, N, T must be positive");
+static int train_fwd_body(const gvx_dims *dd, const gvx_weights *w, const void *packed_, const float *memory,
+                          const float *mel_in, const int64_t *mem_lengths, int B, int N, int T, uint64_t seed, int training,
+                          int row_offset, float *mel_out, float *gate_out, float *align_out, void *stash_, void *stream) {
     const Dims d(*dd);
     if (dd->precision == GVX_BF16)
         return train_fwd_bf16(d, w, (const float *)packed_, memory, mel_in, mem_lengths, B, N, T, seed, training, row_offset, mel_out,
@@ -274,6 +276,7 @@ int gvx_dec_train_fwd(const gvx_dims *dd, const gvx_weights *w, const void *pack
     GVX_CUDA(cudaMemsetAsync(s + S.CUM, 0, (size_t)B * N * sizeof(float), st));
     delete ps_setup;
 
+    pdl_barrier_next();
     for (int t = 0; t < T; ++t) {   // Decoder.decode, tacotron2.py:333-363
         LstmIO a;
         a.x0 = s + S.PRE2 + (size_t)t * B * d.P; a.w0 = d.P; a.ld0 = d.P;
@@ -308,14 +311,10 @@ int gvx_dec_train_fwd(const gvx_dims *dd, const gvx_weights *w, const void *pack
     return 0;
 }
 
-int gvx_dec_infer(const gvx_dims *dd, const gvx_weights *w, const void *packed_, const float *memory,
-                  const int64_t *mem_lengths, int B, int N, int max_steps, float gate_threshold, int ignore_gate,
-                  uint64_t seed, int training, int row_offset, float *mel_out, float *gate_out, float *align_out,
-                  int32_t *n_frames, int *steps_run, void *workspace, void *stream) {
-    GVX_TRY(check_dims(dd));
-    GVX_CHECK(w && packed_ && memory && mel_out && gate_out && align_out && n_frames && steps_run && workspace,
-              "null argument");
-    GVX_CHECK(B > 0 && N > 0 && max_steps > 0, "B, N, max_steps must be positive");
+static int infer_body(const gvx_dims *dd, const gvx_weights *w, const void *packed_, const float *memory,
+                      const int64_t *mem_lengths, int B, int N, int max_steps, float gate_threshold, int ignore_gate,
+                      uint64_t seed, int training, int row_offset, float *mel_out, float *gate_out, float *align_out,
+                      int32_t *n_frames, int *steps_run, void *workspace, void *stream) {
     const Dims d(*dd);
     if (dd->precision == GVX_BF16)
         return infer_bf16(d, w, (const float *)packed_, memory, mem_lengths, B, N, max_steps, gate_threshold, ignore_gate, seed,
@@ -337,12 +336,13 @@ int gvx_dec_infer(const gvx_dims *dd, const gvx_weights *w, const void *packed_,
     GVX_CUDA(cudaMemsetAsync(s + L.WPREV, 0, (size_t)B * N * sizeof(float), st));
     GVX_CUDA(cudaMemsetAsync(s + L.CUM, 0, (size_t)B * N * sizeof(float), st));
     GVX_CUDA(cudaMemsetAsync(s + L.ZERO, 0, (size_t)B * d.OL * sizeof(float), st));
-    GVX_CUDA(cudaMemsetAsync(flags, 0, 64 * sizeof(int), st));
+    GVX_CUDA(cudaMemsetAsync(flags, 0, 32 * sizeof(int), st));
     k_fill_i32<<<grid_for(B), 256, 0, st>>>(n_frames, B, ignore_gate ? max_steps : -1, 0);
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
 
     int t = 0, host_running = B;
+    pdl_barrier_next();
     for (; t < max_steps; ++t) {
         const int cur = t & 1, nxt = cur ^ 1;
         // prenet on the previous mel frame, dropout on (tacotron2.py:398, :143)
@@ -388,6 +388,84 @@ int gvx_dec_infer(const gvx_dims *dd, const gvx_weights *w, const void *packed_,
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     *steps_run = steps;
+    return 0;
+}
+
+// ---------------------------------------------------------------- graph-cached entry points
+static uint32_t *seed_slot_train(const gvx_dims *dd, void *stash, int B, int N, int T) {
+    const Dims d(*dd);
+    const size_t off = dd->precision == GVX_BF16 ? stash_seed_off_bf16(d, B, N, T) : StashL(d, B, N, T).SEED;
+    return reinterpret_cast<uint32_t *>((float *)stash + off);
+}
+static int put_seed(uint32_t *slot, uint64_t seed, cudaStream_t st) {
+    k_set_seed<<<1, 1, 0, st>>>(slot, (uint32_t)(seed & 0xffffffffull), (uint32_t)(seed >> 32));
+    GVX_LAUNCHED(1);
+    GVX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int gvx_dec_train_fwd(const gvx_dims *dd, const gvx_weights *w, const void *packed_, const float *memory,
+                      const float *mel_in, const int64_t *mem_lengths, int B, int N, int T, uint64_t seed, int training,
+                      int row_offset, float *mel_out, float *gate_out, float *align_out, void *stash_, void *stream) {
+    GVX_TRY(check_dims(dd));
+    GVX_CHECK(w && packed_ && memory && mel_in && mel_out && gate_out && align_out && stash_, "null argument");
+    GVX_CHECK(B > 0 && N > 0 && T > 0, "B, N, T must be positive");
+    cudaStream_t user = (cudaStream_t)stream;
+    uint32_t *slot = seed_slot_train(dd, stash_, B, N, T);
+    GVX_TRY(put_seed(slot, seed, user));
+    KeyBuilder kb;
+    kb.add((int)1).add(*dd).add(*w).add(packed_).add(memory).add(mel_in).add(mem_lengths).add(B).add(N).add(T).add(training)
+        .add(row_offset).add(mel_out).add(gate_out).add(align_out).add(stash_);
+    g_seed_ptr = slot;
+    const int rc = run_cached(kb.k, user, [&](cudaStream_t st) {
+        return train_fwd_body(dd, w, packed_, memory, mel_in, mem_lengths, B, N, T, seed, training, row_offset, mel_out, gate_out,
+                              align_out, stash_, (void *)st);
+    });
+    g_seed_ptr = nullptr;
+    return rc;
+}
+
+int gvx_dec_infer(const gvx_dims *dd, const gvx_weights *w, const void *packed_, const float *memory,
+                  const int64_t *mem_lengths, int B, int N, int max_steps, float gate_threshold, int ignore_gate,
+                  uint64_t seed, int training, int row_offset, float *mel_out, float *gate_out, float *align_out,
+                  int32_t *n_frames, int *steps_run, void *workspace, void *stream) {
+    GVX_TRY(check_dims(dd));
+    GVX_CHECK(w && packed_ && memory && mel_out && gate_out && align_out && n_frames && steps_run && workspace,
+              "null argument");
+    GVX_CHECK(B > 0 && N > 0 && max_steps > 0, "B, N, max_steps must be positive");
+    cudaStream_t user = (cudaStream_t)stream;
+    const Dims d(*dd);
+    const bool bf = dd->precision == GVX_BF16;
+    const size_t flags_off = bf ? infer_flags_off_bf16(d, B, N, max_steps) : InferL(d, B, N, max_steps).FLAGS;
+    // the seed slot sits behind the stop flags; the drivers only clear the first 32 ints of that block
+    uint32_t *slot = reinterpret_cast<uint32_t *>((float *)workspace + flags_off) + 32;
+    GVX_TRY(put_seed(slot, seed, user));
+    g_seed_ptr = slot;
+    int rc;
+    if (ignore_gate) {          // fixed step count: no host polling inside, the whole sequence is one graph
+        KeyBuilder kb;
+        kb.add((int)3).add(*dd).add(*w).add(packed_).add(memory).add(mem_lengths).add(B).add(N).add(max_steps).add(gate_threshold)
+            .add(training).add(row_offset).add(mel_out).add(gate_out).add(align_out).add(n_frames).add(workspace);
+        rc = run_cached(kb.k, user, [&](cudaStream_t st) {
+            return infer_body(dd, w, packed_, memory, mem_lengths, B, N, max_steps, gate_threshold, ignore_gate, seed, training,
+                              row_offset, mel_out, gate_out, align_out, n_frames, steps_run, workspace, (void *)st);
+        });
+        *steps_run = max_steps;
+    } else {
+        rc = infer_body(dd, w, packed_, memory, mem_lengths, B, N, max_steps, gate_threshold, ignore_gate, seed, training,
+                        row_offset, mel_out, gate_out, align_out, n_frames, steps_run, workspace, stream);
+    }
+    g_seed_ptr = nullptr;
+    if (rc == 0 && bf)
+        rc = check_tc_err_public(reinterpret_cast<int *>((float *)workspace + infer_err_off_bf16(d, B, N, max_steps)), user,
+                                 "gvx_dec_infer");
+    return rc;
+}
+
+int gvx_graph_stats(unsigned long long *out4) {
+    GVX_CHECK(out4 != nullptr, "null argument");
+    out4[0] = g_graph_stats.eager; out4[1] = g_graph_stats.captured; out4[2] = g_graph_stats.replayed;
+    out4[3] = g_graph_stats.capture_failed;
     return 0;
 }
 

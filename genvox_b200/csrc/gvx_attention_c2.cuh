@@ -31,7 +31,7 @@ struct AttnC2Geom {
 };
 
 struct AttnC2FwdSmem {
-    int wcat, convT, wldT, wlc, v, q, e, w, part, ctxp, xch, scratch, total;
+    int wcat, convT, wldT, wlc, v, q, e, w, part, ctxp, xch, scratch, pms, total;
     __host__ __device__ AttnC2FwdSmem(int N, int E) {
         const AttnC2Geom g(N);
         int o = 0;
@@ -48,6 +48,7 @@ struct AttnC2FwdSmem {
         ctxp = take(E);        // this CTA's partial context, read by the peer
         xch = take(8);         // [0] local max, [1] local sum
         scratch = take(64);
+        pms = take(g.NH * AF_D);   // processed memory of the own tokens, prefetched with cp.async in the PDL prologue
         total = o;
     }
 };
@@ -66,6 +67,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
     float *wprev_row = a.w_prev + (size_t)b * N, *cum_row = a.cum + (size_t)b * N;
 
     pdl_trigger();
+    {   // processed memory rows of the own tokens do not depend on the previous kernel: asynchronous prefetch
+        const float *src = a.pm + ((size_t)b * N + n_lo) * AF_D;
+        for (int i = tid; i < n_own * (AF_D / 4); i += AF_THREADS) cp_async16(sm + L.pms + i * 4, src + (size_t)i * 4, true);
+        cp_async_commit();
+    }
     for (int i = tid; i < AF_F * 2 * AF_KS; i += AF_THREADS) sm[L.wlc + i] = a.wlc[i];
     for (int i = tid; i < AF_F * AF_D / 4; i += AF_THREADS)
         reinterpret_cast<float4 *>(sm + L.wldT)[i] = reinterpret_cast<const float4 *>(a.wldT)[i];
@@ -108,6 +114,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
         dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
         dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
+    cp_async_wait<0>();       // the prefetched processed-memory rows have landed (each thread waits for its own copies)
     __syncthreads();
     if (a.conv_stash) {
         float *cs = a.conv_stash + ((size_t)b * N + n_lo) * AF_F;
@@ -121,13 +128,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
     {
         const float4 q4 = *reinterpret_cast<const float4 *>(sm + L.q + lane * 4);
         const float4 v4 = *reinterpret_cast<const float4 *>(sm + L.v + lane * 4);
-        const float *pm_b = a.pm + ((size_t)b * N + n_lo) * AF_D;
+        const float *pm_b = sm + L.pms;
         const int ngrp = (n_own + 3) / 4;
         for (int grp = wid; grp < ngrp; grp += AF_WARPS) {
             const int n0 = grp * 4;
             float4 p[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)        // issue the processed-memory loads before the dense layer hides them
+            for (int j = 0; j < 4; ++j)
                 p[j] = n0 + j < n_own ? *reinterpret_cast<const float4 *>(pm_b + (size_t)(n0 + j) * AF_D + lane * 4)
                                       : make_float4(0.f, 0.f, 0.f, 0.f);
             float acc[4][4];
@@ -242,7 +249,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
 
 // ------------------------------------------------------------------------------------ backward
 struct AttnC2BwdSmem {
-    int dctx, w, de, v, wld4, wlc, dsb, dconvT, dq, dqp, part, xch, scratch, total;
+    int dctx, w, de, v, wld4, wlc, dsb, dconvT, dq, dqp, part, xch, scratch, ths, total;
     __host__ __device__ AttnC2BwdSmem(int N, int E) {
         const AttnC2Geom g(N);
         int o = 0;
@@ -260,6 +267,7 @@ struct AttnC2BwdSmem {
         part = take(8 * 2 * g.NH);
         xch = take(8);
         scratch = take(64);
+        ths = take(g.NH * AF_D);    // stashed tanh rows of the own tokens, prefetched with cp.async in the PDL prologue
         total = o;
     }
 };
@@ -278,6 +286,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
     const int own_len = max(0, min(len, n_lo + n_own) - n_lo);     // unmasked own tokens
 
     pdl_trigger();
+    {   // the forward pass wrote the tanh stash long ago: asynchronous prefetch of the own tokens' rows
+        const float *src = a.th + ((size_t)b * N + n_lo) * AF_D;
+        for (int i = tid; i < n_own * (AF_D / 4); i += AF_THREADS) cp_async16(sm + L.ths + i * 4, src + (size_t)i * 4, true);
+        cp_async_commit();
+    }
     if (tid < AF_D) sm[L.v + tid] = a.v[tid];
     for (int i = tid; i < AF_D * AF_F; i += AF_THREADS) {
         const int d = i >> 5, f = i & 31;
@@ -294,6 +307,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
         if (rank == 0) a.dctx_out[(size_t)b * E + e] = x;
     }
     for (int n = tid; n < G.NH; n += AF_THREADS) sm[L.w + n] = n < n_own ? a.w_t[(size_t)b * a.w_bstride + n_lo + n] : 0.f;
+    cp_async_wait<0>();
     __syncthreads();
 
     // ---- d w of the own tokens
@@ -355,7 +369,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
                 float4 ds = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (n < own_len) {
                     const float de = sm[L.de + n];
-                    const float4 th = *reinterpret_cast<const float4 *>(a.th + ((size_t)b * N + n_lo + n) * AF_D + lane * 4);
+                    const float4 th = *reinterpret_cast<const float4 *>(sm + L.ths + n * AF_D + lane * 4);
                     ds.x = de * v4.x * (1.f - th.x * th.x);
                     ds.y = de * v4.y * (1.f - th.y * th.y);
                     ds.z = de * v4.z * (1.f - th.z * th.z);

@@ -89,27 +89,19 @@ __global__ void __launch_bounds__(256) k_bf_lstm_bwd(const BfLstmBwd a) {
         }
         return;
     }
-    const int npair = a.HID >> 1;
-    const int total = a.B * npair;
+    // one thread per (row, hidden unit): 4 bf16 d-gates = one 8-byte store into the next GEMM's operand image
+    const int total = a.B * a.HID;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += a.main_blocks * blockDim.x) {
-        const int b = idx / npair, u0 = (idx - b * npair) << 1;
-        uint32_t w[4];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int u = u0 + j;
-            float dh = src_get(a.s0, b, u);
-            if (a.s1.nsplit) dh += src_get(a.s1, b, u);
-            if (a.s2.nsplit) dh += src_get(a.s2, b, u);
-            const float mult = drop_mult(a.drop, a.site, a.t, (uint32_t)(b + a.row_offset), (uint32_t)u);
-            const float4 ga = *reinterpret_cast<const float4 *>(a.gates + (size_t)b * 4 * a.HID + 4 * u);
-            const size_t ci = (size_t)b * a.HID + u;
-            float dcp;
-            const float4 dp = lstm_bwd_point(dh, mult, ga, a.c_prev[ci], a.c_new[ci], a.dc[ci], dcp);
-            a.dc[ci] = dcp;
-            w[2 * j] = pack_bf2(dp.x, dp.y);
-            w[2 * j + 1] = pack_bf2(dp.z, dp.w);
-        }
-        bf_store8(a.dg_dst, b, 4 * u0, make_uint4(w[0], w[1], w[2], w[3]));
+        const int b = idx / a.HID, u = idx - b * a.HID;
+        float dh = src_get(a.s0, b, u);
+        if (a.s1.nsplit) dh += src_get(a.s1, b, u);
+        if (a.s2.nsplit) dh += src_get(a.s2, b, u);
+        const float mult = drop_mult(a.drop, a.site, a.t, (uint32_t)(b + a.row_offset), (uint32_t)u);
+        const float4 ga = *reinterpret_cast<const float4 *>(a.gates + (size_t)b * 4 * a.HID + 4 * u);
+        float dcp;
+        const float4 dp = lstm_bwd_point(dh, mult, ga, a.c_prev[idx], a.c_new[idx], a.dc[idx], dcp);
+        a.dc[idx] = dcp;
+        bf_store4(a.dg_dst, b, 4 * u, make_uint2(pack_bf2(dp.x, dp.y), pack_bf2(dp.z, dp.w)));
     }
 }
 

@@ -89,7 +89,7 @@ int pack_weights_bf16(const Dims &d, const gvx_weights *w, float *packed, cudaSt
 // ---- bf16 training stash -----------------------------------------------------------------------------
 struct StashBfL {
     size_t FR, PRE1, PRE2, PM, CA, GA, CD, GD, ALIGN, CUMS, TH, CONVS, OUT, WPREV, CUM, XAI, XDI, XARM, XDRM, HCRM, PA, PD, PQ, ERR,
-        total;
+        SEED, total;
     size_t xai_stride, xdi_stride;     // bf16 elements per frame image
     int NPAD, KSa, KSd, KSq;
     StashBfL(const Dims &d, int B, int N, int T) {
@@ -112,6 +112,7 @@ struct StashBfL {
         PA = c.take((size_t)KSa * B * g.Ta * TC_M); PD = c.take((size_t)KSd * B * g.Td * TC_M);
         PQ = c.take((size_t)KSq * B * g.Tq * TC_M);
         ERR = c.take(64);
+        SEED = c.take(64);
         total = c.o;
     }
 };
@@ -208,6 +209,26 @@ inline int run_bf_lstm_fwd(const Dims &d, const float *packed, int which, const 
     return 0;
 }
 
+// gate GEMM + LSTM cell: fused cluster kernel when the K range splits in 4 (GVX_FUSED_LSTM=0: GEMM -> partials -> cell kernel)
+inline int run_lstm_bf16(const Dims &d, const float *packed, int which, const bf16 *Wimg, const bf16 *Ximg, float *P, int KS,
+                         int tiles, int kpad, const float *c_prev, float *c_out, float *gates_out, const BfDsts &h_dst, int B,
+                         uint64_t seed, int t, int training, int row_offset, int *err, cudaStream_t st) {
+    if (tc_fused_lstm_enabled() && kpad / TC_KB >= 4 && 4 * tiles <= 148) {
+        const PackedL PL(d);
+        TcLstmArgs p;
+        memset(&p, 0, sizeof(p));
+        p.g.Wimg = Wimg; p.g.Ximg = Ximg; p.g.P = nullptr; p.g.Kpad = kpad; p.g.B = B; p.g.ldp = tiles * TC_M; p.g.KS = 4; p.g.err = err;
+        p.bias = packed + (which == 0 ? PL.ba : PL.bd);
+        p.c_prev = c_prev; p.c_out = c_out; p.gates_out = gates_out; p.h_dst = h_dst;
+        p.drop = make_drop(seed, which == 0 ? d.p_att : d.p_dec, training);
+        p.site = which == 0 ? SITE_ATT : SITE_DEC;
+        p.t = (uint32_t)t; p.row_offset = row_offset; p.HID = which == 0 ? d.A : d.H;
+        return launch_tc_gemm_lstm(p, tiles, st);
+    }
+    GVX_TRY(run_tc(Wimg, Ximg, P, tiles, kpad, KS, B, err, st));
+    return run_bf_lstm_fwd(d, packed, which, P, KS, tiles, c_prev, c_out, gates_out, h_dst, B, seed, t, training, row_offset, st);
+}
+
 inline int check_tc_err(int *err_dev, cudaStream_t st, const char *what) {
     int h = 0;
     GVX_CUDA(cudaMemcpyAsync(&h, err_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -289,6 +310,7 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     GVX_TRY(run_processed_memory(d, w, memory, B, N, s + S.PM, st));
     delete ps_setup;
 
+    pdl_barrier_next();
     for (int t = 0; t < T; ++t) {
         const bool more = t + 1 < T;
         bf16 *xa = XAI + (size_t)t * S.xai_stride, *xd = XDI + (size_t)t * S.xdi_stride;
@@ -297,13 +319,12 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
         bf16 *xdrm_n = more ? XDRM + (size_t)(t + 1) * B * d.Kd : nullptr, *hcrm = HCRM + (size_t)t * B * d.Kp;
         {   // attention LSTM (tacotron2.py:338-341)
             ProfScope ps(PS_ATT_LSTM, st);
-            GVX_TRY(run_tc(WaI, xa, s + S.PA, g.Ta, g.Kpa, S.KSa, B, err, st));
             BfDsts h;
             memset(&h, 0, sizeof(h));
             add_img(h, xd, 0, NPAD); add_rm(h, xdrm, 0, d.Kd);
             add_img(h, xa_n, d.P + d.E, NPAD); add_rm(h, xarm_n, d.P + d.E, d.Ka);
-            GVX_TRY(run_bf_lstm_fwd(d, packed, 0, s + S.PA, S.KSa, g.Ta, s + S.CA + t * BA, s + S.CA + (t + 1) * BA,
-                                    s + S.GA + (size_t)t * 4 * BA, h, B, seed, t, training, row_offset, st));
+            GVX_TRY(run_lstm_bf16(d, packed, 0, WaI, xa, s + S.PA, S.KSa, g.Ta, g.Kpa, s + S.CA + t * BA, s + S.CA + (t + 1) * BA,
+                                  s + S.GA + (size_t)t * 4 * BA, h, B, seed, t, training, row_offset, err, st));
         }
         {   // query projection (:98): X = the h_att prefix of the decoder-LSTM operand image
             ProfScope ps(PS_QUERY, st);
@@ -330,13 +351,12 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
         }
         {   // decoder LSTM (:355-358)
             ProfScope ps(PS_DEC_LSTM, st);
-            GVX_TRY(run_tc(WdI, xd, s + S.PD, g.Td, g.Kpd, S.KSd, B, err, st));
             BfDsts h;
             memset(&h, 0, sizeof(h));
             add_rm(h, hcrm, 0, d.Kp);
             add_img(h, xd_n, d.A + d.E, NPAD); add_rm(h, xdrm_n, d.A + d.E, d.Kd);
-            GVX_TRY(run_bf_lstm_fwd(d, packed, 1, s + S.PD, S.KSd, g.Td, s + S.CD + t * BH, s + S.CD + (t + 1) * BH,
-                                    s + S.GD + (size_t)t * 4 * BH, h, B, seed, t, training, row_offset, st));
+            GVX_TRY(run_lstm_bf16(d, packed, 1, WdI, xd, s + S.PD, S.KSd, g.Td, g.Kpd, s + S.CD + t * BH, s + S.CD + (t + 1) * BH,
+                                  s + S.GD + (size_t)t * 4 * BH, h, B, seed, t, training, row_offset, err, st));
         }
     }
     ProfScope ps_out(PS_OUTPUT, st);
@@ -361,7 +381,7 @@ inline int run_bf_lstm_bwd(const Dims &d, int which, const SrcSum &s0, const Src
     a.site = which == 0 ? SITE_ATT : SITE_DEC;
     a.t = (uint32_t)t; a.row_offset = row_offset; a.B = B; a.HID = which == 0 ? d.A : d.H;
     a.gates = gates; a.c_prev = c_prev; a.c_new = c_new; a.dc = dc; a.dg_dst = dg;
-    a.main_blocks = grid_for((size_t)B * a.HID / 2);
+    a.main_blocks = grid_for((size_t)B * a.HID);
     int extra = 0;
     if (dpre_src) {
         a.dpre_src = *dpre_src; a.pre2 = pre2; a.dz2 = dz2; a.P = d.P;
@@ -409,6 +429,7 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     GVX_CUDA(cudaGetLastError());
     GVX_TRY(gemm_nn(st, TB, d.Kp, d.M + 1, x + W.DOUT, d.OL, packed + PL.Wpg, d.Kp, x + W.DHC, d.Kp, 0.f));
 
+    pdl_barrier_next();
     for (int t = T - 1; t >= 0; --t) {
         const bool last = t == T - 1;
         float *pdxd = x + W.PDXD + (size_t)(t & 1) * W.pdxd_stride, *pdxd_n = x + W.PDXD + (size_t)((t + 1) & 1) * W.pdxd_stride;
@@ -538,7 +559,7 @@ int infer_bf16(const Dims &d, const gvx_weights *w, const float *packed, const f
 
     GVX_TRY(run_processed_memory(d, w, memory, B, N, s + L.PM, st));
     GVX_CUDA(cudaMemsetAsync(err, 0, 64 * sizeof(float), st));
-    GVX_CUDA(cudaMemsetAsync(flags, 0, 64 * sizeof(int), st));
+    GVX_CUDA(cudaMemsetAsync(flags, 0, 32 * sizeof(int), st));
     GVX_CUDA(cudaMemsetAsync(XAI, 0, 2 * L.xai_stride * sizeof(bf16), st));
     GVX_CUDA(cudaMemsetAsync(XDI, 0, 2 * L.xdi_stride * sizeof(bf16), st));
     GVX_CUDA(cudaMemsetAsync(XPI, 0, (size_t)g.Kpp * NPAD * sizeof(bf16), st));
@@ -552,6 +573,7 @@ int infer_bf16(const Dims &d, const gvx_weights *w, const float *packed, const f
     GVX_CUDA(cudaGetLastError());
 
     int t = 0, host_running = B;
+    pdl_barrier_next();
     for (; t < max_steps; ++t) {
         bf16 *xa = XAI + (size_t)(t & 1) * L.xai_stride, *xa_n = XAI + (size_t)((t + 1) & 1) * L.xai_stride;
         bf16 *xd = XDI + (size_t)(t & 1) * L.xdi_stride, *xd_n = XDI + (size_t)((t + 1) & 1) * L.xdi_stride;
@@ -565,12 +587,11 @@ int infer_bf16(const Dims &d, const gvx_weights *w, const float *packed, const f
         }
         {
             ProfScope ps(PS_ATT_LSTM, st);
-            GVX_TRY(run_tc(WaI, xa, s + L.PA, g.Ta, g.Kpa, L.KSa, B, err, st));
             BfDsts h;
             memset(&h, 0, sizeof(h));
             add_img(h, xd, 0, NPAD); add_img(h, xa_n, d.P + d.E, NPAD);
-            GVX_TRY(run_bf_lstm_fwd(d, packed, 0, s + L.PA, L.KSa, g.Ta, s + L.CA, s + L.CA, nullptr, h, B, seed, t, training,
-                                    row_offset, st));
+            GVX_TRY(run_lstm_bf16(d, packed, 0, WaI, xa, s + L.PA, L.KSa, g.Ta, g.Kpa, s + L.CA, s + L.CA, nullptr, h, B, seed, t,
+                                  training, row_offset, err, st));
         }
         {
             ProfScope ps(PS_QUERY, st);
@@ -592,12 +613,11 @@ int infer_bf16(const Dims &d, const gvx_weights *w, const float *packed, const f
         }
         {
             ProfScope ps(PS_DEC_LSTM, st);
-            GVX_TRY(run_tc(WdI, xd, s + L.PD, g.Td, g.Kpd, L.KSd, B, err, st));
             BfDsts h;
             memset(&h, 0, sizeof(h));
             add_img(h, XPI, 0, NPAD); add_img(h, xd_n, d.A + d.E, NPAD);
-            GVX_TRY(run_bf_lstm_fwd(d, packed, 1, s + L.PD, L.KSd, g.Td, s + L.CD, s + L.CD, nullptr, h, B, seed, t, training,
-                                    row_offset, st));
+            GVX_TRY(run_lstm_bf16(d, packed, 1, WdI, xd, s + L.PD, L.KSd, g.Td, g.Kpd, s + L.CD, s + L.CD, nullptr, h, B, seed, t,
+                                  training, row_offset, err, st));
         }
         float *out_t = s + L.OUT + (size_t)t * B * d.OL;
         {
@@ -628,12 +648,16 @@ int infer_bf16(const Dims &d, const gvx_weights *w, const float *packed, const f
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     *steps_run = steps;
-    return check_tc_err(err, st, "gvx_dec_infer");
+    return 0;
 }
 
 size_t packed_total_bf16(const Dims &d) { return PackedBfL(d, PackedL(d).total).total; }
 size_t stash_total_bf16(const Dims &d, int B, int N, int T) { return StashBfL(d, B, N, T).total; }
 size_t bwd_total_bf16(const Dims &d, int B, int N, int T) { return BwdBfL(d, B, N, T).total; }
 size_t infer_total_bf16(const Dims &d, int B, int N, int steps) { return InferBfL(d, B, N, steps).total; }
+size_t stash_seed_off_bf16(const Dims &d, int B, int N, int T) { return StashBfL(d, B, N, T).SEED; }
+size_t infer_flags_off_bf16(const Dims &d, int B, int N, int steps) { return InferBfL(d, B, N, steps).FLAGS; }
+size_t infer_err_off_bf16(const Dims &d, int B, int N, int steps) { return InferBfL(d, B, N, steps).ERR; }
+int check_tc_err_public(int *err_dev, cudaStream_t st, const char *what) { return check_tc_err(err_dev, st, what); }
 
 }  // namespace gvx

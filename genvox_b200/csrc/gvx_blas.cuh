@@ -21,6 +21,9 @@ inline int blas(cublasHandle_t *out, cudaStream_t st) {
     if (!h) {
         GVX_CUBLAS(cublasCreate(&h));
         GVX_CUBLAS(cublasSetMathMode(h, CUBLAS_DEFAULT_MATH));    // true fp32 sgemm (no TF32), like torch's default
+        // a fixed workspace keeps cuBLAS from allocating while its GEMMs are being captured into a CUDA graph
+        void *ws = nullptr;
+        if (cudaMalloc(&ws, (size_t)64 << 20) == cudaSuccess) GVX_CUBLAS(cublasSetWorkspace(h, ws, (size_t)64 << 20));
     }
     GVX_CUBLAS(cublasSetStream(h, st));
     *out = h;

@@ -115,6 +115,12 @@ inline bool pdl_enabled() {
     return on == 1;
 }
 
+// The kernels of a chain read, BEFORE griddepcontrol.wait, only data that was complete before the chain began
+// (weights, processed memory, forward stashes).  Kernels ahead of the chain (prenet / processed-memory GEMMs) also
+// trigger early, so the first kernel of every chain is launched with a full dependency: pdl_barrier_next().
+inline thread_local bool g_pdl_skip_next = false;
+inline void pdl_barrier_next() { g_pdl_skip_next = true; }
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
     cudaLaunchConfig_t cfg;
@@ -127,7 +133,8 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = (pdl_enabled() && !g_pdl_skip_next) ? 1 : 0;
+    g_pdl_skip_next = false;
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
@@ -135,14 +142,19 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 enum : uint32_t { SITE_PRENET0 = 0, SITE_PRENET1 = 1, SITE_ATT = 2, SITE_DEC = 3 };
 
 struct DropCfg {
+    const uint32_t *kptr; // if non-null: {seed low, seed high} in device memory (lets a CUDA graph outlive the seed)
     uint32_t k0, k1;      // seed low / high word
     uint32_t threshold;   // keep iff word >= threshold ( = floor(p * 2^32) )
     float scale;          // 1 / (1 - p)
     int on;               // 0: identity
 };
 
-inline DropCfg make_drop(uint64_t seed, float p, int on) {
+// device seed slot of the call being enqueued (set by the entry points around their launch sequence)
+inline thread_local const uint32_t *g_seed_ptr = nullptr;
+
+inline DropCfg make_drop(uint64_t seed, float p, int on, const uint32_t *kptr = nullptr) {
     DropCfg c;
+    c.kptr = kptr ? kptr : g_seed_ptr;
     c.k0 = (uint32_t)(seed & 0xffffffffull);
     c.k1 = (uint32_t)(seed >> 32);
     double t = (double)p * 4294967296.0;
@@ -172,7 +184,8 @@ __device__ __forceinline__ uint32_t philox_word(uint32_t j, uint32_t row, uint32
 // multiplier applied to element (row, j) of dropout site `site` at index t: 0 or scale
 __device__ __forceinline__ float drop_mult(const DropCfg &c, uint32_t site, uint32_t t, uint32_t row, uint32_t j) {
     if (!c.on) return 1.f;
-    return philox_word(j, row, t, site, c.k0, c.k1) >= c.threshold ? c.scale : 0.f;
+    const uint32_t k0 = c.kptr ? c.kptr[0] : c.k0, k1 = c.kptr ? c.kptr[1] : c.k1;
+    return philox_word(j, row, t, site, k0, k1) >= c.threshold ? c.scale : 0.f;
 }
 
 // ---------------------------------------------------------------- math

@@ -53,6 +53,15 @@ __device__ __forceinline__ void bf_store8(const BfDsts &s, int b, int k, uint4 v
         else *reinterpret_cast<uint4 *>(d.p + (size_t)b * d.ld + kk) = v;
     }
 }
+// 4 consecutive columns k..k+3 (k multiple of 4) of row b
+__device__ __forceinline__ void bf_store4(const BfDsts &s, int b, int k, uint2 v) {
+    for (int i = 0; i < s.n; ++i) {
+        const BfDst &d = s.d[i];
+        const int kk = d.koff + k;
+        if (d.kind == 1) *reinterpret_cast<uint2 *>(d.p + ((size_t)(kk >> 3) * d.ld + b) * 8 + (kk & 7)) = v;
+        else *reinterpret_cast<uint2 *>(d.p + (size_t)b * d.ld + kk) = v;
+    }
+}
 // one column k of row b
 __device__ __forceinline__ void bf_store1(const BfDsts &s, int b, int k, float x) {
     const __nv_bfloat16 h = __float2bfloat16(x);

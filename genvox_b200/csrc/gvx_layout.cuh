@@ -43,7 +43,7 @@ struct PackedL {
 
 // ---- training stash (written by train_fwd, read by train_bwd); time-major [T][B][feat] ----------
 struct StashL {
-    size_t FR, PRE1, PRE2, PM, HA, CA, GA, CTX, HD, CD, GD, Q, ALIGN, CUMS, TH, CONVS, OUT, WPREV, CUM, total;
+    size_t FR, PRE1, PRE2, PM, HA, CA, GA, CTX, HD, CD, GD, Q, ALIGN, CUMS, TH, CONVS, OUT, WPREV, CUM, SEED, total;
     StashL(const Dims &d, int B, int N, int T) {
         Carver c;
         const size_t TB = (size_t)T * B, T1B = (size_t)(T + 1) * B;
@@ -58,6 +58,7 @@ struct StashL {
         CONVS = c.take(TB * N * d.F);        // [T][B][N][F] location-conv output
         OUT = c.take(TB * d.OL);
         WPREV = c.take((size_t)B * N); CUM = c.take((size_t)B * N);
+        SEED = c.take(64);                   // dropout seed of the call {lo, hi}, read by the kernels (graph replay)
         total = c.o;
     }
 };

@@ -115,6 +115,11 @@ __global__ void k_gate_check(const float *__restrict__ out_t, int B, int M, int 
     if (threadIdx.x == 0) flags[0] = running;
 }
 
+__global__ void k_set_seed(uint32_t *p, uint32_t lo, uint32_t hi) {
+    p[0] = lo;
+    p[1] = hi;
+}
+
 __global__ void k_fill_i32(int32_t *p, int n, int32_t v, int only_negative) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         if (!only_negative || p[i] < 0) p[i] = v;

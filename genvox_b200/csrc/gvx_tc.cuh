@@ -26,7 +26,10 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include <cooperative_groups.h>
+
 #include "gvx_common.cuh"
+#include "gvx_io.cuh"
 
 namespace gvx {
 
@@ -271,6 +274,189 @@ inline int launch_tc_gemm(const TcGemmArgs &a, int Mtiles, cudaStream_t st) {
         case 32: return launch_tc_gemm_t<32>(a, Mtiles, st);
         case 64: return launch_tc_gemm_t<64>(a, Mtiles, st);
         case 128: return launch_tc_gemm_t<128>(a, Mtiles, st);
+        default: return fail("tc gemm: batch rows per call must be <= 128 in bf16 mode");
+    }
+}
+
+// ------------------------------------------------------------------ gate GEMM + LSTM cell in one kernel
+// Same pipeline as k_tc_gemm, but the 4 CTAs that split the K range of one 128-row tile form a thread-block
+// cluster: each dumps its fp32 partial accumulator from TMEM to its own shared memory, the cluster syncs, and
+// CTA j finishes hidden units [8j, 8j+8) of the tile — sums the 4 partials (own + 3 through distributed shared
+// memory, always in rank order), adds the bias, applies nn.LSTMCell's pointwise part (tacotron2.py:340,:357) and the
+// carried-state dropout (:341,:358), and writes h (bf16) into the next GEMMs' operand images.  No partials in HBM,
+// one launch less per LSTM step.
+struct TcLstmArgs {
+    TcGemmArgs g;              // P unused; KS must be 4
+    const float *bias;         // [4*HID] unit-major (b_ih + b_hh)
+    const float *c_prev;       // [B, HID]
+    float *c_out;              // [B, HID]
+    float *gates_out;          // [B, 4*HID] unit-major activations or null
+    BfDsts h_dst;
+    DropCfg drop;
+    uint32_t site, t;
+    int row_offset, HID;
+};
+
+template <int NPAD>
+__global__ void __cluster_dims__(1, 4, 1) __launch_bounds__(TC_THREADS, 1) k_tc_gemm_lstm(const TcLstmArgs p) {
+    namespace cg = cooperative_groups;
+    using C = TcCfg<NPAD>;
+    const TcGemmArgs &a = p.g;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = (uint64_t *)(smem + C::BAR_OFF);
+    uint64_t *empty = full + TC_STAGES;
+    uint64_t *tmem_full = empty + TC_STAGES;
+    uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
+    cg::cluster_group cluster = cg::this_cluster();
+
+    pdl_trigger();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x, ks = blockIdx.y;          // ks == rank in the cluster (cluster spans gridDim.y = 4)
+    const int nkb_all = a.Kpad / TC_KB;
+    const int kb0 = (int)((long long)ks * nkb_all / 4), kb1 = (int)((long long)(ks + 1) * nkb_all / 4);
+    const int nkb = kb1 - kb0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    float *red = reinterpret_cast<float *>(smem);          // [NPAD][128] fp32 partial, reuses the drained pipeline stages
+
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint8_t *wsrc = (const uint8_t *)a.Wimg + ((size_t)tile * nkb_all + kb0) * C::WB;
+            const uint8_t *xsrc = (const uint8_t *)a.Ximg + (size_t)kb0 * C::XB;
+            const int npre = nkb < TC_STAGES ? nkb : TC_STAGES;
+            for (int i = 0; i < npre; ++i) {
+                mbar_expect_tx(full + i, (uint32_t)C::SB);
+                tma_bulk_g2s(smem + (size_t)i * C::SB, wsrc + (size_t)i * C::WB, (uint32_t)C::WB, full + i);
+            }
+            pdl_wait();
+            for (int i = 0; i < npre; ++i)
+                tma_bulk_g2s(smem + (size_t)i * C::SB + C::WB, xsrc + (size_t)i * C::XB, (uint32_t)C::XB, full + i);
+            for (int i = npre; i < nkb; ++i) {
+                const int s = i % TC_STAGES;
+                const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+                if (!mbar_wait(empty + s, ph ^ 1u, a.err, 1)) break;
+                mbar_expect_tx(full + s, (uint32_t)C::SB);
+                tma_bulk_g2s(smem + (size_t)s * C::SB, wsrc + (size_t)i * C::WB, (uint32_t)C::WB, full + s);
+                tma_bulk_g2s(smem + (size_t)s * C::SB + C::WB, xsrc + (size_t)i * C::XB, (uint32_t)C::XB, full + s);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(TC_M, NPAD < 16 ? 16 : NPAD);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % TC_STAGES;
+                const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+                if (!mbar_wait(full + s, ph, a.err, 2)) break;
+                tc_fence_after();
+                const uint32_t wbase = smem_u32(smem + (size_t)s * C::SB), xbase = wbase + C::WB;
+#pragma unroll
+                for (int kk = 0; kk < TC_KB / 16; ++kk) {
+                    const uint64_t ad = umma_desc(wbase + kk * 2 * (TC_M * 16), TC_M * 16, 128);
+                    const uint64_t bd = umma_desc(xbase + kk * 2 * (NPAD * 16), NPAD * 16, 128);
+                    umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(empty + s);
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        // TMEM -> shared memory partial, transposed ([col][row]) so that the 32 lanes of a warp hit 32 banks
+        const int q = warp & 3;
+        const bool ok = nkb == 0 || mbar_wait(tmem_full, 0, a.err, 3);
+        tc_fence_after();
+        const int row = q * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NPAD; c0 += 16) {
+            float v[16];
+            if (nkb > 0 && ok) {
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) red[(c0 + j) * TC_M + row] = v[j];
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    cluster.sync();                                        // all four partials are in shared memory
+
+    {
+        const float *r0 = cluster.map_shared_rank(red, 0), *r1 = cluster.map_shared_rank(red, 1);
+        const float *r2 = cluster.map_shared_rank(red, 2), *r3 = cluster.map_shared_rank(red, 3);
+        const int HID = p.HID;
+        for (int idx = threadIdx.x; idx < 8 * a.B; idx += TC_THREADS) {
+            const int l = ks * 8 + (idx & 7), b = idx >> 3;
+            const int unit = tile * 32 + l;
+            if (unit >= HID) continue;
+            float pre[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int o = b * TC_M + g * 32 + l;
+                pre[g] = ((r0[o] + r1[o]) + r2[o]) + r3[o];
+            }
+            const float4 bi = *reinterpret_cast<const float4 *>(p.bias + 4 * unit);
+            const float gi = sigmoidf_(pre[0] + bi.x), gf = sigmoidf_(pre[1] + bi.y);
+            const float gg = tanhf(pre[2] + bi.z), go = sigmoidf_(pre[3] + bi.w);
+            const size_t ci = (size_t)b * HID + unit;
+            const float cn = gf * p.c_prev[ci] + gi * gg;
+            p.c_out[ci] = cn;
+            const float h = go * tanhf(cn) * drop_mult(p.drop, p.site, p.t, (uint32_t)(b + p.row_offset), (uint32_t)unit);
+            if (p.gates_out) *reinterpret_cast<float4 *>(p.gates_out + (size_t)b * 4 * HID + 4 * unit) = make_float4(gi, gf, gg, go);
+            bf_store1(p.h_dst, b, unit, h);
+        }
+    }
+    cluster.sync();                                        // peers may still be reading this CTA's partial
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+    }
+}
+
+template <int NPAD>
+inline int launch_tc_gemm_lstm_t(const TcLstmArgs &p, int Mtiles, cudaStream_t st) {
+    using C = TcCfg<NPAD>;
+    static bool configured = false;
+    if (!configured) {
+        GVX_CUDA(cudaFuncSetAttribute(k_tc_gemm_lstm<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        configured = true;
+    }
+    GVX_CUDA(launch_pdl(k_tc_gemm_lstm<NPAD>, dim3(Mtiles, 4), dim3(TC_THREADS), C::SMEM, st, p));
+    GVX_LAUNCHED(1);
+    return 0;
+}
+
+inline bool tc_fused_lstm_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("GVX_FUSED_LSTM");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
+inline int launch_tc_gemm_lstm(const TcLstmArgs &p, int Mtiles, cudaStream_t st) {
+    GVX_CHECK(p.g.Kpad % TC_KB == 0 && p.g.Kpad / TC_KB >= 4, "fused tc gemm: K must cover at least 4 k-blocks");
+    switch (tc_npad(p.g.B)) {
+        case 16: return launch_tc_gemm_lstm_t<16>(p, Mtiles, st);
+        case 32: return launch_tc_gemm_lstm_t<32>(p, Mtiles, st);
+        case 64: return launch_tc_gemm_lstm_t<64>(p, Mtiles, st);
+        case 128: return launch_tc_gemm_lstm_t<128>(p, Mtiles, st);
         default: return fail("tc gemm: batch rows per call must be <= 128 in bf16 mode");
     }
 }

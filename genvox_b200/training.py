@@ -64,7 +64,7 @@ def allreduce_gradients(params, group=None, bucket_mb=32.0):
 
 
 def decoder_train_step(decoder, optimizer, memory, mel_padded, gate_padded, memory_lengths, grad_clip_thresh=1.0,
-                       group=None, bucket_mb=32.0):
+                       group=None, bucket_mb=32.0, sync_gradients=True):
     """One optimisation step of the decoder.  Returns (loss, grad_norm) as 0-dim device tensors
     (no host sync here; the reference's `.item()` calls at :519,:521 are the caller's choice)."""
     optimizer.zero_grad(set_to_none=True)
@@ -72,7 +72,8 @@ def decoder_train_step(decoder, optimizer, memory, mel_padded, gate_padded, memo
     loss, _, _ = decoder_loss(mel_out, gate_out, mel_padded, gate_padded)
     loss.backward()
     params = [p for p in decoder.parameters() if p.requires_grad]
-    allreduce_gradients(params, group, bucket_mb)
+    if sync_gradients:          # collective: every rank of the group must take part
+        allreduce_gradients(params, group, bucket_mb)
     grad_norm = torch.nn.utils.clip_grad_norm_(params, grad_clip_thresh)
     optimizer.step()
     return loss.detach(), grad_norm

@@ -103,6 +103,11 @@ int gvx_profile_reset(void);
 int gvx_profile_read(int slot, double *total_ms, long long *launches);
 const char *gvx_profile_slot_name(int slot);
 
+/* CUDA-graph cache statistics: {calls run eagerly, graphs captured, graph replays, failed captures}.  The launch
+ * sequence of train_fwd / train_bwd / fixed-step infer is captured the second time a call with identical arguments
+ * (pointers, shapes, flags; the dropout seed lives in device memory) is seen and replayed afterwards. */
+int gvx_graph_stats(unsigned long long *out4);
+
 /* Repacked weights (gate rows interleaved per hidden unit, W_ih|W_hh concatenated, transposed
  * copies for backward).  Replaces nothing in the reference: it is the cached form of the
  * parameters owned by Decoder.__init__ (tacotron2.py:259-301).  Call again whenever the
