@@ -10,6 +10,7 @@
 #include "gvx_blas.cuh"
 #include "gvx_layout.cuh"
 #include "gvx_misc.cuh"
+#include "gvx_persist.cuh"
 
 namespace gvx {
 
@@ -661,3 +662,60 @@ size_t infer_err_off_bf16(const Dims &d, int B, int N, int steps) { return Infer
 int check_tc_err_public(int *err_dev, cudaStream_t st, const char *what) { return check_tc_err(err_dev, st, what); }
 
 }  // namespace gvx
+
+// ---- test hook: the persistent LSTM chain on its own (forward, then optionally BPTT) -----------------------------
+__global__ void k_bf16_rows_to_f32(const __nv_bfloat16 *__restrict__ x, size_t n, float *__restrict__ y) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = __bfloat162float(x[i]);
+}
+
+extern "C" int gvx_test_lstm_chain(const float *w_hh, const float *pre, int B, int T, int H, float p_drop, uint64_t seed,
+                                   int training, float *h_out, float *c_out, float *gates_out, const float *dh_ext,
+                                   float *dgates_out, void *stream) {
+    using namespace gvx;
+    GVX_CHECK(w_hh && pre && h_out && c_out && gates_out && B > 0 && T > 0, "bad argument");
+    GVX_CHECK(pc_supported(H, B), "persistent chain: unsupported shape (need H % 32 == 0, H/8 <= SM count, B <= 64)");
+    cudaStream_t st = (cudaStream_t)stream;
+    bf16 *wimg = nullptr, *wimgT = nullptr, *himg = nullptr, *hrm = nullptr, *gimg = nullptr, *dgrm = nullptr;
+    unsigned *bar = nullptr;
+    int *err = nullptr;
+    const size_t TBH = (size_t)T * B * H;
+    GVX_CUDA(cudaMalloc(&wimg, pc_wimg_elems(H) * 2));
+    GVX_CUDA(cudaMalloc(&wimgT, pc_wimg_elems(H) * 2));
+    GVX_CUDA(cudaMalloc(&himg, (size_t)2 * H * 64 * 2));
+    GVX_CUDA(cudaMalloc(&hrm, TBH * 2));
+    GVX_CUDA(cudaMalloc(&gimg, (size_t)2 * 4 * H * 64 * 2));
+    GVX_CUDA(cudaMalloc(&dgrm, 4 * TBH * 2));
+    GVX_CUDA(cudaMalloc(&bar, 64));
+    GVX_CUDA(cudaMalloc(&err, 64));
+    GVX_CUDA(cudaMemsetAsync(err, 0, 64, st));
+    GVX_CUDA(cudaMemsetAsync(himg, 0, (size_t)2 * H * 64 * 2, st));
+    GVX_CUDA(cudaMemsetAsync(gimg, 0, (size_t)2 * 4 * H * 64 * 2, st));
+    GVX_CUDA(cudaMemsetAsync(c_out, 0, (size_t)B * H * sizeof(float), st));
+    k_pc_pack_w<<<grid_for(pc_wimg_elems(H)), 256, 0, st>>>(w_hh, H, H, 0, wimg);
+    k_pc_pack_w<<<grid_for(pc_wimg_elems(H)), 256, 0, st>>>(w_hh, H, H, 1, wimgT);
+    PcFwdArgs f;
+    memset(&f, 0, sizeof(f));
+    f.Wimg = wimg; f.pre = pre; f.himg = himg; f.c_stash = c_out; f.gates_stash = gates_out;
+    f.out[0] = PcOut{hrm, H, 0, 0, (long long)B * H};
+    f.bar = bar; f.err = err;
+    f.drop = make_drop(seed, p_drop, training, nullptr);
+    f.drop.kptr = nullptr;
+    f.site = SITE_DEC; f.row_offset = 0; f.B = B; f.T = T; f.H = H;
+    int rc = launch_lstm_chain_fwd(f, st);
+    if (!rc) {
+        k_bf16_rows_to_f32<<<grid_for(TBH), 256, 0, st>>>(hrm, TBH, h_out);
+        if (dh_ext && dgates_out) {
+            PcBwdArgs g;
+            memset(&g, 0, sizeof(g));
+            g.Wimg = wimgT; g.gimg = gimg; g.dh_ext = dh_ext; g.dh_ld = H; g.dh_tstride = (long long)B * H;
+            g.gates_stash = gates_out; g.c_stash = c_out; g.dg_rm = dgrm; g.bar = bar; g.err = err;
+            g.drop = f.drop; g.site = SITE_DEC; g.row_offset = 0; g.B = B; g.T = T; g.H = H;
+            rc = launch_lstm_chain_bwd(g, st);
+            if (!rc) k_bf16_rows_to_f32<<<grid_for(4 * TBH), 256, 0, st>>>(dgrm, 4 * TBH, dgates_out);
+        }
+    }
+    if (!rc) rc = check_tc_err(err, st, "persistent lstm chain");
+    else cudaStreamSynchronize(st);
+    cudaFree(wimg); cudaFree(wimgT); cudaFree(himg); cudaFree(hrm); cudaFree(gimg); cudaFree(dgrm); cudaFree(bar); cudaFree(err);
+    return rc;
+}

@@ -165,6 +165,17 @@ int gvx_dec_infer(const gvx_dims *d, const gvx_weights *w, const void *packed,
  * operands rounded to bf16, fp32 accumulation, the K range split over KS CTAs (test hook; allocates). */
 int gvx_test_tc_gemm(const float *W, const float *X, int B, int Mtot, int K, int KS, float *out, void *stream);
 
+/* The persistent LSTM-chain kernels on their own (test hook; allocates): for t < T
+ *   gates_t = pre_t + h_{t-1} . W_hh^T (h, W_hh rounded to bf16, fp32 accumulate), nn.LSTMCell pointwise part
+ *   (tacotron2.py:357), carried-state dropout (:358, Philox site 3), h_{-1} = c_{-1} = 0.
+ *   w_hh [4H, H] torch layout (rows i,f,g,o); pre [T, B, 4H] with columns 4*unit + gate;
+ *   h_out [T, B, H] (dropped h, bf16-rounded); c_out [T+1, B, H]; gates_out [T, B, 4H] activations (4*unit + gate).
+ *   If dh_ext [T, B, H] (gradient w.r.t. the dropped h_t from outside the chain) and dgates_out [T, B, 4H] are given,
+ *   BPTT runs too and dgates_out receives d loss / d pre (bf16-rounded). */
+int gvx_test_lstm_chain(const float *w_hh, const float *pre, int B, int T, int H, float p_drop, uint64_t seed,
+                        int training, float *h_out, float *c_out, float *gates_out, const float *dh_ext,
+                        float *dgates_out, void *stream);
+
 /* Prenet.forward, tacotron2.py:140-144: frames [F, B, n_mels] -> out [F, B, P]; frame f uses
  * Philox t = t0 + f.  tmp: [F, B, P] scratch for the layer-0 output. */
 int gvx_prenet_fwd(const gvx_dims *d, const gvx_weights *w, const float *frames, int F, int B,
