@@ -285,10 +285,11 @@ def run_ours(args, rank, world, local_rank):
         roofs = {}
         for name, Kc in (("dec_lstm", Kd), ("att_lstm", Ka), ("bwd_dec_gemm", Kd), ("bwd_att_gemm", Ka)):
             if name in phases:
-                flops = 2.0 * B * Kc * 4 * H                    # algorithmic FLOPs of one gate GEMM launch
-                ach = flops / (phases[name]["avg_us"] * 1e-6) / 1e12
+                flops = 2.0 * B * Kc * 4 * H * T                # algorithmic FLOPs of the gate GEMMs of all T steps
+                ach = flops / (phases[name]["ms"] * 1e-3) / 1e12     # (one launch per step, or one persistent launch)
                 roofs[name] = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                                "frac": ach / pk["tf_sustained"], "traffic": None, "avg_us": phases[name]["avg_us"],
+                               "us_per_step": 1e3 * phases[name]["ms"] / T, "launches": phases[name]["launches"],
                                "peak_source": pk["source"] + " (bf16 sustained)"
                                + ("" if args.precision == "bf16" else "; this kernel runs fp32 FFMA")}
         for name in ("attention", "bwd_attention"):

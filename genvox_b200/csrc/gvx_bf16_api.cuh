@@ -46,7 +46,7 @@ inline int tc_pick_ks(int mtiles, int nkb) {
 
 // ---- bf16 part of the packed weights, appended after the fp32 PackedL block (offsets in floats) ----
 struct PackedBfL {
-    size_t WaI, WdI, WaTI, WdTI, WqI, WqTI, WpgI, WpgRM, total;
+    size_t WaI, WdI, WaTI, WdTI, WqI, WqTI, WpgI, WpgRM, WdRM, WdhhI, WdhhTI, total;
     PackedBfL(const Dims &d, size_t base) {
         const BfGeom g(d);
         Carver c;
@@ -57,6 +57,11 @@ struct PackedBfL {
         WqI = img(g.Tq, g.Kpq); WqTI = img(g.TqT, g.Dp);
         WpgI = img(g.Tp, g.Kpp);
         WpgRM = c.take(((size_t)(d.M + 1) * d.Kp + 1) / 2);
+        // persistent decoder-LSTM chain (gvx_persist.cuh): unit-major row-major [4H][Kd] copy for the time-batched input
+        // GEMMs, resident W_hh slices for the forward chain and W_hh^T slices for BPTT
+        WdRM = c.take(((size_t)4 * d.H * d.Kd + 1) / 2);
+        WdhhI = c.take((size_t)2 * d.H * d.H);
+        WdhhTI = c.take((size_t)2 * d.H * d.H);
         total = c.o;
     }
 };
@@ -83,6 +88,13 @@ int pack_weights_bf16(const Dims &d, const gvx_weights *w, float *packed, cudaSt
     k_to_bf16<<<grid_for((size_t)(d.M + 1) * d.Kp), 256, 0, st>>>(packed + PL.Wpg, d.Kp, (size_t)(d.M + 1), d.Kp,
                                                                (bf16 *)(packed + BL.WpgRM), d.Kp);
     GVX_LAUNCHED(1);
+    k_to_bf16<<<grid_for((size_t)4 * d.H * d.Kd), 256, 0, st>>>(packed + PL.Wd, d.Kd, (size_t)4 * d.H, d.Kd, (bf16 *)(packed + BL.WdRM), d.Kd);
+    GVX_LAUNCHED(1);
+    if (d.H % 32 == 0) {
+        k_pc_pack_w<<<grid_for(pc_wimg_elems(d.H)), 256, 0, st>>>(w->dec_w_hh, d.H, d.H, 0, (bf16 *)(packed + BL.WdhhI));
+        k_pc_pack_w<<<grid_for(pc_wimg_elems(d.H)), 256, 0, st>>>(w->dec_w_hh, d.H, d.H, 1, (bf16 *)(packed + BL.WdhhTI));
+        GVX_LAUNCHED(2);
+    }
     GVX_CUDA(cudaGetLastError());
     return 0;
 }
@@ -90,7 +102,7 @@ int pack_weights_bf16(const Dims &d, const gvx_weights *w, float *packed, cudaSt
 // ---- bf16 training stash -----------------------------------------------------------------------------
 struct StashBfL {
     size_t FR, PRE1, PRE2, PM, CA, GA, CD, GD, ALIGN, CUMS, TH, CONVS, OUT, WPREV, CUM, XAI, XDI, XARM, XDRM, HCRM, PA, PD, PQ, ERR,
-        SEED, total;
+        SEED, HIMG, BAR, total;
     size_t xai_stride, xdi_stride;     // bf16 elements per frame image
     int NPAD, KSa, KSd, KSq;
     StashBfL(const Dims &d, int B, int N, int T) {
@@ -114,13 +126,15 @@ struct StashBfL {
         PQ = c.take((size_t)KSq * B * g.Tq * TC_M);
         ERR = c.take(64);
         SEED = c.take(64);
+        HIMG = c.take((size_t)64 * d.H);     // [2][H/8][64][8] bf16 ping-pong h_dec image of the persistent chain
+        BAR = c.take(64);
         total = c.o;
     }
 };
 
 struct BwdBfL {
     size_t DOUT, DOUTB, DHC, GDI, GAI, DQI, DGDRM, DGARM, DQRM, PDXD, PDXA, PS4, DCD, DCA, DCTX, DE, DCONV, DZ2, DZ1, DPM, DW, DCUM,
-        DWA, DWD, DBIAS, PART1, PART2, ONES, TMP, COLP, ERR, total;
+        DWA, DWD, DBIAS, PART1, PART2, ONES, TMP, COLP, ERR, GIMG, DXDALL, BAR, total;
     size_t pdxd_stride, pdxa_stride;   // floats per ping-pong half
     int NPAD, KSdT, KSaT, KSs4, post_blocks, colchunks;
     BwdBfL(const Dims &d, int B, int N, int T) {
@@ -152,6 +166,9 @@ struct BwdBfL {
         TMP = c.take((size_t)(d.M + 1) * d.Kp + 64);
         COLP = c.take((size_t)colchunks * 4 * (d.A > d.H ? d.A : d.H));
         ERR = c.take(64);
+        GIMG = c.take((size_t)256 * d.H);    // [2][4H/8][64][8] bf16 ping-pong d-gates image of the persistent BPTT chain
+        DXDALL = c.take(TB * (d.A + d.E));   // [T][B][A+E] d [h_att | ctx] from the decoder-LSTM input, all frames
+        BAR = c.take(64);
         total = c.o;
     }
 };
@@ -262,6 +279,17 @@ inline int gemm_nt_bf16(cudaStream_t st, int M, int N, int K, const bf16 *A, int
     return 0;
 }
 
+// C[M,N] = A[M,K] . Wm[K,N]   (all row-major)
+inline int gemm_nn_bf16(cudaStream_t st, int M, int N, int K, const bf16 *A, int lda, const bf16 *Wm, int ldw, float *Cm, int ldc) {
+    cublasHandle_t h;
+    GVX_TRY(blas(&h, st));
+    const float alpha = 1.f, beta = 0.f;
+    cublasStatus_t s = cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, N, M, K, &alpha, Wm, CUDA_R_16BF, ldw, A, CUDA_R_16BF, lda, &beta, Cm,
+                                    CUDA_R_32F, ldc, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
+    if (s != CUBLAS_STATUS_SUCCESS) { snprintf(g_err, sizeof(g_err), "cublasGemmEx(NN bf16) failed: %d", (int)s); return 1; }
+    return 0;
+}
+
 __global__ void k_add_bias_rows(float *x, size_t rows, int cols, int ld, const float *__restrict__ bias) {
     const size_t total = rows * cols;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -286,6 +314,9 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
          *HCRM = (bf16 *)(s + S.HCRM);
     int *err = (int *)(s + S.ERR);
     const bf16 *WaI = (const bf16 *)(packed + BL.WaI), *WdI = (const bf16 *)(packed + BL.WdI), *WqI = (const bf16 *)(packed + BL.WqI);
+    // persistent decoder-LSTM chain: its input part does not depend on the decoder LSTM under teacher forcing, so the
+    // attention chain runs first for all frames and the decoder-LSTM recurrence follows in ONE launch (gvx_persist.cuh)
+    const bool pc = pc_enabled() && pc_supported(d.H, B);
 
     ProfScope *ps_setup = new ProfScope(PS_SETUP, st);
     GVX_CUDA(cudaMemsetAsync(err, 0, 64 * sizeof(float), st));
@@ -343,14 +374,15 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
             a.align_out = s + S.ALIGN + (size_t)t * N; a.align_bstride = (long long)T * N;
             a.cum_stash = s + S.CUMS + (size_t)t * N;
             a.ctx_out = nullptr; a.ctx_ld = d.E;
-            add_img(a.ctx_bf, xd, d.A, NPAD); add_rm(a.ctx_bf, xdrm, d.A, d.Kd);
+            if (!pc) add_img(a.ctx_bf, xd, d.A, NPAD);
+            add_rm(a.ctx_bf, xdrm, d.A, d.Kd);
             add_img(a.ctx_bf, xa_n, d.P, NPAD); add_rm(a.ctx_bf, xarm_n, d.P, d.Ka);
             add_rm(a.ctx_bf, hcrm, d.H, d.Kp);
             a.th_stash = s + S.TH + (size_t)t * B * N * d.D;
             a.conv_stash = s + S.CONVS + (size_t)t * B * N * d.F;
             GVX_TRY(launch_attention_fwd_best(a, st));
         }
-        {   // decoder LSTM (:355-358)
+        if (!pc) {   // decoder LSTM (:355-358)
             ProfScope ps(PS_DEC_LSTM, st);
             BfDsts h;
             memset(&h, 0, sizeof(h));
@@ -359,6 +391,23 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
             GVX_TRY(run_lstm_bf16(d, packed, 1, WdI, xd, s + S.PD, S.KSd, g.Td, g.Kpd, s + S.CD + t * BH, s + S.CD + (t + 1) * BH,
                                   s + S.GD + (size_t)t * 4 * BH, h, B, seed, t, training, row_offset, err, st));
         }
+    }
+    if (pc) {   // decoder LSTM (:355-358) for all frames: time-batched input part, then the persistent recurrence
+        ProfScope ps(PS_DEC_LSTM, st);
+        GVX_TRY(gemm_nt_bf16(st, T * B, 4 * d.H, d.A + d.E, XDRM, d.Kd, (const bf16 *)(packed + BL.WdRM), d.Kd, s + S.GD, 4 * d.H));
+        GVX_CUDA(cudaMemsetAsync(s + S.HIMG, 0, (size_t)64 * d.H * sizeof(float), st));
+        PcFwdArgs f;
+        memset(&f, 0, sizeof(f));
+        f.Wimg = (const bf16 *)(packed + BL.WdhhI);
+        f.pre = s + S.GD; f.bias = packed + PL.bd;
+        f.himg = (bf16 *)(s + S.HIMG);
+        f.c_stash = s + S.CD; f.gates_stash = s + S.GD;
+        f.out[0] = PcOut{HCRM, d.Kp, 0, 0, (long long)B * d.Kp};
+        f.out[1] = PcOut{XDRM, d.Kd, d.A + d.E, 1, (long long)B * d.Kd};
+        f.bar = (unsigned *)(s + S.BAR); f.err = err;
+        f.drop = make_drop(seed, d.p_dec, training);
+        f.site = SITE_DEC; f.row_offset = row_offset; f.B = B; f.T = T; f.H = d.H;
+        GVX_TRY(launch_lstm_chain_fwd(f, st));
     }
     ProfScope ps_out(PS_OUTPUT, st);
     // mel / gate projections for all frames (:360-362): [T*B, H+E] bf16 . Wpg^T
@@ -430,13 +479,37 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     GVX_CUDA(cudaGetLastError());
     GVX_TRY(gemm_nn(st, TB, d.Kp, d.M + 1, x + W.DOUT, d.OL, packed + PL.Wpg, d.Kp, x + W.DHC, d.Kp, 0.f));
 
+    const bool pc = pc_enabled() && pc_supported(d.H, B);
+    const int AE = d.A + d.E;
+    if (pc) {
+        {   // BPTT of the decoder-LSTM recurrence for all frames in one persistent launch (gvx_persist.cuh)
+            ProfScope ps(PS_BWD_DEC_POINT, st);
+            GVX_CUDA(cudaMemsetAsync(x + W.GIMG, 0, (size_t)256 * d.H * sizeof(float), st));
+            PcBwdArgs a;
+            memset(&a, 0, sizeof(a));
+            a.Wimg = (const bf16 *)(packed + BL.WdhhTI);
+            a.gimg = (bf16 *)(x + W.GIMG);
+            a.dh_ext = x + W.DHC; a.dh_ld = d.Kp; a.dh_tstride = (long long)B * d.Kp;
+            a.gates_stash = s + S.GD; a.c_stash = s + S.CD; a.dg_rm = DGDRM;
+            a.bar = (unsigned *)(x + W.BAR); a.err = err;
+            a.drop = make_drop(seed, d.p_dec, training);
+            a.site = SITE_DEC; a.row_offset = row_offset; a.B = B; a.T = T; a.H = d.H;
+            GVX_TRY(launch_lstm_chain_bwd(a, st));
+        }
+        {   // d [h_att_t | ctx_t] from the decoder-LSTM input, all frames: d gates_dec . W_ih
+            ProfScope ps(PS_BWD_DEC_GEMM, st);
+            GVX_TRY(gemm_nn_bf16(st, TB, AE, 4 * d.H, DGDRM, 4 * d.H, (const bf16 *)(packed + BL.WdRM), d.Kd, x + W.DXDALL, AE));
+        }
+    }
+
     pdl_barrier_next();
     for (int t = T - 1; t >= 0; --t) {
         const bool last = t == T - 1;
         float *pdxd = x + W.PDXD + (size_t)(t & 1) * W.pdxd_stride, *pdxd_n = x + W.PDXD + (size_t)((t + 1) & 1) * W.pdxd_stride;
         float *pdxa = x + W.PDXA + (size_t)(t & 1) * W.pdxa_stride, *pdxa_n = x + W.PDXA + (size_t)((t + 1) & 1) * W.pdxa_stride;
         const long long sd = (long long)B * ldd, sa = (long long)B * lda;
-        {   // S1: decoder-LSTM pointwise backward
+        const float *dxd_t = x + W.DXDALL + (size_t)t * B * AE;
+        if (!pc) {   // S1: decoder-LSTM pointwise backward
             ProfScope ps(PS_BWD_DEC_POINT, st);
             BfDsts dg;
             memset(&dg, 0, sizeof(dg));
@@ -446,7 +519,7 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
                                     s + S.GD + (size_t)t * 4 * BH, s + S.CD + t * BH, s + S.CD + (t + 1) * BH, x + W.DCD, dg, B, seed,
                                     t, training, row_offset, nullptr, nullptr, nullptr, st));
         }
-        {   // S2: d x_dec = d gates_dec . W_dec
+        if (!pc) {   // S2: d x_dec = d gates_dec . W_dec
             ProfScope ps(PS_BWD_DEC_GEMM, st);
             GVX_TRY(run_tc(WdTI, GDI, pdxd, gm.TdT, gm.G4H, W.KSdT, B, err, st));
         }
@@ -459,7 +532,7 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
             a.w_t = s + S.ALIGN + (size_t)t * N; a.w_bstride = (long long)T * N;
             a.th = s + S.TH + (size_t)t * B * N * d.D;
             a.dctx1 = src_plain(x + W.DHC + (size_t)t * B * d.Kp + d.H, d.Kp);
-            a.dctx2 = src_split(pdxd + d.A, ldd, W.KSdT, sd);
+            a.dctx2 = pc ? src_plain(dxd_t + d.A, AE) : src_split(pdxd + d.A, ldd, W.KSdT, sd);
             a.dctx3 = last ? src_none() : src_split(pdxa_n + d.P, lda, W.KSaT, sa);
             a.d_align = d_align ? d_align + (size_t)t * N : nullptr; a.da_bstride = (long long)T * N;
             a.dw_carry = x + W.DW; a.dcum_carry = x + W.DCUM;
@@ -477,7 +550,8 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
             memset(&dg, 0, sizeof(dg));
             add_img(dg, GAI, 0, NPAD); add_rm(dg, DGARM + (size_t)t * B * 4 * d.A, 0, 4 * d.A);
             SrcSum dpre = last ? src_none() : src_split(pdxa_n, lda, W.KSaT, sa);
-            GVX_TRY(run_bf_lstm_bwd(d, 0, src_split(x + W.PS4, lds4, W.KSs4, (long long)B * lds4), src_split(pdxd, ldd, W.KSdT, sd),
+            GVX_TRY(run_bf_lstm_bwd(d, 0, src_split(x + W.PS4, lds4, W.KSs4, (long long)B * lds4),
+                                    pc ? src_plain(dxd_t, AE) : src_split(pdxd, ldd, W.KSdT, sd),
                                     last ? src_none() : src_split(pdxa_n + d.P + d.E, lda, W.KSaT, sa),
                                     s + S.GA + (size_t)t * 4 * BA, s + S.CA + t * BA, s + S.CA + (t + 1) * BA, x + W.DCA, dg, B, seed,
                                     t, training, row_offset, last ? nullptr : &dpre, last ? nullptr : s + S.PRE2 + (size_t)(t + 1) * B * d.P,

@@ -93,7 +93,8 @@ struct PcOut {
 // ================================================================================================ forward
 struct PcFwdArgs {
     const __nv_bfloat16 *Wimg;   // [H/8][H/8][32][8]   CTA, k-chunk, local gate row 4*lu+g, k in chunk  (W_hh)
-    const float *pre;            // [T][B][4H]  unit-major columns 4u+g: input contribution + b_ih + b_hh
+    const float *pre;            // [T][B][4H]  unit-major columns 4u+g: input contribution (may alias gates_stash)
+    const float *bias;           // [4H] unit-major b_ih + b_hh, or null
     __nv_bfloat16 *himg;         // [2][H/8][64][8]  ping-pong operand image of h; half 0 = h_{-1} (zeros), pad rows zero
     float *c_stash;              // [T+1][B][H]  row 0 = c_{-1} (caller), row t+1 written at step t
     float *gates_stash;          // [T][B][4H] gate activations (i,f,g,o per unit) or null
@@ -200,6 +201,9 @@ __global__ void __launch_bounds__(PC_THREADS, 1) k_lstm_chain_fwd(const PcFwdArg
         float c[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) c[i] = valid ? a.c_stash[(size_t)b * H + u0 + i] : 0.f;
+        float4 bi[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bi[i] = a.bias ? *reinterpret_cast<const float4 *>(a.bias + 4 * (u0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
         bool ok = true;
         for (int t = 0; t < T; ++t) {
             float4 pr[8];
@@ -221,8 +225,8 @@ __global__ void __launch_bounds__(PC_THREADS, 1) k_lstm_chain_fwd(const PcFwdArg
                 float4 *gs = a.gates_stash ? reinterpret_cast<float4 *>(a.gates_stash + ((size_t)t * a.B + b) * 4 * H + 4 * u0) : nullptr;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float gi = sigmoidf_(acc[4 * i] + pr[i].x), gf = sigmoidf_(acc[4 * i + 1] + pr[i].y);
-                    const float gg = tanhf(acc[4 * i + 2] + pr[i].z), go = sigmoidf_(acc[4 * i + 3] + pr[i].w);
+                    const float gi = sigmoidf_(acc[4 * i] + pr[i].x + bi[i].x), gf = sigmoidf_(acc[4 * i + 1] + pr[i].y + bi[i].y);
+                    const float gg = tanhf(acc[4 * i + 2] + pr[i].z + bi[i].z), go = sigmoidf_(acc[4 * i + 3] + pr[i].w + bi[i].w);
                     const float cn = gf * c[i] + gi * gg;
                     c[i] = cn;
                     hv[i] = go * tanhf(cn) * drop_mult(a.drop, a.site, (uint32_t)t, (uint32_t)(b + a.row_offset), (uint32_t)(u0 + i));
