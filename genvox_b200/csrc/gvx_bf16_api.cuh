@@ -60,8 +60,8 @@ struct PackedBfL {
         // persistent decoder-LSTM chain (gvx_persist.cuh): unit-major row-major [4H][Kd] copy for the time-batched input
         // GEMMs, resident W_hh slices for the forward chain and W_hh^T slices for BPTT
         WdRM = c.take(((size_t)4 * d.H * d.Kd + 1) / 2);
-        WdhhI = c.take((size_t)2 * d.H * d.H);
-        WdhhTI = c.take((size_t)2 * d.H * d.H);
+        WdhhI = c.take((pc_wimg_elems(d.H) + 1) / 2);
+        WdhhTI = c.take((pc_wimg_elems(d.H) + 1) / 2);
         total = c.o;
     }
 };
@@ -126,7 +126,7 @@ struct StashBfL {
         PQ = c.take((size_t)KSq * B * g.Tq * TC_M);
         ERR = c.take(64);
         SEED = c.take(64);
-        HIMG = c.take((size_t)64 * d.H);     // [2][H/8][64][8] bf16 ping-pong h_dec image of the persistent chain
+        HIMG = c.take(pc_himg_elems(d.H) / 2);     // [2][H/64][64][64] bf16 ping-pong h_dec image of the persistent chain
         BAR = c.take(64);
         total = c.o;
     }
@@ -166,7 +166,7 @@ struct BwdBfL {
         TMP = c.take((size_t)(d.M + 1) * d.Kp + 64);
         COLP = c.take((size_t)colchunks * 4 * (d.A > d.H ? d.A : d.H));
         ERR = c.take(64);
-        GIMG = c.take((size_t)256 * d.H);    // [2][4H/8][64][8] bf16 ping-pong d-gates image of the persistent BPTT chain
+        GIMG = c.take(pc_gimg_elems(d.H) / 2);     // [2][4][H/64][64][64] bf16 ping-pong d-gates image of the persistent BPTT chain
         DXDALL = c.take(TB * (d.A + d.E));   // [T][B][A+E] d [h_att | ctx] from the decoder-LSTM input, all frames
         BAR = c.take(64);
         total = c.o;
@@ -395,7 +395,7 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     if (pc) {   // decoder LSTM (:355-358) for all frames: time-batched input part, then the persistent recurrence
         ProfScope ps(PS_DEC_LSTM, st);
         GVX_TRY(gemm_nt_bf16(st, T * B, 4 * d.H, d.A + d.E, XDRM, d.Kd, (const bf16 *)(packed + BL.WdRM), d.Kd, s + S.GD, 4 * d.H));
-        GVX_CUDA(cudaMemsetAsync(s + S.HIMG, 0, (size_t)64 * d.H * sizeof(float), st));
+        GVX_CUDA(cudaMemsetAsync(s + S.HIMG, 0, pc_himg_elems(d.H) * sizeof(bf16), st));
         PcFwdArgs f;
         memset(&f, 0, sizeof(f));
         f.Wimg = (const bf16 *)(packed + BL.WdhhI);
@@ -484,7 +484,7 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     if (pc) {
         {   // BPTT of the decoder-LSTM recurrence for all frames in one persistent launch (gvx_persist.cuh)
             ProfScope ps(PS_BWD_DEC_POINT, st);
-            GVX_CUDA(cudaMemsetAsync(x + W.GIMG, 0, (size_t)256 * d.H * sizeof(float), st));
+            GVX_CUDA(cudaMemsetAsync(x + W.GIMG, 0, pc_gimg_elems(d.H) * sizeof(bf16), st));
             PcBwdArgs a;
             memset(&a, 0, sizeof(a));
             a.Wimg = (const bf16 *)(packed + BL.WdhhTI);
@@ -737,6 +737,12 @@ int check_tc_err_public(int *err_dev, cudaStream_t st, const char *what) { retur
 
 }  // namespace gvx
 
+// ---- debug hook: device buffer ([2][1024][32] long long: forward chain, backward chain) receiving clock64 stamps of CTA 0
+extern "C" int gvx_debug_timeline(void *device_buffer) {
+    gvx::pc_dbg_buffer() = (long long *)device_buffer;
+    return 0;
+}
+
 // ---- test hook: the persistent LSTM chain on its own (forward, then optionally BPTT) -----------------------------
 __global__ void k_bf16_rows_to_f32(const __nv_bfloat16 *__restrict__ x, size_t n, float *__restrict__ y) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = __bfloat162float(x[i]);
@@ -755,15 +761,15 @@ extern "C" int gvx_test_lstm_chain(const float *w_hh, const float *pre, int B, i
     const size_t TBH = (size_t)T * B * H;
     GVX_CUDA(cudaMalloc(&wimg, pc_wimg_elems(H) * 2));
     GVX_CUDA(cudaMalloc(&wimgT, pc_wimg_elems(H) * 2));
-    GVX_CUDA(cudaMalloc(&himg, (size_t)2 * H * 64 * 2));
+    GVX_CUDA(cudaMalloc(&himg, pc_himg_elems(H) * 2));
     GVX_CUDA(cudaMalloc(&hrm, TBH * 2));
-    GVX_CUDA(cudaMalloc(&gimg, (size_t)2 * 4 * H * 64 * 2));
+    GVX_CUDA(cudaMalloc(&gimg, pc_gimg_elems(H) * 2));
     GVX_CUDA(cudaMalloc(&dgrm, 4 * TBH * 2));
     GVX_CUDA(cudaMalloc(&bar, 64));
     GVX_CUDA(cudaMalloc(&err, 64));
     GVX_CUDA(cudaMemsetAsync(err, 0, 64, st));
-    GVX_CUDA(cudaMemsetAsync(himg, 0, (size_t)2 * H * 64 * 2, st));
-    GVX_CUDA(cudaMemsetAsync(gimg, 0, (size_t)2 * 4 * H * 64 * 2, st));
+    GVX_CUDA(cudaMemsetAsync(himg, 0, pc_himg_elems(H) * 2, st));
+    GVX_CUDA(cudaMemsetAsync(gimg, 0, pc_gimg_elems(H) * 2, st));
     GVX_CUDA(cudaMemsetAsync(c_out, 0, (size_t)B * H * sizeof(float), st));
     k_pc_pack_w<<<grid_for(pc_wimg_elems(H)), 256, 0, st>>>(w_hh, H, H, 0, wimg);
     k_pc_pack_w<<<grid_for(pc_wimg_elems(H)), 256, 0, st>>>(w_hh, H, H, 1, wimgT);

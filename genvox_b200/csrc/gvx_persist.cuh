@@ -35,7 +35,7 @@ namespace gvx {
 
 constexpr int PC_ROWS = 64;                               // batch rows of an activation image (B <= 64)
 constexpr int PC_N = 32;                                  // UMMA N: 8 units x 4 gates (fwd) / 32 output units (bwd)
-constexpr int PC_CHUNK_BYTES = 64 * PC_ROWS * 2;          // one TMA chunk: 64 K elements = 8 k-chunks of [64][8] bf16
+constexpr int PC_CHUNK_BYTES = 64 * PC_ROWS * 2;          // one TMA chunk = one 64-element K slab of [64 rows][128 B], SWIZZLE_128B
 constexpr int PC_MAXRING = 16;
 constexpr int PC_THREADS = 128;
 constexpr long long PC_WAIT_CYCLES = 4000000000ll;        // ~2 s of SM clock
@@ -83,6 +83,10 @@ __device__ __forceinline__ bool gbar_wait(const unsigned *ctr, unsigned target, 
 // generic-proxy global writes of other CTAs -> async-proxy (TMA) reads: fence on both sides of the barrier
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+__device__ __forceinline__ void pc_stamp(long long *dbg, int cta, int t, int k) {
+    if (dbg && cta == 0 && t < 1024) dbg[t * 32 + k] = clock64();
+}
+
 // row-major bf16 destination of the hidden state of frame t + toff (skipped when t + toff >= T)
 struct PcOut {
     __nv_bfloat16 *p;
@@ -104,18 +108,35 @@ struct PcFwdArgs {
     DropCfg drop;
     uint32_t site;
     int row_offset, B, T, H;
+    long long *dbg;              // optional timeline of CTA 0 (gvx_debug_timeline): [t][8] clock64 stamps
 };
 
-__global__ void __launch_bounds__(PC_THREADS, 1) k_lstm_chain_fwd(const PcFwdArgs a) {
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// Forward chain.  512 threads: warp 2 = TMA producer, warp 3 = MMA issuer (one elected lane each, lean single-thread
+// loops: no per-chunk empty barriers - the whole h image fits the ring and the grid barrier of step t already implies
+// that this CTA's MMAs of step t-1 have drained), warps {0,1,4,5,8,9,12,13} = epilogue: TMEM lane quadrant = warp & 1
+// (batch rows), column quarter = warp >> 2 (two hidden units per thread).
+constexpr int PCF_THREADS = 512;
+
+__global__ void __launch_bounds__(PCF_THREADS, 1) k_lstm_chain_fwd(const PcFwdArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int H = a.H, T = a.T;
-    const int img_bytes = H * 128;                         // one h image: H/8 k-chunks x 1 KB
-    const int nchunk = (img_bytes + PC_CHUNK_BYTES - 1) / PC_CHUNK_BYTES;
-    const int R = nchunk < PC_MAXRING ? nchunk : PC_MAXRING;
-    const uint32_t wbytes = (uint32_t)H * 64;              // 32 rows x H x 2 B
+    const int nchunk = (H + 63) / 64;                      // K slabs of 64 (K padded with zero columns); <= PC_MAXRING
+    const int img_bytes = nchunk * PC_CHUNK_BYTES;         // one h image: [slab][64 rows][128 B]
+    const uint32_t wbytes = (uint32_t)nchunk * 4096;       // [slab][32 rows][128 B]
     uint8_t *ring = smem;
-    uint8_t *wsm = ring + (size_t)R * PC_CHUNK_BYTES;      // the M = 128 MMA over-reads 1 KB past a chunk: lands here
+    uint8_t *wsm = ring + (size_t)nchunk * PC_CHUNK_BYTES; // the M = 128 MMA over-reads 64 rows past a slab: lands here
     PcShared *sh = (PcShared *)(wsm + wbytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, j = blockIdx.x;
     const unsigned ncta = gridDim.x;
@@ -146,22 +167,17 @@ __global__ void __launch_bounds__(PC_THREADS, 1) k_lstm_chain_fwd(const PcFwdArg
                 const uint32_t n = wbytes - off < 16384 ? wbytes - off : 16384;
                 tma_bulk_g2s(wsm + off, wsrc + off, n, &sh->wbar);
             }
-            uint32_t g = 0;
-            bool ok = true;
-            for (int t = 0; t < T && ok; ++t) {
-                if (t > 0) ok = gbar_wait(a.bar, ncta * (unsigned)t, &sh->dead, a.err, 11);
-                if (!ok) break;
-                fence_proxy_async_all();
+            for (int t = 0; t < T; ++t) {
+                if (t > 0 && !gbar_wait(a.bar, ncta * (unsigned)t, &sh->dead, a.err, 11)) break;
+                pc_stamp(a.dbg, j, t, 0);
+                fence_proxy_async_global();       // other CTAs' generic-proxy stores of h -> this thread's async-proxy reads
+                pc_stamp(a.dbg, j, t, 7);
                 const uint8_t *src = (const uint8_t *)a.himg + (size_t)(t & 1) * img_bytes;
-                for (int c = 0; c < nchunk; ++c, ++g) {
-                    const int s = g % R;
-                    const uint32_t ph = (g / R) & 1u;
-                    if (!pc_mbar_wait(sh->empty + s, ph ^ 1u, &sh->dead, a.err, 12)) { ok = false; break; }
-                    const int left = img_bytes - c * PC_CHUNK_BYTES;
-                    const uint32_t n = left < PC_CHUNK_BYTES ? left : PC_CHUNK_BYTES;
-                    mbar_expect_tx(sh->full + s, n);
-                    tma_bulk_g2s(ring + (size_t)s * PC_CHUNK_BYTES, src + (size_t)c * PC_CHUNK_BYTES, n, sh->full + s);
+                for (int c = 0; c < nchunk; ++c) {
+                    mbar_expect_tx(sh->full + c, PC_CHUNK_BYTES);
+                    tma_bulk_g2s(ring + (size_t)c * PC_CHUNK_BYTES, src + (size_t)c * PC_CHUNK_BYTES, PC_CHUNK_BYTES, sh->full + c);
                 }
+                pc_stamp(a.dbg, j, t, 1);
             }
         }
         __syncwarp();
@@ -169,85 +185,93 @@ __global__ void __launch_bounds__(PC_THREADS, 1) k_lstm_chain_fwd(const PcFwdArg
         // ------------------------------------------------ MMA issuer
         if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_bf16(128, PC_N);
-            const int nk16 = H / 16;
             bool ok = pc_mbar_wait(&sh->wbar, 0, &sh->dead, a.err, 13);
-            uint32_t g = 0;
-            const uint32_t ring_a = smem_u32(ring), w_a = smem_u32(wsm);
+            const uint64_t a0 = umma_desc_sw128(smem_u32(ring)), b0 = umma_desc_sw128(smem_u32(wsm));
             for (int t = 0; t < T && ok; ++t) {
-                for (int c = 0; c < nchunk; ++c, ++g) {
-                    const int s = g % R;
-                    const uint32_t ph = (g / R) & 1u;
-                    if (!pc_mbar_wait(sh->full + s, ph, &sh->dead, a.err, 14)) { ok = false; break; }
+                const uint32_t ph = (uint32_t)t & 1u;
+                for (int c = 0; c < nchunk; ++c) {
+                    if (!pc_mbar_wait(sh->full + c, ph, &sh->dead, a.err, 14)) { ok = false; break; }
+                    if (c < 16) pc_stamp(a.dbg, j, t, 8 + c);
                     tc_fence_after();
-                    const int k0 = c * 4, k1 = k0 + 4 < nk16 ? k0 + 4 : nk16;
-                    for (int q = k0; q < k1; ++q) {
-                        // A: h image chunk [8 k-chunks][64][8]: LBO 1 KB (between the two k-chunks of a K=16 MMA), SBO 128 B
-                        const uint64_t ad = umma_desc(ring_a + s * PC_CHUNK_BYTES + (q - k0) * 2048, 1024, 128);
-                        // B: resident weights [H/8][32][8]: LBO 512 B, SBO 128 B
-                        const uint64_t bd = umma_desc(w_a + q * 1024, 512, 128);
-                        umma_bf16(tmem_base, ad, bd, idesc, q > 0 ? 1u : 0u);
-                    }
-                    umma_commit(sh->empty + s);
+                    // descriptors advance in 16-byte units: slab stride 8 KB (A) / 4 KB (B), 32 B per K = 16 step
+                    const uint64_t ad = a0 + (uint64_t)(c * (PC_CHUNK_BYTES >> 4)), bd = b0 + (uint64_t)(c * (4096 >> 4));
+                    umma_bf16(tmem_base, ad, bd, idesc, c > 0 ? 1u : 0u);
+                    umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
+                    umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
+                    umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
                 }
                 if (ok) umma_commit(&sh->tmem_full);
+                pc_stamp(a.dbg, j, t, 2);
             }
         }
         __syncwarp();
-    } else {
-        // ------------------------------------------------ epilogue: one thread = one batch row, 8 hidden units
-        const int b = warp * 32 + lane;
+    } else if ((warp & 2) == 0) {
+        // ------------------------------------------------ epilogue: one thread = one batch row, 2 hidden units
+        const int b = (warp & 1) * 32 + lane, cq = warp >> 2;
         const bool valid = b < a.B;
-        const int u0 = 8 * j;
-        float c[8];
+        const int u0 = 8 * j + 2 * cq;
+        float c[2];
+        float4 bi[2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) c[i] = valid ? a.c_stash[(size_t)b * H + u0 + i] : 0.f;
-        float4 bi[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) bi[i] = a.bias ? *reinterpret_cast<const float4 *>(a.bias + 4 * (u0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 2; ++i) {
+            c[i] = valid ? a.c_stash[(size_t)b * H + u0 + i] : 0.f;
+            bi[i] = a.bias ? *reinterpret_cast<const float4 *>(a.bias + 4 * (u0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 1) * 32) << 16) + (uint32_t)(8 * cq);
+        // 4-byte slot of this thread inside the 16-byte chunk (units 8j..8j+7 of row b) of the swizzled h image
+        const size_t himg_off = (size_t)(j >> 3) * PC_CHUNK_BYTES + b * 128 + (((j & 7) ^ (b & 7)) << 4) + 4 * cq;
         bool ok = true;
         for (int t = 0; t < T; ++t) {
-            float4 pr[8];
+            float4 pr[2];
             if (valid) {
                 const float4 *pp = reinterpret_cast<const float4 *>(a.pre + ((size_t)t * a.B + b) * 4 * H + 4 * u0);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) pr[i] = __ldcs(pp + i);
+                pr[0] = __ldcs(pp);
+                pr[1] = __ldcs(pp + 1);
             }
             if (ok) ok = __all_sync(0xffffffffu, pc_mbar_wait(&sh->tmem_full, (uint32_t)t & 1u, &sh->dead, a.err, 15)) != 0;
-            float acc[32];
+            if (threadIdx.x == 0) pc_stamp(a.dbg, j, t, 3);
+            float acc[8];
             if (ok) {
                 tc_fence_after();
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16), acc);
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + 16u, acc + 16);
+                tmem_ld8(taddr, acc);
                 tc_fence_before();
             }
+            float4 ga[2];
+            uint32_t hp = 0u;
             if (ok && valid) {
-                float hv[8];
-                float4 *gs = a.gates_stash ? reinterpret_cast<float4 *>(a.gates_stash + ((size_t)t * a.B + b) * 4 * H + 4 * u0) : nullptr;
+                float hv[2];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 2; ++i) {
                     const float gi = sigmoidf_(acc[4 * i] + pr[i].x + bi[i].x), gf = sigmoidf_(acc[4 * i + 1] + pr[i].y + bi[i].y);
                     const float gg = tanhf(acc[4 * i + 2] + pr[i].z + bi[i].z), go = sigmoidf_(acc[4 * i + 3] + pr[i].w + bi[i].w);
                     const float cn = gf * c[i] + gi * gg;
                     c[i] = cn;
                     hv[i] = go * tanhf(cn) * drop_mult(a.drop, a.site, (uint32_t)t, (uint32_t)(b + a.row_offset), (uint32_t)(u0 + i));
-                    if (gs) gs[i] = make_float4(gi, gf, gg, go);
+                    ga[i] = make_float4(gi, gf, gg, go);
                 }
-                float4 *cs = reinterpret_cast<float4 *>(a.c_stash + ((size_t)(t + 1) * a.B + b) * H + u0);
-                cs[0] = make_float4(c[0], c[1], c[2], c[3]);
-                cs[1] = make_float4(c[4], c[5], c[6], c[7]);
-                const uint4 hp = make_uint4(pack_bf2(hv[0], hv[1]), pack_bf2(hv[2], hv[3]), pack_bf2(hv[4], hv[5]), pack_bf2(hv[6], hv[7]));
-                *reinterpret_cast<uint4 *>(a.himg + (size_t)((t + 1) & 1) * H * 64 + ((size_t)j * PC_ROWS + b) * 8) = hp;
+                hp = pack_bf2(hv[0], hv[1]);
+                // the next step's operand first: everything else is only read after the kernel and is written past the barrier
+                *reinterpret_cast<uint32_t *>((uint8_t *)a.himg + (size_t)((t + 1) & 1) * img_bytes + himg_off) = hp;
+                fence_proxy_async_global();
+            }
+            if (threadIdx.x == 0) pc_stamp(a.dbg, j, t, 4);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // release at gpu scope is cumulative over the stores ordered before it by the CTA barrier
+            if (threadIdx.x == 0) { gbar_arrive(a.bar); pc_stamp(a.dbg, j, t, 6); }
+            if (ok && valid) {
+                if (a.gates_stash) {
+                    float4 *gs = reinterpret_cast<float4 *>(a.gates_stash + ((size_t)t * a.B + b) * 4 * H + 4 * u0);
+                    gs[0] = ga[0];
+                    gs[1] = ga[1];
+                }
+                *reinterpret_cast<float2 *>(a.c_stash + ((size_t)(t + 1) * a.B + b) * H + u0) = make_float2(c[0], c[1]);
 #pragma unroll
                 for (int o = 0; o < 2; ++o) {
                     const PcOut &d = a.out[o];
                     if (d.p && t + d.toff < T)
-                        *reinterpret_cast<uint4 *>(d.p + (size_t)(t + d.toff) * d.tstride + (size_t)b * d.ld + d.koff + u0) = hp;
+                        *reinterpret_cast<uint32_t *>(d.p + (size_t)(t + d.toff) * d.tstride + (size_t)b * d.ld + d.koff + u0) = hp;
                 }
             }
-            __threadfence();
-            fence_proxy_async_all();
-            asm volatile("bar.sync 1, 64;" ::: "memory");
-            if (threadIdx.x == 0) gbar_arrive(a.bar);
         }
     }
     __syncthreads();
@@ -271,20 +295,24 @@ struct PcBwdArgs {
     DropCfg drop;
     uint32_t site;
     int row_offset, B, T, H;
+    long long *dbg;
 };
 
-__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PC_THREADS, 1) k_lstm_chain_bwd(const PcBwdArgs a) {
+// Same organisation as the forward chain: 512 threads, warp 2 = TMA, warp 3 = MMA (lean single-thread loops, no
+// per-chunk empty barriers), warps with (warp & 2) == 0 = epilogue (TMEM lane quadrant = warp & 1, column quarter =
+// warp >> 2: the thread finishes the cell backward of two hidden units of one batch row = one 16-byte image chunk).
+// Every thread of the cluster takes part in the one cluster barrier per step (the K-quarter partial exchange).
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PCF_THREADS, 1) k_lstm_chain_bwd(const PcBwdArgs a) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int H = a.H, T = a.T;
-    const int q_bytes = H * 128;                           // this CTA's K quarter of the d-gates image
-    const int nchunk = (q_bytes + PC_CHUNK_BYTES - 1) / PC_CHUNK_BYTES;
-    const int R = nchunk < PC_MAXRING ? nchunk : PC_MAXRING;
-    const uint32_t wbytes = (uint32_t)H * 64;
+    const int nchunk = (H + 63) / 64;
+    const int q_bytes = nchunk * PC_CHUNK_BYTES;           // this CTA's K quarter of the d-gates image: [slab][64 rows][128 B]
+    const uint32_t wbytes = (uint32_t)nchunk * 4096;
     uint8_t *ring = smem;
-    uint8_t *wsm = ring + (size_t)R * PC_CHUNK_BYTES;
+    uint8_t *wsm = ring + (size_t)nchunk * PC_CHUNK_BYTES;
     float *part = (float *)(wsm + wbytes);                 // [32 units][64 rows] fp32 partial of this K quarter
     PcShared *sh = (PcShared *)(part + PC_N * PC_ROWS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, j = blockIdx.x;
@@ -312,7 +340,6 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PC_THREADS, 1) k_lst
     if (warp == 2) {
         // ------------------------------------------------ TMA producer
         const bool leader = elect_one();
-        uint32_t g = 0;
         bool ok = true;
         if (leader) {
             mbar_expect_tx(&sh->wbar, wbytes);
@@ -325,17 +352,13 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PC_THREADS, 1) k_lst
         for (int i = 0; i < T; ++i) {
             if (leader && ok) {
                 if (i > 0) ok = gbar_wait(a.bar, ncta * (unsigned)i, &sh->dead, a.err, 21);
+                pc_stamp(a.dbg, j, i, 0);
                 if (ok) {
-                    fence_proxy_async_all();
+                    fence_proxy_async_global();
                     const uint8_t *src = (const uint8_t *)a.gimg + (size_t)(i & 1) * 4 * q_bytes + (size_t)s_rank * q_bytes;
-                    for (int c = 0; c < nchunk; ++c, ++g) {
-                        const int s = g % R;
-                        const uint32_t ph = (g / R) & 1u;
-                        if (!pc_mbar_wait(sh->empty + s, ph ^ 1u, &sh->dead, a.err, 22)) { ok = false; break; }
-                        const int left = q_bytes - c * PC_CHUNK_BYTES;
-                        const uint32_t n = left < PC_CHUNK_BYTES ? left : PC_CHUNK_BYTES;
-                        mbar_expect_tx(sh->full + s, n);
-                        tma_bulk_g2s(ring + (size_t)s * PC_CHUNK_BYTES, src + (size_t)c * PC_CHUNK_BYTES, n, sh->full + s);
+                    for (int c = 0; c < nchunk; ++c) {
+                        mbar_expect_tx(sh->full + c, PC_CHUNK_BYTES);
+                        tma_bulk_g2s(ring + (size_t)c * PC_CHUNK_BYTES, src + (size_t)c * PC_CHUNK_BYTES, PC_CHUNK_BYTES, sh->full + c);
                     }
                 }
             }
@@ -346,78 +369,74 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PC_THREADS, 1) k_lst
         // ------------------------------------------------ MMA issuer
         const bool leader = elect_one();
         constexpr uint32_t idesc = umma_idesc_bf16(128, PC_N);
-        const int nk16 = H / 16;
         bool ok = true;
         if (leader) ok = pc_mbar_wait(&sh->wbar, 0, &sh->dead, a.err, 23);
-        uint32_t g = 0;
-        const uint32_t ring_a = smem_u32(ring), w_a = smem_u32(wsm);
+        const uint64_t a0 = umma_desc_sw128(smem_u32(ring)), b0 = umma_desc_sw128(smem_u32(wsm));
         for (int i = 0; i < T; ++i) {
             if (leader && ok) {
-                for (int c = 0; c < nchunk; ++c, ++g) {
-                    const int s = g % R;
-                    const uint32_t ph = (g / R) & 1u;
-                    if (!pc_mbar_wait(sh->full + s, ph, &sh->dead, a.err, 24)) { ok = false; break; }
+                const uint32_t ph = (uint32_t)i & 1u;
+                for (int c = 0; c < nchunk; ++c) {
+                    if (!pc_mbar_wait(sh->full + c, ph, &sh->dead, a.err, 24)) { ok = false; break; }
                     tc_fence_after();
-                    const int k0 = c * 4, k1 = k0 + 4 < nk16 ? k0 + 4 : nk16;
-                    for (int q = k0; q < k1; ++q) {
-                        const uint64_t ad = umma_desc(ring_a + s * PC_CHUNK_BYTES + (q - k0) * 2048, 1024, 128);
-                        const uint64_t bd = umma_desc(w_a + q * 1024, 512, 128);
-                        umma_bf16(tmem_base, ad, bd, idesc, q > 0 ? 1u : 0u);
-                    }
-                    umma_commit(sh->empty + s);
+                    const uint64_t ad = a0 + (uint64_t)(c * (PC_CHUNK_BYTES >> 4)), bd = b0 + (uint64_t)(c * (4096 >> 4));
+                    umma_bf16(tmem_base, ad, bd, idesc, c > 0 ? 1u : 0u);
+                    umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
+                    umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
+                    umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
                 }
                 if (ok) umma_commit(&sh->tmem_full);
+                pc_stamp(a.dbg, j, i, 2);
             }
             __syncwarp();
             cluster.sync();
         }
-    } else {
+    } else if ((warp & 2) == 0) {
         // ------------------------------------------------ epilogue
-        const int b = warp * 32 + lane;
+        const int b = (warp & 1) * 32 + lane, cq = warp >> 2;
         const bool valid = b < a.B;
-        const int u0 = 8 * j;                              // == 32 * (j / 4) + 8 * s_rank
+        const int u0 = 8 * j + 2 * cq;                     // 8j == 32 * (j / 4) + 8 * s_rank
         const float *p0 = cluster.map_shared_rank(part, 0), *p1 = cluster.map_shared_rank(part, 1);
         const float *p2 = cluster.map_shared_rank(part, 2), *p3 = cluster.map_shared_rank(part, 3);
-        float dc[8], c_new[8];
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 1) * 32) << 16) + (uint32_t)(8 * cq);
+        // gate rows 4*u0 .. 4*u0+7 = 8-element k chunk 4j+cq of the 4H range = one 16-byte chunk of the swizzled image
+        const int kc = 4 * j + cq, quarter = kc / (H / 8), cc = kc - quarter * (H / 8);
+        const size_t gimg_off = (size_t)quarter * q_bytes + (size_t)(cc >> 3) * PC_CHUNK_BYTES + b * 128 + (((cc & 7) ^ (b & 7)) << 4);
+        float dc[2] = {0.f, 0.f}, c_new[2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            dc[i] = 0.f;
-            c_new[i] = valid ? a.c_stash[((size_t)T * a.B + b) * H + u0 + i] : 0.f;
-        }
+        for (int k = 0; k < 2; ++k) c_new[k] = valid ? a.c_stash[((size_t)T * a.B + b) * H + u0 + k] : 0.f;
         bool ok = true;
         for (int i = 0; i < T; ++i) {
             const int t = T - 1 - i;
-            float4 ga[8];
-            float c_prev[8], dhe[8];
+            float4 ga[2];
+            float c_prev[2], dhe[2];
             if (valid) {
                 const float4 *gp = reinterpret_cast<const float4 *>(a.gates_stash + ((size_t)t * a.B + b) * 4 * H + 4 * u0);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) ga[k] = __ldcs(gp + k);
-                const float4 *cp = reinterpret_cast<const float4 *>(a.c_stash + ((size_t)t * a.B + b) * H + u0);
-                const float4 c0 = __ldcs(cp), c1 = __ldcs(cp + 1);
-                c_prev[0] = c0.x; c_prev[1] = c0.y; c_prev[2] = c0.z; c_prev[3] = c0.w;
-                c_prev[4] = c1.x; c_prev[5] = c1.y; c_prev[6] = c1.z; c_prev[7] = c1.w;
-                const float *dp = a.dh_ext + (size_t)t * a.dh_tstride + (size_t)b * a.dh_ld + u0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) dhe[k] = __ldcs(dp + k);
+                ga[0] = __ldcs(gp);
+                ga[1] = __ldcs(gp + 1);
+                const float2 c2 = __ldcs(reinterpret_cast<const float2 *>(a.c_stash + ((size_t)t * a.B + b) * H + u0));
+                c_prev[0] = c2.x; c_prev[1] = c2.y;
+                const float2 d2 = __ldcs(reinterpret_cast<const float2 *>(a.dh_ext + (size_t)t * a.dh_tstride + (size_t)b * a.dh_ld + u0));
+                dhe[0] = d2.x; dhe[1] = d2.y;
             }
             if (ok) ok = __all_sync(0xffffffffu, pc_mbar_wait(&sh->tmem_full, (uint32_t)i & 1u, &sh->dead, a.err, 25)) != 0;
+            if (threadIdx.x == 0) pc_stamp(a.dbg, j, i, 3);
             if (ok) {
                 tc_fence_after();
-                float acc[32];
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16), acc);
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + 16u, acc + 16);
+                float acc[8];
+                tmem_ld8(taddr, acc);
                 tc_fence_before();
 #pragma unroll
-                for (int n = 0; n < 32; ++n) part[n * PC_ROWS + b] = acc[n];
+                for (int n = 0; n < 8; ++n) part[(8 * cq + n) * PC_ROWS + b] = acc[n];
             }
             __syncwarp();
             cluster.sync();                                // the four K-quarter partials of this cluster are in shared memory
+            if (threadIdx.x == 0) pc_stamp(a.dbg, j, i, 4);
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if (ok && valid) {
-                uint32_t dgp[16];
+                uint32_t dgp[4];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int o = (8 * s_rank + k) * PC_ROWS + b;
+                for (int k = 0; k < 2; ++k) {
+                    const int o = (8 * s_rank + 2 * cq + k) * PC_ROWS + b;
                     const float dh = dhe[k] + (((p0[o] + p1[o]) + p2[o]) + p3[o]);
                     const float mult = drop_mult(a.drop, a.site, (uint32_t)t, (uint32_t)(b + a.row_offset), (uint32_t)(u0 + k));
                     float dcp;
@@ -427,21 +446,17 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PC_THREADS, 1) k_lst
                     dgp[2 * k] = pack_bf2(d4.x, d4.y);
                     dgp[2 * k + 1] = pack_bf2(d4.z, d4.w);
                 }
-                // gate rows 4*u0 .. 4*u0+31 = k-chunks 4j .. 4j+3 of the image, 64 contiguous bytes of the row-major rows
-                __nv_bfloat16 *img = a.gimg + (size_t)((i + 1) & 1) * 4 * H * 64;
-                uint4 *rm = reinterpret_cast<uint4 *>(a.dg_rm + ((size_t)t * a.B + b) * 4 * H + 4 * u0);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint4 v = make_uint4(dgp[4 * c], dgp[4 * c + 1], dgp[4 * c + 2], dgp[4 * c + 3]);
-                    *reinterpret_cast<uint4 *>(img + ((size_t)(4 * j + c) * PC_ROWS + b) * 8) = v;
-                    rm[c] = v;
-                }
+                v = make_uint4(dgp[0], dgp[1], dgp[2], dgp[3]);
+                *reinterpret_cast<uint4 *>((uint8_t *)a.gimg + (size_t)((i + 1) & 1) * 4 * q_bytes + gimg_off) = v;
+                fence_proxy_async_global();
             }
-            __threadfence();
-            fence_proxy_async_all();
-            asm volatile("bar.sync 1, 64;" ::: "memory");
-            if (threadIdx.x == 0) gbar_arrive(a.bar);
+            if (threadIdx.x == 0) pc_stamp(a.dbg, j, i, 5);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 0) { gbar_arrive(a.bar); pc_stamp(a.dbg, j, i, 6); }
+            if (ok && valid) *reinterpret_cast<uint4 *>(a.dg_rm + ((size_t)t * a.B + b) * 4 * H + 4 * u0) = v;
         }
+    } else {
+        for (int i = 0; i < T; ++i) cluster.sync();
     }
     __syncthreads();
     cluster.sync();                                        // peers may still be reading this CTA's partial
@@ -451,34 +466,43 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PC_THREADS, 1) k_lst
 }
 
 // ================================================================================================ host side
-// recurrent-weight images.  w_hh: torch layout [4H, H] (rows g*H + u), ld = row stride.
-// mode 0 (forward):  img[j][kc][4*lu+g][e] = w_hh[g*H + 8j+lu][kc*8+e]
-// mode 1 (backward): img[j=4r+s][kc][n][e] = w_hh[g*H + u][32r+n],  4u+g = s*H + kc*8+e
+// recurrent-weight images.  w_hh: torch layout [4H, H] (rows g*H + u), ld = row stride.  Per CTA j the image is
+// [Kp/64 slabs][32 rows][128 B] in the SWIZZLE_128B K-major layout (16-byte chunk c of row r at position c ^ (r & 7)),
+// K padded to a multiple of 64 with zeros.
+// mode 0 (forward):  row r = 4*lu+g, k  ->  w_hh[g*H + 8j+lu][k]
+// mode 1 (backward): CTA j = 4r'+s, row n = output unit 32r'+n, k  ->  w_hh[g*H + u][32r'+n] with 4u+g = s*H + k
 __global__ void k_pc_pack_w(const float *__restrict__ w_hh, int ld, int H, int mode, __nv_bfloat16 *__restrict__ img) {
-    const size_t total = (size_t)(H / 8) * (H / 8) * 32 * 8;
+    const int nslab = (H + 63) / 64;
+    const size_t per_cta = (size_t)nslab * 2048;
+    const size_t total = (size_t)(H / 8) * per_cta;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int e = (int)(i & 7), r = (int)((i >> 3) & 31);
-        const size_t rest = i >> 8;
-        const int kc = (int)(rest % (H / 8)), j = (int)(rest / (H / 8));
-        float v;
-        if (mode == 0) {
-            const int lu = r >> 2, g = r & 3;
-            v = w_hh[(size_t)(g * H + 8 * j + lu) * ld + kc * 8 + e];
-        } else {
-            const int rr = j >> 2, s = j & 3;
-            const int kg = s * H + kc * 8 + e, u = kg >> 2, g = kg & 3;
-            v = w_hh[(size_t)(g * H + u) * ld + 32 * rr + r];
+        const int j = (int)(i / per_cta);
+        const int rem = (int)(i - (size_t)j * per_cta);
+        const int slab = rem >> 11, r = (rem >> 6) & 31, cpos = (rem >> 3) & 7, e = rem & 7;
+        const int k = slab * 64 + ((cpos ^ (r & 7)) << 3) + e;
+        float v = 0.f;
+        if (k < H) {
+            if (mode == 0) {
+                const int lu = r >> 2, g = r & 3;
+                v = w_hh[(size_t)(g * H + 8 * j + lu) * ld + k];
+            } else {
+                const int rr = j >> 2, sq = j & 3;
+                const int gk = sq * H + k, u = gk >> 2, g = gk & 3;
+                v = w_hh[(size_t)(g * H + u) * ld + 32 * rr + r];
+            }
         }
         img[i] = __float2bfloat16(v);
     }
 }
 
-inline size_t pc_wimg_elems(int H) { return (size_t)(H / 8) * (H / 8) * 32 * 8; }   // == 4 * H * H
+inline size_t pc_wimg_elems(int H) { return (size_t)(H / 8) * ((H + 63) / 64) * 2048; }   // == 4 * H * H when H % 64 == 0
+inline size_t pc_himg_elems(int H) { return (size_t)2 * ((H + 63) / 64) * 64 * PC_ROWS; }     // ping-pong h image (bf16 elements)
+inline size_t pc_gimg_elems(int H) { return 4 * pc_himg_elems(H); }                            // ping-pong d-gates image
 inline size_t pc_smem_bytes(int H, bool bwd) {
-    const int img_bytes = H * 128;
-    const int nchunk = (img_bytes + PC_CHUNK_BYTES - 1) / PC_CHUNK_BYTES;
-    const int R = nchunk < PC_MAXRING ? nchunk : PC_MAXRING;
-    return (size_t)R * PC_CHUNK_BYTES + (size_t)H * 64 + (bwd ? PC_N * PC_ROWS * 4 : 0) + sizeof(PcShared) + 1024 + 1024;
+    const int nchunk = (H + 63) / 64;
+    const int R = nchunk;
+    // + 8 KB: the M = 128 MMA reads 64 rows past the last ring slot (ignored accumulator lanes) - keep that inside the allocation
+    return (size_t)R * PC_CHUNK_BYTES + (size_t)nchunk * 4096 + (bwd ? PC_N * PC_ROWS * 4 : 0) + sizeof(PcShared) + 8192 + 1024;
 }
 
 // can the persistent chain run for this shape on the current device?
@@ -490,7 +514,7 @@ inline bool pc_supported(int H, int B) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     if (H % 32 != 0 || H < 32 || B < 1 || B > PC_ROWS) return false;
-    if (H / 8 > sms) return false;
+    if (H / 8 > sms || (H + 63) / 64 > PC_MAXRING) return false;
     if (pc_smem_bytes(H, true) > 227 * 1024) return false;
     return true;
 }
@@ -503,7 +527,14 @@ inline bool pc_enabled() {
     return on == 1;
 }
 
-inline int launch_lstm_chain_fwd(const PcFwdArgs &a, cudaStream_t st) {
+inline long long *&pc_dbg_buffer() {
+    static long long *p = nullptr;
+    return p;
+}
+
+inline int launch_lstm_chain_fwd(const PcFwdArgs &a_in, cudaStream_t st) {
+    PcFwdArgs a = a_in;
+    a.dbg = pc_dbg_buffer();
     const size_t smem = pc_smem_bytes(a.H, false);
     static size_t configured = 0;
     if (configured < smem) {
@@ -511,12 +542,14 @@ inline int launch_lstm_chain_fwd(const PcFwdArgs &a, cudaStream_t st) {
         configured = smem;
     }
     GVX_CUDA(cudaMemsetAsync(a.bar, 0, sizeof(unsigned), st));
-    k_lstm_chain_fwd<<<a.H / 8, PC_THREADS, smem, st>>>(a);
+    k_lstm_chain_fwd<<<a.H / 8, PCF_THREADS, smem, st>>>(a);
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     return 0;
 }
-inline int launch_lstm_chain_bwd(const PcBwdArgs &a, cudaStream_t st) {
+inline int launch_lstm_chain_bwd(const PcBwdArgs &a_in, cudaStream_t st) {
+    PcBwdArgs a = a_in;
+    a.dbg = pc_dbg_buffer() ? pc_dbg_buffer() + 32 * 1024 : nullptr;
     const size_t smem = pc_smem_bytes(a.H, true);
     static size_t configured = 0;
     if (configured < smem) {
@@ -524,7 +557,7 @@ inline int launch_lstm_chain_bwd(const PcBwdArgs &a, cudaStream_t st) {
         configured = smem;
     }
     GVX_CUDA(cudaMemsetAsync(a.bar, 0, sizeof(unsigned), st));
-    k_lstm_chain_bwd<<<a.H / 8, PC_THREADS, smem, st>>>(a);
+    k_lstm_chain_bwd<<<a.H / 8, PCF_THREADS, smem, st>>>(a);
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     return 0;

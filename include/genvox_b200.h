@@ -176,6 +176,10 @@ int gvx_test_lstm_chain(const float *w_hh, const float *pre, int B, int T, int H
                         int training, float *h_out, float *c_out, float *gates_out, const float *dh_ext,
                         float *dgates_out, void *stream);
 
+/* Debug hook: when non-null, CTA 0 of the persistent chain kernels writes clock64 stamps per step into
+ * device_buffer ([2][1024][32] int64: forward chain, backward chain).  Pass NULL to switch it off. */
+int gvx_debug_timeline(void *device_buffer);
+
 /* Prenet.forward, tacotron2.py:140-144: frames [F, B, n_mels] -> out [F, B, P]; frame f uses
  * Philox t = t0 + f.  tmp: [F, B, P] scratch for the layer-0 output. */
 int gvx_prenet_fwd(const gvx_dims *d, const gvx_weights *w, const float *frames, int F, int B,
