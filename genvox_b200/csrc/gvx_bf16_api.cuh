@@ -10,6 +10,7 @@
 #include "gvx_blas.cuh"
 #include "gvx_layout.cuh"
 #include "gvx_misc.cuh"
+#include "gvx_fused_fwd.cuh"
 #include "gvx_persist.cuh"
 
 namespace gvx {
@@ -46,7 +47,7 @@ inline int tc_pick_ks(int mtiles, int nkb) {
 
 // ---- bf16 part of the packed weights, appended after the fp32 PackedL block (offsets in floats) ----
 struct PackedBfL {
-    size_t WaI, WdI, WaTI, WdTI, WqI, WqTI, WpgI, WpgRM, WdRM, WdhhI, WdhhTI, total;
+    size_t WaI, WdI, WaTI, WdTI, WqI, WqTI, WpgI, WpgRM, WdRM, WdhhI, WdhhTI, WaRecI, WaPRM, WqB, total;
     PackedBfL(const Dims &d, size_t base) {
         const BfGeom g(d);
         Carver c;
@@ -62,6 +63,11 @@ struct PackedBfL {
         WdRM = c.take(((size_t)4 * d.H * d.Kd + 1) / 2);
         WdhhI = c.take((pc_wimg_elems(d.H) + 1) / 2);
         WdhhTI = c.take((pc_wimg_elems(d.H) + 1) / 2);
+        // fused attention chain (gvx_fused_fwd.cuh): resident recurrent weights of the attention LSTM, the prenet columns
+        // of W_ih as row-major bf16 for the time-batched input GEMM, W_q as row-major bf16
+        WaRecI = c.take(fa_wimg_elems() / 2);
+        WaPRM = c.take(((size_t)4 * d.A * d.P + 1) / 2);
+        WqB = c.take(((size_t)d.D * d.A + 1) / 2);
         total = c.o;
     }
 };
@@ -95,6 +101,12 @@ int pack_weights_bf16(const Dims &d, const gvx_weights *w, float *packed, cudaSt
         k_pc_pack_w<<<grid_for(pc_wimg_elems(d.H)), 256, 0, st>>>(w->dec_w_hh, d.H, d.H, 1, (bf16 *)(packed + BL.WdhhTI));
         GVX_LAUNCHED(2);
     }
+    if (d.A == FA_A && d.E == FA_E) {
+        k_fa_pack_w<<<grid_for(fa_wimg_elems()), 256, 0, st>>>(packed + PL.Wa, d.Ka, d.P, (bf16 *)(packed + BL.WaRecI));
+        k_to_bf16<<<grid_for((size_t)4 * d.A * d.P), 256, 0, st>>>(packed + PL.Wa, d.Ka, (size_t)4 * d.A, d.P, (bf16 *)(packed + BL.WaPRM), d.P);
+        k_to_bf16<<<grid_for((size_t)d.D * d.A), 256, 0, st>>>(w->query_w, d.A, (size_t)d.D, d.A, (bf16 *)(packed + BL.WqB), d.A);
+        GVX_LAUNCHED(3);
+    }
     GVX_CUDA(cudaGetLastError());
     return 0;
 }
@@ -102,7 +114,7 @@ int pack_weights_bf16(const Dims &d, const gvx_weights *w, float *packed, cudaSt
 // ---- bf16 training stash -----------------------------------------------------------------------------
 struct StashBfL {
     size_t FR, PRE1, PRE2, PM, CA, GA, CD, GD, ALIGN, CUMS, TH, CONVS, OUT, WPREV, CUM, XAI, XDI, XARM, XDRM, HCRM, PA, PD, PQ, ERR,
-        SEED, HIMG, BAR, total;
+        SEED, HIMG, BAR, XIMG, MEMB, BAR2, QBUF, total;
     size_t xai_stride, xdi_stride;     // bf16 elements per frame image
     int NPAD, KSa, KSd, KSq;
     StashBfL(const Dims &d, int B, int N, int T) {
@@ -128,6 +140,10 @@ struct StashBfL {
         SEED = c.take(64);
         HIMG = c.take(pc_himg_elems(d.H) / 2);     // [2][H/64][64][64] bf16 ping-pong h_dec image of the persistent chain
         BAR = c.take(64);
+        XIMG = c.take(fa_ximg_bytes() / 4);        // ping-pong [h_att | ctx] operand image of the fused attention chain
+        MEMB = c.take(((size_t)B * N * d.E + 1) / 2);     // bf16 copy of the encoder memory (context operand)
+        BAR2 = c.take(32 * 18);                    // 2 grid barriers + 16 row-group counters, one 128-byte line each
+        QBUF = c.take((size_t)2 * 64 * d.D);
         total = c.o;
     }
 };
@@ -317,12 +333,20 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     // persistent decoder-LSTM chain: its input part does not depend on the decoder LSTM under teacher forcing, so the
     // attention chain runs first for all frames and the decoder-LSTM recurrence follows in ONE launch (gvx_persist.cuh)
     const bool pc = pc_enabled() && pc_supported(d.H, B);
+    // fused attention chain: attention LSTM + query + attention of all frames in ONE persistent launch (gvx_fused_fwd.cuh)
+    const bool fa = pc && fa_enabled() && fa_supported(d, B, N);
 
     ProfScope *ps_setup = new ProfScope(PS_SETUP, st);
     GVX_CUDA(cudaMemsetAsync(err, 0, 64 * sizeof(float), st));
     // operand images start as zeros: K padding, ctx_{-1} = h_{-1} = 0 (tacotron2.py:303-315)
-    GVX_CUDA(cudaMemsetAsync(XAI, 0, (size_t)T * S.xai_stride * sizeof(bf16), st));
-    GVX_CUDA(cudaMemsetAsync(XDI, 0, (size_t)T * S.xdi_stride * sizeof(bf16), st));
+    if (!fa) {
+        GVX_CUDA(cudaMemsetAsync(XAI, 0, (size_t)T * S.xai_stride * sizeof(bf16), st));
+        GVX_CUDA(cudaMemsetAsync(XDI, 0, (size_t)T * S.xdi_stride * sizeof(bf16), st));
+    } else {
+        GVX_CUDA(cudaMemsetAsync(s + S.XIMG, 0, fa_ximg_bytes(), st));
+        k_to_bf16<<<grid_for((size_t)B * N * d.E), 256, 0, st>>>(memory, d.E, (size_t)B * N, d.E, (bf16 *)(s + S.MEMB), d.E);
+        GVX_LAUNCHED(1);
+    }
     GVX_CUDA(cudaMemsetAsync(XARM, 0, (size_t)B * d.Ka * sizeof(bf16), st));
     GVX_CUDA(cudaMemsetAsync(XDRM, 0, (size_t)B * d.Kd * sizeof(bf16), st));
     GVX_CUDA(cudaMemsetAsync(s + S.CA, 0, BA * sizeof(float), st));
@@ -335,15 +359,38 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     {
         BfDsts bf;
         memset(&bf, 0, sizeof(bf));
-        bf.d[bf.n++] = BfDst{XAI, 1, 0, NPAD, (long long)S.xai_stride};
+        if (!fa) bf.d[bf.n++] = BfDst{XAI, 1, 0, NPAD, (long long)S.xai_stride};
         bf.d[bf.n++] = BfDst{XARM, 2, 0, d.Ka, (long long)B * d.Ka};
         GVX_TRY(run_prenet(d, w, s + S.FR, d.M, T * B, B, seed, 0, row_offset, s + S.PRE1, s + S.PRE2, st, &bf));
     }
     GVX_TRY(run_processed_memory(d, w, memory, B, N, s + S.PM, st));
     delete ps_setup;
 
+    if (fa) {
+        {   // prenet part of the attention-LSTM gate pre-activations for all frames (tacotron2.py:338-340)
+            ProfScope ps(PS_ATT_LSTM, st);
+            GVX_TRY(gemm_nt_bf16(st, T * B, 4 * d.A, d.P, XARM, d.Ka, (const bf16 *)(packed + BL.WaPRM), d.P, s + S.GA, 4 * d.A));
+        }
+        ProfScope ps(PS_ATTENTION, st);
+        FaArgs f;
+        memset(&f, 0, sizeof(f));
+        f.Wimg = (const bf16 *)(packed + BL.WaRecI);
+        f.pre = s + S.GA; f.bias = packed + PL.ba;
+        f.ximg = (uint8_t *)(s + S.XIMG);
+        f.c_stash = s + S.CA; f.gates_stash = s + S.GA;
+        f.xdrm = XDRM; f.xarm = XARM; f.hcrm = HCRM;
+        f.Kd = d.Kd; f.Ka = d.Ka; f.Kp = d.Kp; f.P = d.P; f.H = d.H;
+        f.Wq = (const bf16 *)(packed + BL.WqB);
+        f.pm = s + S.PM; f.memb = (const bf16 *)(s + S.MEMB);
+        f.wlc = w->loc_conv_w; f.wldT = packed + PL.wldT; f.v = w->v_w; f.lengths = mem_lengths;
+        f.align_out = s + S.ALIGN; f.cum_stash = s + S.CUMS; f.th_stash = s + S.TH; f.conv_stash = s + S.CONVS;
+        f.bar = (unsigned *)(s + S.BAR2); f.qbuf = s + S.QBUF; f.err = err;
+        f.drop = make_drop(seed, d.p_att, training);
+        f.row_offset = row_offset; f.B = B; f.N = N; f.T = T;
+        GVX_TRY(launch_att_chain_fwd(f, st));
+    }
     pdl_barrier_next();
-    for (int t = 0; t < T; ++t) {
+    for (int t = 0; t < T && !fa; ++t) {
         const bool more = t + 1 < T;
         bf16 *xa = XAI + (size_t)t * S.xai_stride, *xd = XDI + (size_t)t * S.xdi_stride;
         bf16 *xa_n = more ? XAI + (size_t)(t + 1) * S.xai_stride : nullptr, *xd_n = more ? XDI + (size_t)(t + 1) * S.xdi_stride : nullptr;
@@ -738,6 +785,14 @@ int check_tc_err_public(int *err_dev, cudaStream_t st, const char *what) { retur
 }  // namespace gvx
 
 // ---- debug hook: device buffer ([2][1024][32] long long: forward chain, backward chain) receiving clock64 stamps of CTA 0
+// ---- debug hook: force a code path on (1) / off (0) / back to the environment default (-1)
+extern "C" int gvx_debug_option(const char *name, int value) {
+    if (!strcmp(name, "fused")) gvx::fa_mode() = value;
+    else if (!strcmp(name, "persistent")) gvx::pc_mode() = value;
+    else { snprintf(gvx::g_err, sizeof(gvx::g_err), "gvx_debug_option: unknown option %s", name); return 1; }
+    return 0;
+}
+
 extern "C" int gvx_debug_timeline(void *device_buffer) {
     gvx::pc_dbg_buffer() = (long long *)device_buffer;
     return 0;

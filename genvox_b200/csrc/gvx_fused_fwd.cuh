@@ -1,0 +1,681 @@
+// genvox_b200 — the teacher-forced ATTENTION CHAIN of the decoder in ONE persistent launch (bf16 mode).
+//
+// Per decoder step the reference runs (tacotron2.py:338-353)
+//     attention_rnn (nn.LSTMCell on [prenet_t | ctx_{t-1}], state h_att/c_att)  ->  state dropout
+//     query = query_layer(h_att_t); location conv + dense over (w_{t-1}, cum_{t-1}); energies = v . tanh(q + loc + pm)
+//     masked softmax -> w_t; ctx_t = w_t . memory; cum += w_t
+// and this chain feeds itself only through (h_att, c_att, ctx, w, cum): under teacher forcing the decoder LSTM and the
+// projections hang off it and run afterwards (gvx_persist.cuh, time-batched GEMMs).  The kernel below runs all T steps:
+//
+//   * grid = 128 CTAs (one per SM, all co-resident) in 64 clusters of 2.  CTA j owns hidden units [8j, 8j+8) of the
+//     attention LSTM: its slice of the RECURRENT weights ([32 gate rows] x [h_att | ctx] = 32 x 1536 bf16, 96 KB,
+//     SWIZZLE_128B K-major) stays in shared memory for the whole sequence, the cell state in registers.  The prenet part
+//     of the gate pre-activations does not depend on the chain and comes from one time-batched GEMM (`pre`).
+//   * per step the [64 rows x 1536] bf16 operand image (h_att_{t-1} | ctx_{t-1}), written by all CTAs, is streamed in by
+//     TMA bulk copies through a 4-slot ring and contracted on tcgen05 (UMMA 128 x 32 x 16, batch rows on the M side,
+//     accumulator in TMEM).  The h_att part (2/3 of K) is already complete while the attention phase of the previous step
+//     is still running, so its copies and MMAs overlap that phase; only the ctx part is on the critical path.
+//   * the attention phase is row-parallel: a group of 8 consecutive CTAs owns batch rows 4g..4g+3, two CTAs (one
+//     cluster) per row (token halves).  The query projection is split over the group - each CTA keeps a 16 x 1024 slice of
+//     W_q in REGISTERS as mma.sync B fragments and computes 16 dims for the 4 rows - and exchanged through a small global
+//     buffer with a release/acquire counter per group (an 8-CTA cluster would use distributed shared memory, but only 15
+//     clusters of 8 are co-resident on this part: measured, the 16th never starts); the softmax and the context are
+//     combined across the two CTAs of a row in one DSMEM exchange (local max / sum / partial context).
+//   * the location conv + dense layer of step t only needs (w_{t-1}, cum_{t-1}), which live in shared memory: they are
+//     computed BEFORE the LSTM epilogue of step t, i.e. while the tensor core contracts the ctx part.
+//   * two grid-wide barriers per step (release/acquire counters): h_att_t complete, ctx_t complete.
+//
+// Everything the backward pass needs is stashed exactly as the per-step kernels do (gvx_bf16_api.cuh).
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_bf16.h>
+
+#include "gvx_attention_fast.cuh"
+#include "gvx_persist.cuh"
+
+namespace gvx {
+
+constexpr int FA_THREADS = 512;
+constexpr int FA_NW = 448;                     // worker threads: every warp except 2 (TMA) and 3 (MMA)
+constexpr int FA_A = 1024, FA_E = 512;
+constexpr int FA_HSLAB = FA_A / 64;            // 16 K slabs of h_att
+constexpr int FA_NSLAB = (FA_A + FA_E) / 64;   // 24 K slabs of [h_att | ctx]
+constexpr int FA_RING = 4;
+constexpr int FA_MAXN = 160;
+constexpr int FA_IMG_BYTES = FA_NSLAB * PC_CHUNK_BYTES;     // one operand image: [24][64 rows][128 B]
+constexpr int FA_CLUSTER = 2;                 // the two CTAs (token halves) of one batch row
+constexpr int FA_GROUP = 8;                   // CTAs sharing 4 batch rows: they split the query projection 8 ways
+
+struct FaGeom {
+    int NH, nblk, NPS;
+    __host__ __device__ explicit FaGeom(int N) {
+        NH = (((N + 1) / 2) + 7) & ~7;
+        nblk = NH / 8;
+        NPS = NH + 40;
+    }
+};
+
+struct FaShared {
+    uint64_t full[FA_RING], empty[FA_RING], tmem_full, wbar, sbar;
+    uint32_t tmem_slot;
+    volatile int dead;
+};
+
+struct FaSmem {      // byte offsets from the 1 KB aligned base
+    int ring, wsm, lp, convT, wldT, wlc, part, ctxp, wcat, e, p, v, qfull, qred, xch, sh, total;
+    __host__ __device__ explicit FaSmem(int N) {
+        const FaGeom g(N);
+        int o = 0;
+        auto take = [&](int bytes) { int r = o; o += (bytes + 127) & ~127; return r; };
+        ring = take(FA_RING * PC_CHUNK_BYTES);
+        wsm = take(FA_NSLAB * 4096);           // also absorbs the 64-row over-read of the last ring slot
+        lp = take(g.NH * AF_D * 4);
+        convT = take(AF_F * g.NH * 4);
+        wldT = take(AF_F * AF_D * 4);
+        wlc = take(AF_F * 2 * AF_KS * 4);
+        part = take(3 * FA_E * 4);
+        ctxp = take(FA_E * 4);
+        wcat = take(2 * g.NPS * 4);
+        e = take(g.NH * 4);
+        p = take(g.NH * 4);
+        v = take(AF_D * 4);
+        qfull = take(AF_D * 4);
+        qred = take(8 * 4 * 16 * 4);
+        xch = take(64);
+        sh = take((int)sizeof(FaShared));
+        total = o + 1024;
+    }
+};
+
+struct FaArgs {
+    // ---- attention LSTM
+    const __nv_bfloat16 *Wimg;   // [128 CTAs][24 slabs][32 rows][128 B]  recurrent weights, K order [h_att | ctx]
+    const float *pre;            // [T][B][4A] unit-major: prenet contribution (may alias gates_stash)
+    const float *bias;           // [4A] unit-major b_ih + b_hh
+    uint8_t *ximg;               // [2][24][64][128 B] ping-pong operand image, zero at launch
+    float *c_stash;              // [T+1][B][A], row 0 = zeros
+    float *gates_stash;          // [T][B][4A]
+    __nv_bfloat16 *xdrm;         // [T][B][Kd]: h_att_t at column 0, ctx_t at column A
+    __nv_bfloat16 *xarm;         // [T][B][Ka]: ctx_t at column P and h_att_t at column P+E of frame t+1
+    __nv_bfloat16 *hcrm;         // [T][B][Kp]: ctx_t at column H
+    int Kd, Ka, Kp, P, H;
+    // ---- attention
+    const __nv_bfloat16 *Wq;     // [D][A] row-major bf16
+    const float *pm;             // [B][N][D]
+    const __nv_bfloat16 *memb;   // [B][N][E] bf16 copy of the encoder memory
+    const float *wlc, *wldT, *v;
+    const int64_t *lengths;
+    float *align_out;            // [B][T][N]
+    float *cum_stash;            // [B][T][N]
+    float *th_stash;             // [T][B][N][D]
+    float *conv_stash;           // [T][B][N][F]
+    unsigned *bar;               // counters 128 B apart, zero at launch: [0] h_att complete, [1] ctx complete, [2 + g] query
+                                 // slices of row group g delivered
+    float *qbuf;                 // [2][64][D] ping-pong query exchange between the 8 CTAs of a row group
+    int *err;
+    DropCfg drop;
+    int row_offset, B, N, T;
+    long long *dbg;
+    int *prog;                   // optional [3][128] progress markers (post-mortem of a stuck launch)
+};
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t caddr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(caddr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ld_cluster_f32(uint32_t caddr) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(caddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t caddr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok;
+}
+constexpr long long FA_WAIT_CYCLES = 1000000000ll;       // ~0.5 s of SM clock
+// Bounded spin shared by every software wait of the fused kernel: gives up when this CTA is already dead, when ANY CTA
+// has recorded an error (err[0] != 0: the whole grid then drains in microseconds instead of one timeout per CTA), or on
+// timeout (records `code`).
+template <class F>
+__device__ __forceinline__ bool fa_spin(F ready, volatile int *dead, int *err, int code) {
+    if (ready()) return true;
+    const long long t0 = clock64();
+    for (unsigned it = 1;; ++it) {
+        if (ready()) return true;
+        if (*dead) return false;
+        if ((it & 63u) == 0u) {
+            if (*reinterpret_cast<volatile int *>(err) != 0) { *dead = 1; return false; }
+            if (clock64() - t0 > FA_WAIT_CYCLES) {
+                *dead = 1;
+                atomicCAS(err, 0, code);
+                return false;
+            }
+        }
+    }
+}
+__device__ __forceinline__ bool fa_wait_cluster(uint64_t *bar, uint32_t parity, volatile int *dead, int *err, int code) {
+    return fa_spin([&] { return mbar_try_wait_cluster(bar, parity) != 0; }, dead, err, code);
+}
+__device__ __forceinline__ bool fa_wait_mbar(uint64_t *bar, uint32_t parity, volatile int *dead, int *err, int code) {
+    return fa_spin([&] { return mbar_try_wait(bar, parity) != 0; }, dead, err, code);
+}
+__device__ __forceinline__ bool fa_wait_gbar(const unsigned *ctr, unsigned target, volatile int *dead, int *err, int code) {
+    return fa_spin([&] { return ld_acquire_u32(ctr) >= target; }, dead, err, code);
+}
+// progress marker of CTA j / role r (0 workers, 1 TMA, 2 MMA) for post-mortems: prog[r * 128 + j] = value
+__device__ __forceinline__ void fa_mark(int *prog, int role, int cta, int value) {
+    if (prog) prog[role * 128 + cta] = value;
+}
+__device__ __forceinline__ void fa_bar_workers() { asm volatile("bar.sync 2, 448;" ::: "memory"); }
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float bf_lo(uint32_t x) { return __uint_as_float(x << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t x) { return __uint_as_float(x & 0xffff0000u); }
+
+__global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS, 1) k_att_chain_fwd(const FaArgs a) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int N = a.N, T = a.T, B = a.B;
+    const FaGeom G(N);
+    const FaSmem L(N);
+    uint8_t *ring = smem + L.ring, *wsm = smem + L.wsm;
+    float *lp = (float *)(smem + L.lp), *convT = (float *)(smem + L.convT), *wldT = (float *)(smem + L.wldT);
+    float *wlc = (float *)(smem + L.wlc), *part = (float *)(smem + L.part), *ctxp = (float *)(smem + L.ctxp);
+    float *wcat = (float *)(smem + L.wcat), *es = (float *)(smem + L.e), *ps = (float *)(smem + L.p);
+    float *vs = (float *)(smem + L.v), *qfull = (float *)(smem + L.qfull), *qred = (float *)(smem + L.qred);
+    float *xch = (float *)(smem + L.xch);
+    FaShared *sh = (FaShared *)(smem + L.sh);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, j = blockIdx.x;
+    const unsigned ncta = gridDim.x;
+    const int half = (int)cluster.block_rank(), peer = half ^ 1;      // == j & 1
+    const int grp8 = j / FA_GROUP, rank = j % FA_GROUP;                 // row group and this CTA's slot in it
+    const int row = 4 * grp8 + (rank >> 1);
+    const bool rvalid = row < B;
+    const int rowc = rvalid ? row : B - 1;
+    const int len = a.lengths ? (int)a.lengths[rowc] : N;
+    const int n_lo = half * G.NH;
+    const int n_own = max(0, min(N, n_lo + G.NH) - n_lo);
+    const int own_len = max(0, min(len, n_lo + n_own) - n_lo);
+    unsigned *bar1 = a.bar, *bar2 = a.bar + 32, *qflag = a.bar + 32 * (2 + grp8);
+    // worker index: warps 0,1,4..15 -> 0..13
+    const int widx = warp < 2 ? warp : warp - 2;
+    const int wtid = widx * 32 + lane;
+    const bool worker = warp != 2 && warp != 3;
+
+    if (tid == 0) {
+        for (int s = 0; s < FA_RING; ++s) { mbar_init(sh->full + s, 1); mbar_init(sh->empty + s, 1); }
+        mbar_init(&sh->tmem_full, 1);
+        mbar_init(&sh->wbar, 1);
+        mbar_init(&sh->sbar, 1);
+        sh->dead = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_slot)), "n"(32) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < AF_F * 2 * AF_KS; i += FA_THREADS) wlc[i] = a.wlc[i];
+    for (int i = tid; i < AF_F * AF_D / 4; i += FA_THREADS) reinterpret_cast<float4 *>(wldT)[i] = reinterpret_cast<const float4 *>(a.wldT)[i];
+    if (tid < AF_D) vs[tid] = a.v[tid];
+    for (int i = tid; i < 2 * G.NPS; i += FA_THREADS) wcat[i] = 0.f;       // w_{-1} = cum_{-1} = 0 (tacotron2.py:303-315)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sh->tmem_slot;
+    cluster.sync();          // every CTA's mbarriers are initialised before any remote arrive
+
+    if (warp == 2) {
+        // ================================================================ TMA producer
+        if (elect_one()) {
+            mbar_expect_tx(&sh->wbar, FA_NSLAB * 4096);
+            const uint8_t *wsrc = (const uint8_t *)a.Wimg + (size_t)j * FA_NSLAB * 4096;
+            for (uint32_t off = 0; off < FA_NSLAB * 4096; off += 16384) tma_bulk_g2s(wsm + off, wsrc + off, 16384, &sh->wbar);
+            int slot = 0;
+            uint32_t ph = 0;
+            bool ok = true;
+            for (int t = 0; t < T && ok; ++t) {
+                const uint8_t *src = a.ximg + (size_t)(t & 1) * FA_IMG_BYTES;
+#pragma unroll 1
+                for (int part_i = 0; part_i < 2 && ok; ++part_i) {
+                    if (t > 0) ok = fa_wait_gbar(part_i == 0 ? bar1 : bar2, ncta * (unsigned)t, &sh->dead, a.err, 31 + part_i);
+                    if (!ok) break;
+                    if (part_i == 1) pc_stamp(a.dbg, j, t, 0);
+                    fa_mark(a.prog, 1, j, 4 * t + 2 * part_i + 1);
+                    fence_proxy_async_global();
+                    const int c0 = part_i == 0 ? 0 : FA_HSLAB, c1 = part_i == 0 ? FA_HSLAB : FA_NSLAB;
+                    for (int c = c0; c < c1; ++c) {
+                        if (!fa_wait_mbar(sh->empty + slot, ph ^ 1u, &sh->dead, a.err, 33)) { ok = false; break; }
+                        mbar_expect_tx(sh->full + slot, PC_CHUNK_BYTES);
+                        tma_bulk_g2s(ring + (size_t)slot * PC_CHUNK_BYTES, src + (size_t)c * PC_CHUNK_BYTES, PC_CHUNK_BYTES, sh->full + slot);
+                        if (++slot == FA_RING) { slot = 0; ph ^= 1u; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 3) {
+        // ================================================================ MMA issuer
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, PC_N);
+            bool ok = fa_wait_mbar(&sh->wbar, 0, &sh->dead, a.err, 34);
+            const uint64_t a0 = umma_desc_sw128(smem_u32(ring)), b0 = umma_desc_sw128(smem_u32(wsm));
+            int slot = 0;
+            uint32_t ph = 0;
+            for (int t = 0; t < T && ok; ++t) {
+                for (int c = 0; c < FA_NSLAB; ++c) {
+                    if (!fa_wait_mbar(sh->full + slot, ph, &sh->dead, a.err, 35)) { ok = false; break; }
+                    tc_fence_after();
+                    const uint64_t ad = a0 + (uint64_t)(slot * (PC_CHUNK_BYTES >> 4)), bd = b0 + (uint64_t)(c * (4096 >> 4));
+                    umma_bf16(tmem_base, ad, bd, idesc, c > 0 ? 1u : 0u);
+                    umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
+                    umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
+                    umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
+                    umma_commit(sh->empty + slot);
+                    if (++slot == FA_RING) { slot = 0; ph ^= 1u; }
+                }
+                if (ok) umma_commit(&sh->tmem_full);
+                pc_stamp(a.dbg, j, t, 1);
+                fa_mark(a.prog, 2, j, t + 1);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================================================ workers
+        const bool epi = (warp & 2) == 0;                  // warps 0,1,4,5,8,9,12,13: LSTM epilogue
+        // ---- LSTM epilogue state: one batch row, two hidden units per thread
+        const int eb = (warp & 1) * 32 + lane, cq = warp >> 2;
+        const bool evalid = epi && eb < B;
+        const int u0 = 8 * j + 2 * cq;
+        float cst[2] = {0.f, 0.f};
+        float4 bi[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+        if (epi) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) bi[i] = *reinterpret_cast<const float4 *>(a.bias + 4 * (u0 + i));
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 1) * 32) << 16) + (uint32_t)(8 * cq);
+        const size_t himg_off = (size_t)(j >> 3) * PC_CHUNK_BYTES + eb * 128 + (((j & 7) ^ (eb & 7)) << 4) + 4 * cq;
+
+        // ---- query projection: warps widx 0..7 hold W_q[16 rank .. +16][128 widx .. +128] as mma.sync B fragments
+        const int g4 = lane >> 2, tig = lane & 3;
+        uint32_t wq[8][2][2];
+        if (widx < 8) {
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const __nv_bfloat16 *wrow = a.Wq + (size_t)(16 * rank + 8 * nt + g4) * FA_A + 128 * widx + 16 * s + 2 * tig;
+                    wq[s][nt][0] = *reinterpret_cast<const uint32_t *>(wrow);
+                    wq[s][nt][1] = *reinterpret_cast<const uint32_t *>(wrow + 8);
+                }
+        }
+        const int qrow = min(4 * grp8 + g4, B - 1);         // batch row whose h_att feeds A-fragment row g4 (g4 < 4)
+        const float4 v4 = *reinterpret_cast<const float4 *>(vs + lane * 4);
+        const uint32_t peer_xch = mapa_u32(smem_u32(xch), (uint32_t)peer);
+        const uint32_t peer_ps = mapa_u32(smem_u32(ps), (uint32_t)peer);
+        const uint32_t peer_ctxp = mapa_u32(smem_u32(ctxp), (uint32_t)peer);
+        const uint32_t peer_sbar = mapa_u32(smem_u32(&sh->sbar), (uint32_t)peer);
+        for (int t = 0; t < T; ++t) {
+            // ============================================================ location features of step t (w_{t-1}, cum_{t-1})
+            for (int task = wtid; task < AF_F * G.nblk; task += FA_NW) {
+                const int f = task / G.nblk, n0 = (task - f * G.nblk) * 8;
+                float acc[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) acc[jj] = 0.f;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    float x[40];
+                    const float4 *xr = reinterpret_cast<const float4 *>(wcat + c * G.NPS + n0);
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) {
+                        const float4 t4 = xr[i];
+                        x[4 * i] = t4.x; x[4 * i + 1] = t4.y; x[4 * i + 2] = t4.z; x[4 * i + 3] = t4.w;
+                    }
+                    const float *wr = wlc + (f * 2 + c) * AF_KS;
+#pragma unroll
+                    for (int k = 0; k < AF_KS; ++k) {
+                        const float wk = wr[k];
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) acc[jj] = fmaf(wk, x[jj + k], acc[jj]);
+                    }
+                }
+                float4 *dst = reinterpret_cast<float4 *>(convT + f * G.NH + n0);
+                dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
+            fa_bar_workers();
+            if (rvalid && a.conv_stash) {
+                float *cs = a.conv_stash + (((size_t)t * B + row) * N + n_lo) * AF_F;
+                for (int i = wtid; i < n_own * AF_F; i += FA_NW) cs[i] = convT[(i & 31) * G.NH + (i >> 5)];
+            }
+            {   // location dense -> lp[n][d]; a warp takes 4 tokens, a lane 4 attention dims.  (q + loc) + pm is formed at the
+                // tanh in the same order as the per-step kernels, so pm (L2 resident, read-only) is added there.
+                const int ngrp = (n_own + 3) / 4;
+                for (int grp = widx; grp < ngrp; grp += 14) {
+                    const int n0 = grp * 4;
+                    float loc[4][4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) loc[jj][i] = 0.f;
+#pragma unroll 8
+                    for (int f = 0; f < AF_F; ++f) {
+                        const float4 wd = *reinterpret_cast<const float4 *>(wldT + f * AF_D + lane * 4);
+                        const float4 c4 = *reinterpret_cast<const float4 *>(convT + f * G.NH + n0);
+                        const float cj[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            loc[jj][0] = fmaf(cj[jj], wd.x, loc[jj][0]);
+                            loc[jj][1] = fmaf(cj[jj], wd.y, loc[jj][1]);
+                            loc[jj][2] = fmaf(cj[jj], wd.z, loc[jj][2]);
+                            loc[jj][3] = fmaf(cj[jj], wd.w, loc[jj][3]);
+                        }
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+                        *reinterpret_cast<float4 *>(lp + (size_t)(n0 + jj) * AF_D + lane * 4) =
+                            make_float4(loc[jj][0], loc[jj][1], loc[jj][2], loc[jj][3]);
+                }
+            }
+
+            // ============================================================ attention LSTM cell of step t
+            if (epi) {
+                float4 pr[2];
+                if (evalid) {
+                    const float4 *pp = reinterpret_cast<const float4 *>(a.pre + ((size_t)t * B + eb) * 4 * FA_A + 4 * u0);
+                    pr[0] = __ldcs(pp);
+                    pr[1] = __ldcs(pp + 1);
+                }
+                // (the wait returns at once when the CTA is already draining; `ok` stays warp-uniform)
+                const bool ok = __all_sync(0xffffffffu, fa_wait_mbar(&sh->tmem_full, (uint32_t)t & 1u, &sh->dead, a.err, 36)) != 0;
+                if (tid == 0) { pc_stamp(a.dbg, j, t, 2); fa_mark(a.prog, 0, j, 8 * t + 1); }
+                float acc[8];
+                if (ok) {
+                    tc_fence_after();
+                    tmem_ld8(taddr, acc);
+                    tc_fence_before();
+                }
+                float4 ga[2];
+                uint32_t hp = 0u;
+                if (ok && evalid) {
+                    float hv[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const float gi = sigmoidf_(acc[4 * i] + pr[i].x + bi[i].x), gf = sigmoidf_(acc[4 * i + 1] + pr[i].y + bi[i].y);
+                        const float gg = tanhf(acc[4 * i + 2] + pr[i].z + bi[i].z), go = sigmoidf_(acc[4 * i + 3] + pr[i].w + bi[i].w);
+                        const float cn = gf * cst[i] + gi * gg;
+                        cst[i] = cn;
+                        hv[i] = go * tanhf(cn) * drop_mult(a.drop, SITE_ATT, (uint32_t)t, (uint32_t)(eb + a.row_offset), (uint32_t)(u0 + i));
+                        ga[i] = make_float4(gi, gf, gg, go);
+                    }
+                    hp = pack_bf2(hv[0], hv[1]);
+                    // what the chain itself consumes first: the next step's operand image and the rows the query reads
+                    *reinterpret_cast<uint32_t *>(a.ximg + (size_t)((t + 1) & 1) * FA_IMG_BYTES + himg_off) = hp;
+                    *reinterpret_cast<uint32_t *>(a.xdrm + ((size_t)t * B + eb) * a.Kd + u0) = hp;
+                    fence_proxy_async_global();
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (tid == 0) { gbar_arrive(bar1); pc_stamp(a.dbg, j, t, 3); }
+                if (ok && evalid) {
+                    float4 *gs = reinterpret_cast<float4 *>(a.gates_stash + ((size_t)t * B + eb) * 4 * FA_A + 4 * u0);
+                    gs[0] = ga[0];
+                    gs[1] = ga[1];
+                    *reinterpret_cast<float2 *>(a.c_stash + ((size_t)(t + 1) * B + eb) * FA_A + u0) = make_float2(cst[0], cst[1]);
+                    if (t + 1 < T) *reinterpret_cast<uint32_t *>(a.xarm + ((size_t)(t + 1) * B + eb) * a.Ka + a.P + FA_E + u0) = hp;
+                }
+            }
+
+            // ============================================================ attention of step t
+            if (tid == 0) fa_wait_gbar(bar1, ncta * (unsigned)(t + 1), &sh->dead, a.err, 37);
+            fa_bar_workers();                               // h_att_t of every unit is visible
+            if (tid == 0) { pc_stamp(a.dbg, j, t, 4); fa_mark(a.prog, 0, j, 8 * t + 2); }
+            if (widx < 8) {   // query slice: q[4 rows][16 dims] partial over k in [128 widx, +128)
+                float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+                const __nv_bfloat16 *hrow = a.xdrm + ((size_t)t * B + qrow) * a.Kd + 128 * widx + 2 * tig;
+                uint32_t ha[8][2];
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    ha[s][0] = g4 < 4 ? __ldcg(reinterpret_cast<const unsigned int *>(hrow + 16 * s)) : 0u;
+                    ha[s][1] = g4 < 4 ? __ldcg(reinterpret_cast<const unsigned int *>(hrow + 16 * s + 8)) : 0u;
+                }
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    mma_bf16_16816(c0, ha[s][0], 0u, ha[s][1], 0u, wq[s][0][0], wq[s][0][1]);
+                    mma_bf16_16816(c1, ha[s][0], 0u, ha[s][1], 0u, wq[s][1][0], wq[s][1][1]);
+                }
+                if (g4 < 4) {
+                    float *dst = qred + (widx * 4 + g4) * 16 + 2 * tig;
+                    dst[0] = c0[0]; dst[1] = c0[1];
+                    dst[8] = c1[0]; dst[9] = c1[1];
+                }
+            }
+            fa_bar_workers();
+            float *qb = a.qbuf + (size_t)(t & 1) * PC_ROWS * AF_D;
+            if (wtid < 64) {   // (row i, dim dd): fixed-order sum of the 8 K partials -> exchange buffer of the row group
+                const int i = wtid >> 4, dd = wtid & 15;
+                float q = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) q += qred[(w8 * 4 + i) * 16 + dd];
+                __stcg(qb + (size_t)(4 * grp8 + i) * AF_D + 16 * rank + dd, q);
+            }
+            fa_bar_workers();
+            if (tid == 0) {
+                gbar_arrive(qflag);                         // release: this CTA's 4 x 16 slice is in the buffer
+                fa_wait_gbar(qflag, FA_GROUP * (unsigned)(t + 1), &sh->dead, a.err, 38);
+            }
+            fa_bar_workers();
+            if (tid == 0) { pc_stamp(a.dbg, j, t, 5); fa_mark(a.prog, 0, j, 8 * t + 3); }
+            {   // energies of the own tokens
+                const float4 q4 = __ldcg(reinterpret_cast<const float4 *>(qb + (size_t)(rvalid ? row : 0) * AF_D + lane * 4));
+                const float *pm_b = a.pm + ((size_t)rowc * N + n_lo) * AF_D;
+                const int ngrp = (n_own + 3) / 4;
+                for (int grp = widx; grp < ngrp; grp += 14) {
+                    const int n0 = grp * 4;
+                    float pe[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        pe[jj] = 0.f;
+                        if (n0 + jj < n_own) {
+                            const float4 l4 = *reinterpret_cast<const float4 *>(lp + (size_t)(n0 + jj) * AF_D + lane * 4);
+                            const float4 p4 = __ldg(reinterpret_cast<const float4 *>(pm_b + (size_t)(n0 + jj) * AF_D + lane * 4));
+                            float4 th;
+                            th.x = tanh_fast((q4.x + l4.x) + p4.x);
+                            th.y = tanh_fast((q4.y + l4.y) + p4.y);
+                            th.z = tanh_fast((q4.z + l4.z) + p4.z);
+                            th.w = tanh_fast((q4.w + l4.w) + p4.w);
+                            if (rvalid && a.th_stash)
+                                __stcs(reinterpret_cast<float4 *>(a.th_stash + (((size_t)t * B + row) * N + n_lo + n0 + jj) * AF_D + lane * 4), th);
+                            pe[jj] = fmaf(v4.x, th.x, fmaf(v4.y, th.y, fmaf(v4.z, th.z, v4.w * th.w)));
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) pe[jj] += __shfl_xor_sync(0xffffffffu, pe[jj], o);
+                    }
+                    if (lane < 4) {
+                        const int nl = n0 + lane;
+                        const float pv = lane == 0 ? pe[0] : (lane == 1 ? pe[1] : (lane == 2 ? pe[2] : pe[3]));
+                        if (nl < n_own) es[nl] = (n_lo + nl) < len ? pv : -INFINITY;
+                    }
+                }
+            }
+            fa_bar_workers();
+            // local softmax statistics (every warp computes the same max: no extra barrier)
+            float mloc = -INFINITY;
+            for (int n = lane; n < n_own; n += 32) mloc = fmaxf(mloc, es[n]);
+            mloc = warp_max(mloc);
+            if (widx == 13) {
+                float s = 0.f;
+                for (int n = lane; n < n_own; n += 32) {
+                    const float pexp = mloc == -INFINITY ? 0.f : expf(es[n] - mloc);
+                    ps[n] = pexp;
+                    s += pexp;
+                }
+                s = warp_sum(s);
+                if (lane == 0) { xch[0] = mloc; xch[1] = s; }
+            } else if (wtid < 384) {
+                // partial context over the own unmasked tokens: 3 token groups x 128 column quads
+                const int tg = wtid >> 7, te = wtid & 127;
+                const __nv_bfloat16 *mem_b = a.memb + ((size_t)rowc * N + n_lo) * FA_E + 4 * te;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+                for (int n = tg; n < own_len; n += 3) {
+                    const float pexp = expf(es[n] - mloc);
+                    const uint2 m2 = __ldg(reinterpret_cast<const uint2 *>(mem_b + (size_t)n * FA_E));
+                    acc.x = fmaf(pexp, bf_lo(m2.x), acc.x); acc.y = fmaf(pexp, bf_hi(m2.x), acc.y);
+                    acc.z = fmaf(pexp, bf_lo(m2.y), acc.z); acc.w = fmaf(pexp, bf_hi(m2.y), acc.w);
+                }
+                *reinterpret_cast<float4 *>(part + tg * FA_E + 4 * te) = acc;
+            }
+            fa_bar_workers();
+            for (int e = wtid; e < FA_E; e += FA_NW) ctxp[e] = (part[e] + part[FA_E + e]) + part[2 * FA_E + e];
+            fa_bar_workers();
+            if (tid == 0) mbar_arrive_cluster(peer_sbar);    // release: this CTA's max / sum / exp / partial context are complete
+            fa_wait_cluster(&sh->sbar, (uint32_t)t & 1u, &sh->dead, a.err, 39);
+            if (tid == 0) { pc_stamp(a.dbg, j, t, 6); fa_mark(a.prog, 0, j, 8 * t + 4); }
+            {   // combine the two halves of the row (always "half 0 + half 1": both CTAs get identical values)
+                const float m_s = xch[0], s_s = xch[1];
+                const float m_p = ld_cluster_f32(peer_xch), s_p = ld_cluster_f32(peer_xch + 4);
+                const float M = fmaxf(m_s, m_p);
+                const float a_s = m_s == -INFINITY ? 0.f : expf(m_s - M), a_p = m_p == -INFINITY ? 0.f : expf(m_p - M);
+                const float S = half == 0 ? s_s * a_s + s_p * a_p : s_p * a_p + s_s * a_s;
+                if (wtid < n_own) {
+                    const int n = wtid, ng = n_lo + n;
+                    const float w = ps[n] * a_s / S;
+                    const float c_old = wcat[G.NPS + AF_PAD + n];
+                    if (rvalid) {
+                        a.align_out[((size_t)row * T + t) * N + ng] = w;
+                        if (a.cum_stash) a.cum_stash[((size_t)row * T + t) * N + ng] = c_old;
+                    }
+                    wcat[AF_PAD + n] = w;
+                    wcat[G.NPS + AF_PAD + n] = c_old + w;
+                } else if (wtid >= 96 && wtid < 96 + AF_PAD) {
+                    // 15-token halo on the peer's side: the same arithmetic the peer applies to its own tokens
+                    const int h = wtid - 96;
+                    const int pl = half == 0 ? h : G.NH - AF_PAD + h;               // peer-local token
+                    const int ng = half == 0 ? G.NH + h : pl;                        // global token
+                    const int wi = half == 0 ? AF_PAD + G.NH + h : h;                // wcat index
+                    if (ng >= 0 && ng < N) {
+                        const float w = ld_cluster_f32(peer_ps + 4 * pl) * a_p / S;
+                        wcat[wi] = w;
+                        wcat[G.NPS + wi] += w;
+                    }
+                } else if (wtid >= 128 && wtid < 160) {
+                    // this CTA finalises its half of the context columns: 8 columns per thread
+                    const int e0 = half * (FA_E / 2) + 8 * (wtid - 128);
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float cx[2];
+#pragma unroll
+                        for (int q2 = 0; q2 < 2; ++q2) {
+                            const int e = e0 + 2 * k + q2;
+                            const float mine = ctxp[e] * a_s, other = ld_cluster_f32(peer_ctxp + 4 * e) * a_p;
+                            cx[q2] = (half == 0 ? mine + other : other + mine) / S;
+                        }
+                        pk[k] = pack_bf2(cx[0], cx[1]);
+                    }
+                    const uint4 v = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    if (rvalid) {
+                        const int kc = (FA_A + e0) >> 3;                             // 16-byte chunk of the K range
+                        *reinterpret_cast<uint4 *>(a.ximg + (size_t)((t + 1) & 1) * FA_IMG_BYTES + (size_t)(kc >> 3) * PC_CHUNK_BYTES + row * 128 +
+                                                   (((kc & 7) ^ (row & 7)) << 4)) = v;
+                        fence_proxy_async_global();
+                        *reinterpret_cast<uint4 *>(a.xdrm + ((size_t)t * B + row) * a.Kd + FA_A + e0) = v;
+                        *reinterpret_cast<uint4 *>(a.hcrm + ((size_t)t * B + row) * a.Kp + a.H + e0) = v;
+                        if (t + 1 < T) *reinterpret_cast<uint4 *>(a.xarm + ((size_t)(t + 1) * B + row) * a.Ka + a.P + e0) = v;
+                    }
+                }
+            }
+            fa_bar_workers();
+            if (tid == 0) { gbar_arrive(bar2); pc_stamp(a.dbg, j, t, 7); fa_mark(a.prog, 0, j, 8 * t + 5); }
+        }
+    }
+    __syncthreads();
+    cluster.sync();          // peers may still be reading this CTA's shared memory
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(32) : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+// recurrent attention-LSTM weights of CTA j: [24 slabs][32 rows][128 B], SWIZZLE_128B; row r = packed gate row 32j + r
+// (4*unit + gate), K order [h_att | ctx].  Wa_packed: [4A][Ka] fp32, columns [prenet P | ctx E | h_att A].
+__global__ void k_fa_pack_w(const float *__restrict__ Wa_packed, int Ka, int P, __nv_bfloat16 *__restrict__ img) {
+    const size_t per_cta = (size_t)FA_NSLAB * 2048, total = 128 * per_cta;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i / per_cta);
+        const int rem = (int)(i - (size_t)j * per_cta);
+        const int slab = rem >> 11, r = (rem >> 6) & 31, cpos = (rem >> 3) & 7, e = rem & 7;
+        const int k = slab * 64 + ((cpos ^ (r & 7)) << 3) + e;
+        const int col = k < FA_A ? P + FA_E + k : P + (k - FA_A);
+        img[i] = __float2bfloat16(Wa_packed[(size_t)(32 * j + r) * Ka + col]);
+    }
+}
+inline size_t fa_wimg_elems() { return (size_t)128 * FA_NSLAB * 2048; }
+inline size_t fa_ximg_bytes() { return (size_t)2 * FA_IMG_BYTES; }
+
+inline bool fa_supported(const Dims &d, int B, int N) {
+    static int sms = -1;
+    if (sms < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (d.A != FA_A || d.E != FA_E || d.D != AF_D || d.F != AF_F || d.KS != AF_KS) return false;
+    if (B < 1 || B > PC_ROWS || N < 1 || N > FA_MAXN || sms < 128) return false;
+    if (d.P % 8 != 0 || d.H % 8 != 0) return false;
+    return FaSmem(N).total <= 227 * 1024;
+}
+inline int &fa_mode() {        // -1 = not yet read from the environment, 0 = off, 1 = on
+    static int on = -1;
+    return on;
+}
+inline bool fa_enabled() {
+    int &on = fa_mode();
+    if (on < 0) {
+        const char *e = getenv("GVX_FUSED");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
+inline int launch_att_chain_fwd(const FaArgs &a_in, cudaStream_t st) {
+    FaArgs a = a_in;
+    a.dbg = pc_dbg_buffer();
+    a.prog = pc_dbg_buffer() ? (int *)(pc_dbg_buffer() + 2 * 32 * 1024) : nullptr;     // third plane of the debug buffer
+    const size_t smem = FaSmem(a.N).total;
+    static size_t configured = 0;
+    if (configured < smem) {
+        GVX_CUDA(cudaFuncSetAttribute(k_att_chain_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    GVX_CUDA(cudaMemsetAsync(a.bar, 0, 32 * 18 * sizeof(unsigned), st));
+    k_att_chain_fwd<<<128, FA_THREADS, smem, st>>>(a);
+    GVX_LAUNCHED(1);
+    GVX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace gvx

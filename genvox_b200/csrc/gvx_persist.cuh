@@ -518,8 +518,12 @@ inline bool pc_supported(int H, int B) {
     if (pc_smem_bytes(H, true) > 227 * 1024) return false;
     return true;
 }
-inline bool pc_enabled() {
+inline int &pc_mode() {        // -1 = not yet read from the environment, 0 = off, 1 = on
     static int on = -1;
+    return on;
+}
+inline bool pc_enabled() {
+    int &on = pc_mode();
     if (on < 0) {
         const char *e = getenv("GVX_PERSISTENT");
         on = (e && e[0] == '0') ? 0 : 1;

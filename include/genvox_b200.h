@@ -180,6 +180,11 @@ int gvx_test_lstm_chain(const float *w_hh, const float *pre, int B, int T, int H
  * device_buffer ([2][1024][32] int64: forward chain, backward chain).  Pass NULL to switch it off. */
 int gvx_debug_timeline(void *device_buffer);
 
+/* Debug hook: force a code path on (1), off (0) or back to its environment default (-1).  Options: "fused" (the
+ * persistent attention chain, env GVX_FUSED), "persistent" (the persistent decoder-LSTM chains, env GVX_PERSISTENT).
+ * The parity tests use it to compare the fused and the per-step paths on the same inputs. */
+int gvx_debug_option(const char *name, int value);
+
 /* Prenet.forward, tacotron2.py:140-144: frames [F, B, n_mels] -> out [F, B, P]; frame f uses
  * Philox t = t0 + f.  tmp: [F, B, P] scratch for the layer-0 output. */
 int gvx_prenet_fwd(const gvx_dims *d, const gvx_weights *w, const float *frames, int F, int B,
