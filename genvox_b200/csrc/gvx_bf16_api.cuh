@@ -143,7 +143,7 @@ struct StashBfL {
         XIMG = c.take(fa_ximg_bytes() / 4);        // ping-pong [h_att | ctx] operand image of the fused attention chain
         MEMB = c.take(((size_t)B * N * d.E + 1) / 2);     // bf16 copy of the encoder memory (context operand)
         BAR2 = c.take(32 * 18);                    // 2 grid barriers + 16 row-group counters, one 128-byte line each
-        QBUF = c.take((size_t)2 * 64 * d.D);
+        QBUF = c.take((size_t)2 * 2 * 64 * d.D);   // 64-bit (value, tag) words
         total = c.o;
     }
 };
@@ -384,7 +384,7 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
         f.pm = s + S.PM; f.memb = (const bf16 *)(s + S.MEMB);
         f.wlc = w->loc_conv_w; f.wldT = packed + PL.wldT; f.v = w->v_w; f.lengths = mem_lengths;
         f.align_out = s + S.ALIGN; f.cum_stash = s + S.CUMS; f.th_stash = s + S.TH; f.conv_stash = s + S.CONVS;
-        f.bar = (unsigned *)(s + S.BAR2); f.qbuf = s + S.QBUF; f.err = err;
+        f.bar = (unsigned *)(s + S.BAR2); f.qbuf = (unsigned long long *)(s + S.QBUF); f.err = err;
         f.drop = make_drop(seed, d.p_att, training);
         f.row_offset = row_offset; f.B = B; f.N = N; f.T = T;
         GVX_TRY(launch_att_chain_fwd(f, st));
@@ -784,7 +784,7 @@ int check_tc_err_public(int *err_dev, cudaStream_t st, const char *what) { retur
 
 }  // namespace gvx
 
-// ---- debug hook: device buffer ([2][1024][32] long long: forward chain, backward chain) receiving clock64 stamps of CTA 0
+// ---- debug hook: device buffer ([4][1024][32] long long: decoder-LSTM forward chain, backward chain, progress markers, fused attention chain) receiving clock64 stamps of CTA 0
 // ---- debug hook: force a code path on (1) / off (0) / back to the environment default (-1)
 extern "C" int gvx_debug_option(const char *name, int value) {
     if (!strcmp(name, "fused")) gvx::fa_mode() = value;

@@ -62,18 +62,17 @@ struct FaShared {
 };
 
 struct FaSmem {      // byte offsets from the 1 KB aligned base
-    int ring, wsm, lp, convT, wldT, wlc, part, ctxp, wcat, e, p, v, qfull, qred, xch, sh, total;
+    int ring, wsm, lp, convT, wldT, wlc, ctxp, wcat, e, p, v, qfull, qred, xch, sh, total;
     __host__ __device__ explicit FaSmem(int N) {
         const FaGeom g(N);
         int o = 0;
         auto take = [&](int bytes) { int r = o; o += (bytes + 127) & ~127; return r; };
         ring = take(FA_RING * PC_CHUNK_BYTES);
         wsm = take(FA_NSLAB * 4096);           // also absorbs the 64-row over-read of the last ring slot
-        lp = take(g.NH * AF_D * 4);
+        lp = take(g.NH * AF_D * 4 > 7 * FA_E * 4 ? g.NH * AF_D * 4 : 7 * FA_E * 4);     // also the [7][512] partial contexts
         convT = take(AF_F * g.NH * 4);
         wldT = take(AF_F * AF_D * 4);
         wlc = take(AF_F * 2 * AF_KS * 4);
-        part = take(3 * FA_E * 4);
         ctxp = take(FA_E * 4);
         wcat = take(2 * g.NPS * 4);
         e = take(g.NH * 4);
@@ -111,7 +110,8 @@ struct FaArgs {
     float *conv_stash;           // [T][B][N][F]
     unsigned *bar;               // counters 128 B apart, zero at launch: [0] h_att complete, [1] ctx complete, [2 + g] query
                                  // slices of row group g delivered
-    float *qbuf;                 // [2][64][D] ping-pong query exchange between the 8 CTAs of a row group
+    unsigned long long *qbuf;    // [2][64][D] ping-pong query exchange between the 8 CTAs of a row group: (value, step tag)
+                                 // pairs in one 64-bit word, zero at launch
     int *err;
     DropCfg drop;
     int row_offset, B, N, T;
@@ -177,6 +177,11 @@ __device__ __forceinline__ bool fa_wait_gbar(const unsigned *ctr, unsigned targe
     return fa_spin([&] { return ld_acquire_u32(ctr) >= target; }, dead, err, code);
 }
 // progress marker of CTA j / role r (0 workers, 1 TMA, 2 MMA) for post-mortems: prog[r * 128 + j] = value
+__device__ __forceinline__ long long fa_globaltimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void fa_mark(int *prog, int role, int cta, int value) {
     if (prog) prog[role * 128 + cta] = value;
 }
@@ -185,6 +190,21 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float sigmoid_fast(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+    return r;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ float bf_lo(uint32_t x) { return __uint_as_float(x << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t x) { return __uint_as_float(x & 0xffff0000u); }
@@ -199,7 +219,8 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
     const FaSmem L(N);
     uint8_t *ring = smem + L.ring, *wsm = smem + L.wsm;
     float *lp = (float *)(smem + L.lp), *convT = (float *)(smem + L.convT), *wldT = (float *)(smem + L.wldT);
-    float *wlc = (float *)(smem + L.wlc), *part = (float *)(smem + L.part), *ctxp = (float *)(smem + L.ctxp);
+    float *wlc = (float *)(smem + L.wlc), *ctxp = (float *)(smem + L.ctxp);
+    float *part = lp;        // [7][512] partial contexts: lp is dead between the energies and the next location phase
     float *wcat = (float *)(smem + L.wcat), *es = (float *)(smem + L.e), *ps = (float *)(smem + L.p);
     float *vs = (float *)(smem + L.v), *qfull = (float *)(smem + L.qfull), *qred = (float *)(smem + L.qred);
     float *xch = (float *)(smem + L.xch);
@@ -222,6 +243,7 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
     const int wtid = widx * 32 + lane;
     const bool worker = warp != 2 && warp != 3;
 
+    if (tid == 0 && j == 0 && a.dbg) a.dbg[9] = fa_globaltimer();
     if (tid == 0) {
         for (int s = 0; s < FA_RING; ++s) { mbar_init(sh->full + s, 1); mbar_init(sh->empty + s, 1); }
         mbar_init(&sh->tmem_full, 1);
@@ -244,6 +266,7 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
     tc_fence_after();
     const uint32_t tmem_base = sh->tmem_slot;
     cluster.sync();          // every CTA's mbarriers are initialised before any remote arrive
+    if (tid == 0 && j == 0 && a.dbg) a.dbg[10] = fa_globaltimer();
 
     if (warp == 2) {
         // ================================================================ TMA producer
@@ -368,11 +391,17 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                 float *cs = a.conv_stash + (((size_t)t * B + row) * N + n_lo) * AF_F;
                 for (int i = wtid; i < n_own * AF_F; i += FA_NW) cs[i] = convT[(i & 31) * G.NH + (i >> 5)];
             }
-            {   // location dense -> lp[n][d]; a warp takes 4 tokens, a lane 4 attention dims.  (q + loc) + pm is formed at the
-                // tanh in the same order as the per-step kernels, so pm (L2 resident, read-only) is added there.
+            {   // location dense + processed memory -> lp[n][d]; a warp takes 4 tokens, a lane 4 attention dims.  The processed
+                // memory rows (L2 resident, read-only) are requested first and land while the FFMA loop runs.
+                const float *pm_b = a.pm + ((size_t)rowc * N + n_lo) * AF_D;
                 const int ngrp = (n_own + 3) / 4;
                 for (int grp = widx; grp < ngrp; grp += 14) {
                     const int n0 = grp * 4;
+                    float4 pmv[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+                        pmv[jj] = n0 + jj < n_own ? __ldg(reinterpret_cast<const float4 *>(pm_b + (size_t)(n0 + jj) * AF_D + lane * 4))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
                     float loc[4][4];
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj)
@@ -394,9 +423,10 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj)
                         *reinterpret_cast<float4 *>(lp + (size_t)(n0 + jj) * AF_D + lane * 4) =
-                            make_float4(loc[jj][0], loc[jj][1], loc[jj][2], loc[jj][3]);
+                            make_float4(loc[jj][0] + pmv[jj].x, loc[jj][1] + pmv[jj].y, loc[jj][2] + pmv[jj].z, loc[jj][3] + pmv[jj].w);
                 }
             }
+            if (tid == 0) pc_stamp(a.dbg, j, t, 12);
 
             // ============================================================ attention LSTM cell of step t
             if (epi) {
@@ -421,11 +451,12 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                     float hv[2];
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        const float gi = sigmoidf_(acc[4 * i] + pr[i].x + bi[i].x), gf = sigmoidf_(acc[4 * i + 1] + pr[i].y + bi[i].y);
-                        const float gg = tanhf(acc[4 * i + 2] + pr[i].z + bi[i].z), go = sigmoidf_(acc[4 * i + 3] + pr[i].w + bi[i].w);
+                        // SFU activations (ex2 / rcp, abs. error ~2e-7); the stashed activations are what BPTT differentiates
+                        const float gi = sigmoid_fast(acc[4 * i] + pr[i].x + bi[i].x), gf = sigmoid_fast(acc[4 * i + 1] + pr[i].y + bi[i].y);
+                        const float gg = tanh_fast(acc[4 * i + 2] + pr[i].z + bi[i].z), go = sigmoid_fast(acc[4 * i + 3] + pr[i].w + bi[i].w);
                         const float cn = gf * cst[i] + gi * gg;
                         cst[i] = cn;
-                        hv[i] = go * tanhf(cn) * drop_mult(a.drop, SITE_ATT, (uint32_t)t, (uint32_t)(eb + a.row_offset), (uint32_t)(u0 + i));
+                        hv[i] = go * tanh_fast(cn) * drop_mult(a.drop, SITE_ATT, (uint32_t)t, (uint32_t)(eb + a.row_offset), (uint32_t)(u0 + i));
                         ga[i] = make_float4(gi, gf, gg, go);
                     }
                     hp = pack_bf2(hv[0], hv[1]);
@@ -470,24 +501,35 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                 }
             }
             fa_bar_workers();
-            float *qb = a.qbuf + (size_t)(t & 1) * PC_ROWS * AF_D;
-            if (wtid < 64) {   // (row i, dim dd): fixed-order sum of the 8 K partials -> exchange buffer of the row group
+            unsigned long long *qb = a.qbuf + (size_t)(t & 1) * PC_ROWS * AF_D;
+            if (wtid < 64) {   // (row i, dim dd): fixed-order sum of the 8 K partials -> exchange buffer of the row group.
+                // value and step tag travel in ONE 64-bit word: the consumers poll the data itself, no separate flag
                 const int i = wtid >> 4, dd = wtid & 15;
                 float q = 0.f;
 #pragma unroll
                 for (int w8 = 0; w8 < 8; ++w8) q += qred[(w8 * 4 + i) * 16 + dd];
-                __stcg(qb + (size_t)(4 * grp8 + i) * AF_D + 16 * rank + dd, q);
-            }
-            fa_bar_workers();
-            if (tid == 0) {
-                gbar_arrive(qflag);                         // release: this CTA's 4 x 16 slice is in the buffer
-                fa_wait_gbar(qflag, FA_GROUP * (unsigned)(t + 1), &sh->dead, a.err, 38);
+                st_relaxed_u64(qb + (size_t)(4 * grp8 + i) * AF_D + 16 * rank + dd,
+                               ((unsigned long long)(unsigned)(t + 1) << 32) | (unsigned long long)__float_as_uint(q));
+            } else if (widx == 13) {
+                // one warp collects the 128 dims of this CTA's row (4 per lane) and stages them in shared memory
+                const unsigned long long *src = qb + (size_t)(rvalid ? row : 0) * AF_D + 4 * lane;
+                float qv[4] = {0.f, 0.f, 0.f, 0.f};
+                fa_spin([&] {
+                    bool all = true;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const unsigned long long w = ld_relaxed_u64(src + k);
+                        all = all && (unsigned)(w >> 32) == (unsigned)(t + 1);
+                        qv[k] = __uint_as_float((unsigned)w);
+                    }
+                    return all;
+                }, &sh->dead, a.err, 38);
+                *reinterpret_cast<float4 *>(qfull + 4 * lane) = make_float4(qv[0], qv[1], qv[2], qv[3]);
             }
             fa_bar_workers();
             if (tid == 0) { pc_stamp(a.dbg, j, t, 5); fa_mark(a.prog, 0, j, 8 * t + 3); }
             {   // energies of the own tokens
-                const float4 q4 = __ldcg(reinterpret_cast<const float4 *>(qb + (size_t)(rvalid ? row : 0) * AF_D + lane * 4));
-                const float *pm_b = a.pm + ((size_t)rowc * N + n_lo) * AF_D;
+                const float4 q4 = *reinterpret_cast<const float4 *>(qfull + lane * 4);
                 const int ngrp = (n_own + 3) / 4;
                 for (int grp = widx; grp < ngrp; grp += 14) {
                     const int n0 = grp * 4;
@@ -497,12 +539,11 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                         pe[jj] = 0.f;
                         if (n0 + jj < n_own) {
                             const float4 l4 = *reinterpret_cast<const float4 *>(lp + (size_t)(n0 + jj) * AF_D + lane * 4);
-                            const float4 p4 = __ldg(reinterpret_cast<const float4 *>(pm_b + (size_t)(n0 + jj) * AF_D + lane * 4));
                             float4 th;
-                            th.x = tanh_fast((q4.x + l4.x) + p4.x);
-                            th.y = tanh_fast((q4.y + l4.y) + p4.y);
-                            th.z = tanh_fast((q4.z + l4.z) + p4.z);
-                            th.w = tanh_fast((q4.w + l4.w) + p4.w);
+                            th.x = tanh_fast(q4.x + l4.x);
+                            th.y = tanh_fast(q4.y + l4.y);
+                            th.z = tanh_fast(q4.z + l4.z);
+                            th.w = tanh_fast(q4.w + l4.w);
                             if (rvalid && a.th_stash)
                                 __stcs(reinterpret_cast<float4 *>(a.th_stash + (((size_t)t * B + row) * N + n_lo + n0 + jj) * AF_D + lane * 4), th);
                             pe[jj] = fmaf(v4.x, th.x, fmaf(v4.y, th.y, fmaf(v4.z, th.z, v4.w * th.w)));
@@ -525,31 +566,54 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
             float mloc = -INFINITY;
             for (int n = lane; n < n_own; n += 32) mloc = fmaxf(mloc, es[n]);
             mloc = warp_max(mloc);
-            if (widx == 13) {
-                float s = 0.f;
-                for (int n = lane; n < n_own; n += 32) {
-                    const float pexp = mloc == -INFINITY ? 0.f : expf(es[n] - mloc);
-                    ps[n] = pexp;
-                    s += pexp;
+            {
+                // partial context over the own unmasked tokens: 7 token groups x 64 column octets, every 16-byte load of the
+                // bf16 memory rows issued before the first use (one L2 round trip instead of one per small batch)
+                const int tg = wtid >> 6, te = wtid & 63;
+                const __nv_bfloat16 *mem_b = a.memb + ((size_t)rowc * N + n_lo) * FA_E + 8 * te;
+                constexpr int HB = 7;                                // loads in flight per thread; 2 batches cover 98 tokens
+                static_assert(2 * 7 * HB >= (FA_MAXN / 2 + 7), "token groups do not cover the own tokens");
+                if (widx == 13) {   // (this warp also publishes the exponentials and their sum)
+                    float s = 0.f;
+                    for (int n = lane; n < n_own; n += 32) {
+                        const float pexp = mloc == -INFINITY ? 0.f : expf(es[n] - mloc);
+                        ps[n] = pexp;
+                        s += pexp;
+                    }
+                    s = warp_sum(s);
+                    if (lane == 0) { xch[0] = mloc; xch[1] = s; }
                 }
-                s = warp_sum(s);
-                if (lane == 0) { xch[0] = mloc; xch[1] = s; }
-            } else if (wtid < 384) {
-                // partial context over the own unmasked tokens: 3 token groups x 128 column quads
-                const int tg = wtid >> 7, te = wtid & 127;
-                const __nv_bfloat16 *mem_b = a.memb + ((size_t)rowc * N + n_lo) * FA_E + 4 * te;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-                for (int n = tg; n < own_len; n += 3) {
-                    const float pexp = expf(es[n] - mloc);
-                    const uint2 m2 = __ldg(reinterpret_cast<const uint2 *>(mem_b + (size_t)n * FA_E));
-                    acc.x = fmaf(pexp, bf_lo(m2.x), acc.x); acc.y = fmaf(pexp, bf_hi(m2.x), acc.y);
-                    acc.z = fmaf(pexp, bf_lo(m2.y), acc.z); acc.w = fmaf(pexp, bf_hi(m2.y), acc.w);
+                float acc[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    uint4 mv[HB];
+#pragma unroll
+                    for (int i = 0; i < HB; ++i) {
+                        const int n = tg + 7 * (HB * hb + i);
+                        mv[i] = n < own_len ? __ldg(reinterpret_cast<const uint4 *>(mem_b + (size_t)n * FA_E)) : make_uint4(0u, 0u, 0u, 0u);
+                    }
+#pragma unroll
+                    for (int i = 0; i < HB; ++i) {
+                        const int n = tg + 7 * (HB * hb + i);
+                        if (n < own_len) {
+                            const float pexp = expf(es[n] - mloc);
+                            acc[0] = fmaf(pexp, bf_lo(mv[i].x), acc[0]); acc[1] = fmaf(pexp, bf_hi(mv[i].x), acc[1]);
+                            acc[2] = fmaf(pexp, bf_lo(mv[i].y), acc[2]); acc[3] = fmaf(pexp, bf_hi(mv[i].y), acc[3]);
+                            acc[4] = fmaf(pexp, bf_lo(mv[i].z), acc[4]); acc[5] = fmaf(pexp, bf_hi(mv[i].z), acc[5]);
+                            acc[6] = fmaf(pexp, bf_lo(mv[i].w), acc[6]); acc[7] = fmaf(pexp, bf_hi(mv[i].w), acc[7]);
+                        }
+                    }
                 }
-                *reinterpret_cast<float4 *>(part + tg * FA_E + 4 * te) = acc;
+                float4 *dst = reinterpret_cast<float4 *>(part + tg * FA_E + 8 * te);
+                dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
             }
             fa_bar_workers();
-            for (int e = wtid; e < FA_E; e += FA_NW) ctxp[e] = (part[e] + part[FA_E + e]) + part[2 * FA_E + e];
+            for (int e = wtid; e < FA_E; e += FA_NW)
+                ctxp[e] = ((part[e] + part[FA_E + e]) + (part[2 * FA_E + e] + part[3 * FA_E + e])) +
+                          ((part[4 * FA_E + e] + part[5 * FA_E + e]) + part[6 * FA_E + e]);
             fa_bar_workers();
             if (tid == 0) mbar_arrive_cluster(peer_sbar);    // release: this CTA's max / sum / exp / partial context are complete
             fa_wait_cluster(&sh->sbar, (uint32_t)t & 1u, &sh->dead, a.err, 39);
@@ -584,14 +648,16 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                 } else if (wtid >= 128 && wtid < 160) {
                     // this CTA finalises its half of the context columns: 8 columns per thread
                     const int e0 = half * (FA_E / 2) + 8 * (wtid - 128);
+                    float oth[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) oth[k] = ld_cluster_f32(peer_ctxp + 4 * (e0 + k));
                     uint32_t pk[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         float cx[2];
 #pragma unroll
                         for (int q2 = 0; q2 < 2; ++q2) {
-                            const int e = e0 + 2 * k + q2;
-                            const float mine = ctxp[e] * a_s, other = ld_cluster_f32(peer_ctxp + 4 * e) * a_p;
+                            const float mine = ctxp[e0 + 2 * k + q2] * a_s, other = oth[2 * k + q2] * a_p;
                             cx[q2] = (half == 0 ? mine + other : other + mine) / S;
                         }
                         pk[k] = pack_bf2(cx[0], cx[1]);
@@ -609,11 +675,17 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                 }
             }
             fa_bar_workers();
-            if (tid == 0) { gbar_arrive(bar2); pc_stamp(a.dbg, j, t, 7); fa_mark(a.prog, 0, j, 8 * t + 5); }
+            if (tid == 0) {
+                gbar_arrive(bar2);
+                pc_stamp(a.dbg, j, t, 7);
+                fa_mark(a.prog, 0, j, 8 * t + 5);
+                if (j == 0 && a.dbg && t < 1024) a.dbg[t * 32 + 8] = fa_globaltimer();
+            }
         }
     }
     __syncthreads();
     cluster.sync();          // peers may still be reading this CTA's shared memory
+    if (tid == 0 && j == 0 && a.dbg) a.dbg[11] = fa_globaltimer();
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(32) : "memory");
     }
@@ -663,7 +735,7 @@ inline bool fa_enabled() {
 
 inline int launch_att_chain_fwd(const FaArgs &a_in, cudaStream_t st) {
     FaArgs a = a_in;
-    a.dbg = pc_dbg_buffer();
+    a.dbg = pc_dbg_buffer() ? pc_dbg_buffer() + 3 * 32 * 1024 : nullptr;                // fourth plane: fused-chain stamps
     a.prog = pc_dbg_buffer() ? (int *)(pc_dbg_buffer() + 2 * 32 * 1024) : nullptr;     // third plane of the debug buffer
     const size_t smem = FaSmem(a.N).total;
     static size_t configured = 0;
@@ -672,6 +744,7 @@ inline int launch_att_chain_fwd(const FaArgs &a_in, cudaStream_t st) {
         configured = smem;
     }
     GVX_CUDA(cudaMemsetAsync(a.bar, 0, 32 * 18 * sizeof(unsigned), st));
+    GVX_CUDA(cudaMemsetAsync(a.qbuf, 0, (size_t)2 * PC_ROWS * AF_D * sizeof(unsigned long long), st));
     k_att_chain_fwd<<<128, FA_THREADS, smem, st>>>(a);
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());

@@ -177,7 +177,7 @@ int gvx_test_lstm_chain(const float *w_hh, const float *pre, int B, int T, int H
                         float *dgates_out, void *stream);
 
 /* Debug hook: when non-null, CTA 0 of the persistent chain kernels writes clock64 stamps per step into
- * device_buffer ([2][1024][32] int64: forward chain, backward chain).  Pass NULL to switch it off. */
+ * device_buffer ([4][1024][32] int64: decoder-LSTM forward chain, backward chain, progress markers, fused attention chain).  Pass NULL to switch it off. */
 int gvx_debug_timeline(void *device_buffer);
 
 /* Debug hook: force a code path on (1), off (0) or back to its environment default (-1).  Options: "fused" (the
