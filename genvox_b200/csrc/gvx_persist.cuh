@@ -130,7 +130,9 @@ constexpr int PCF_THREADS = 512;
 
 __global__ void __launch_bounds__(PCF_THREADS, 1) k_lstm_chain_fwd(const PcFwdArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1 KB alignment computed as an OFFSET into the shared array: the compiler keeps the shared address space (LDS/STS,
+    // not generic LD/ST) for everything derived from it
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int H = a.H, T = a.T;
     const int nchunk = (H + 63) / 64;                      // K slabs of 64 (K padded with zero columns); <= PC_MAXRING
     const int img_bytes = nchunk * PC_CHUNK_BYTES;         // one h image: [slab][64 rows][128 B]
@@ -306,7 +308,9 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PCF_THREADS, 1) k_ls
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1 KB alignment computed as an OFFSET into the shared array: the compiler keeps the shared address space (LDS/STS,
+    // not generic LD/ST) for everything derived from it
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int H = a.H, T = a.T;
     const int nchunk = (H + 63) / 64;
     const int q_bytes = nchunk * PC_CHUNK_BYTES;           // this CTA's K quarter of the d-gates image: [slab][64 rows][128 B]

@@ -159,7 +159,9 @@ template <int NPAD>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(const TcGemmArgs a) {
     using C = TcCfg<NPAD>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1 KB alignment computed as an OFFSET into the shared array: the compiler keeps the shared address space (LDS/STS,
+    // not generic LD/ST) for everything derived from it
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t *full = (uint64_t *)(smem + C::BAR_OFF);
     uint64_t *empty = full + TC_STAGES;
     uint64_t *tmem_full = empty + TC_STAGES;
@@ -316,7 +318,9 @@ __global__ void __cluster_dims__(1, 4, 1) __launch_bounds__(TC_THREADS, 1) k_tc_
     using C = TcCfg<NPAD>;
     const TcGemmArgs &a = p.g;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1 KB alignment computed as an OFFSET into the shared array: the compiler keeps the shared address space (LDS/STS,
+    // not generic LD/ST) for everything derived from it
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t *full = (uint64_t *)(smem + C::BAR_OFF);
     uint64_t *empty = full + TC_STAGES;
     uint64_t *tmem_full = empty + TC_STAGES;
