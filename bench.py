@@ -309,6 +309,14 @@ def run_ours(args, rank, world, local_rank):
                 if name == "attention" and fused:
                     roofs[name]["note"] = ("one persistent launch = attention LSTM + query + attention of all T steps; "
                                            "latency-bound (2 grid barriers + 2 exchanges per step), operands L2 resident")
+        tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
+        if os.path.isfile(tpath):          # DRAM bytes per launch from the committed ncu --set full capture (cold cache)
+            with open(tpath) as fh:
+                traffic = json.load(fh)
+            for k, r in roofs.items():
+                if k in traffic:
+                    r["traffic"] = traffic[k]["dram_bytes_per_launch"]
+                    r["traffic_note"] = f'ncu {traffic[k]["kernel"]}, {traffic[k]["launch"]}, cold cache'
         if roofs:
             dominant = max(roofs, key=lambda k: phases[k]["ms"])
             line["roofline"] = dict(roofs[dominant], kernel=dominant)

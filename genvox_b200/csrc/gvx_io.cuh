@@ -26,9 +26,15 @@ inline SrcSum src_split(const float *p, int ld, int nsplit, long long stride) { 
 inline SrcSum src_none() { return SrcSum{nullptr, 0, 0, 0}; }
 
 // destination of a bf16 activation vector: engine image or row-major rows
+// element offset of (row b, column kk) inside an engine operand image: [K/64 slabs][npad rows][64] bf16, SWIZZLE_128B
+// (the 16-byte chunk c of row b sits at chunk position c ^ (b & 7) of the row's 128 bytes; gvx_tc.cuh)
+__device__ __forceinline__ size_t bf_img_off(int kk, int b, int npad) {
+    return (size_t)(kk >> 6) * ((size_t)npad * 64) + (size_t)b * 64 + (size_t)((((kk >> 3) & 7) ^ (b & 7)) << 3) + (kk & 7);
+}
+
 struct BfDst {
     __nv_bfloat16 *p;
-    int kind;    // 0 none, 1 image [K/8][npad][8] starting at element column `koff`, 2 row-major (ld) starting at column `koff`
+    int kind;    // 0 none, 1 engine image (see bf_img_off) starting at element column `koff`, 2 row-major (ld) starting at column `koff`
     int koff;    // multiple of 8
     int ld;      // image: NPAD; row-major: row stride in elements
     long long tstride;   // elements between consecutive frames (bf_store1_t only)
@@ -49,7 +55,7 @@ __device__ __forceinline__ void bf_store8(const BfDsts &s, int b, int k, uint4 v
     for (int i = 0; i < s.n; ++i) {
         const BfDst &d = s.d[i];
         const int kk = d.koff + k;
-        if (d.kind == 1) *reinterpret_cast<uint4 *>(d.p + ((size_t)(kk >> 3) * d.ld + b) * 8) = v;
+        if (d.kind == 1) *reinterpret_cast<uint4 *>(d.p + bf_img_off(kk, b, d.ld)) = v;
         else *reinterpret_cast<uint4 *>(d.p + (size_t)b * d.ld + kk) = v;
     }
 }
@@ -58,7 +64,7 @@ __device__ __forceinline__ void bf_store4(const BfDsts &s, int b, int k, uint2 v
     for (int i = 0; i < s.n; ++i) {
         const BfDst &d = s.d[i];
         const int kk = d.koff + k;
-        if (d.kind == 1) *reinterpret_cast<uint2 *>(d.p + ((size_t)(kk >> 3) * d.ld + b) * 8 + (kk & 7)) = v;
+        if (d.kind == 1) *reinterpret_cast<uint2 *>(d.p + bf_img_off(kk, b, d.ld)) = v;
         else *reinterpret_cast<uint2 *>(d.p + (size_t)b * d.ld + kk) = v;
     }
 }
@@ -68,7 +74,7 @@ __device__ __forceinline__ void bf_store1(const BfDsts &s, int b, int k, float x
     for (int i = 0; i < s.n; ++i) {
         const BfDst &d = s.d[i];
         const int kk = d.koff + k;
-        if (d.kind == 1) d.p[((size_t)(kk >> 3) * d.ld + b) * 8 + (kk & 7)] = h;
+        if (d.kind == 1) d.p[bf_img_off(kk, b, d.ld)] = h;
         else d.p[(size_t)b * d.ld + kk] = h;
     }
 }
@@ -79,7 +85,7 @@ __device__ __forceinline__ void bf_store1_t(const BfDsts &s, int t, int b, int k
         const BfDst &d = s.d[i];
         const int kk = d.koff + k;
         __nv_bfloat16 *base = d.p + (size_t)t * d.tstride;
-        if (d.kind == 1) base[((size_t)(kk >> 3) * d.ld + b) * 8 + (kk & 7)] = h;
+        if (d.kind == 1) base[bf_img_off(kk, b, d.ld)] = h;
         else base[(size_t)b * d.ld + kk] = h;
     }
 }

@@ -7,13 +7,13 @@
 // and the mel/gate projections (:361-362) in bf16 mode.
 //
 // Operand images.  Both operands live in HBM already in the shared-memory image tcgen05 wants
-// (K-major, SWIZZLE_NONE "interleaved" core matrices: 8 rows x 16 bytes, 128 B contiguous), so one
-// k-block of an operand is ONE contiguous chunk and is fetched by one TMA bulk copy
-// (cp.async.bulk ... mbarrier::complete_tx) issued by a single elected thread:
-//   W image  [Mtiles][Kpad/8][128][8] bf16    (row tile, k-chunk of 8, row in tile, k in chunk)
-//   X image  [Kpad/8][NPAD][8]        bf16    (k-chunk, batch row, k in chunk)
-// UMMA descriptors: leading-dimension byte offset = distance between the two k-chunks of one K=16 MMA
-// (rows * 16 B), stride byte offset = distance between 8-row groups (128 B).
+// (K-major, SWIZZLE_128B: rows of 128 B = 64 bf16 along K, 8-row groups of 1 KB, 16-byte chunk c of row r at chunk
+// position c ^ (r & 7)), so one 64-element k-block of an operand is ONE contiguous chunk and is fetched by one TMA
+// bulk copy (cp.async.bulk ... mbarrier::complete_tx) issued by a single elected thread:
+//   W image  [Mtiles][Kpad/64][128 rows][64] bf16    (row tile, k-block, row in tile, swizzled k in block)
+//   X image  [Kpad/64][NPAD rows][64]        bf16    (k-block, batch row, swizzled k in block)
+// UMMA descriptors: SWIZZLE_128B, stride byte offset 1 KB; a K = 16 step inside the block advances the start address by
+// 32 B.  (The first version used the no-swizzle interleaved layout: ~180 cycles per 128 x 32 x 16 MMA, measured.)
 //
 // Mapping: the weights are the M side (UMMA_M = 128 rows per CTA, full TMEM lane use), the batch is
 // the N side (UMMA_N = NPAD <= 256); grid = (Mtiles, KS): the K range is split over KS CTAs so that
@@ -224,13 +224,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_gemm(const TcGemmArgs a) {
                 if (!mbar_wait(full + s, ph, a.err, 2)) break;
                 tc_fence_after();
                 const uint32_t wbase = smem_u32(smem + (size_t)s * C::SB), xbase = wbase + C::WB;
+                const uint64_t ad = umma_desc_sw128(wbase), bd = umma_desc_sw128(xbase);
 #pragma unroll
-                for (int kk = 0; kk < TC_KB / 16; ++kk) {
-                    // one MMA consumes two k-chunks (16 elements): advance by 2 * LBO
-                    const uint64_t ad = umma_desc(wbase + kk * 2 * (TC_M * 16), TC_M * 16, 128);
-                    const uint64_t bd = umma_desc(xbase + kk * 2 * (NPAD * 16), NPAD * 16, 128);
-                    umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
-                }
+                for (int kk = 0; kk < TC_KB / 16; ++kk)      // a K = 16 step = 32 B = 2 descriptor address units
+                    umma_bf16(tmem_base, ad + 2 * kk, bd + 2 * kk, idesc, (i > 0 || kk > 0) ? 1u : 0u);
                 umma_commit(empty + s);        // smem slot is free once these MMAs have read it
             }
             umma_commit(tmem_full);            // accumulator complete
@@ -381,12 +378,10 @@ __global__ void __cluster_dims__(1, 4, 1) __launch_bounds__(TC_THREADS, 1) k_tc_
                 if (!mbar_wait(full + s, ph, a.err, 2)) break;
                 tc_fence_after();
                 const uint32_t wbase = smem_u32(smem + (size_t)s * C::SB), xbase = wbase + C::WB;
+                const uint64_t ad = umma_desc_sw128(wbase), bd = umma_desc_sw128(xbase);
 #pragma unroll
-                for (int kk = 0; kk < TC_KB / 16; ++kk) {
-                    const uint64_t ad = umma_desc(wbase + kk * 2 * (TC_M * 16), TC_M * 16, 128);
-                    const uint64_t bd = umma_desc(xbase + kk * 2 * (NPAD * 16), NPAD * 16, 128);
-                    umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
-                }
+                for (int kk = 0; kk < TC_KB / 16; ++kk)      // a K = 16 step = 32 B = 2 descriptor address units
+                    umma_bf16(tmem_base, ad + 2 * kk, bd + 2 * kk, idesc, (i > 0 || kk > 0) ? 1u : 0u);
                 umma_commit(empty + s);
             }
             umma_commit(tmem_full);
@@ -479,7 +474,7 @@ inline int launch_tc_gemm_lstm(const TcLstmArgs &p, int Mtiles, cudaStream_t st)
 }
 
 // ------------------------------------------------------------------ operand image builders
-// generic weight image: element (tile, kc, r, j) <- src(m = tile*128 + r, k = kc*8 + j), zero outside
+// generic weight image: element (tile, k-block, r, swizzled k) <- src(m = tile*128 + r, k), zero outside
 // mode 0: src[m*ld + k]                               (plain [Mtot, K])
 // mode 1: LSTM forward: m = tile*128 + g*32 + l  -> torch row g*HID + 32*tile + l; k < Kih ? w_ih : w_hh
 // mode 2: LSTM backward (transposed): m = input feature, k = 4*u + g -> torch row g*HID + u, column m
@@ -492,11 +487,12 @@ struct TcPackW {
 __global__ void k_tc_pack_w(const TcPackW p, int Mtiles, int Kpad, __nv_bfloat16 *__restrict__ img) {
     const size_t total = (size_t)Mtiles * Kpad * TC_M;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int j = (int)(i & 7);
-        const int r = (int)((i >> 3) & (TC_M - 1));
-        const size_t rest = i >> 10;                       // tile * (Kpad/8) + kc
-        const int kc = (int)(rest % (Kpad / 8)), tile = (int)(rest / (Kpad / 8));
-        const int m = tile * TC_M + r, k = kc * 8 + j;
+        // image index -> (tile, k-block, row, chunk position, element); the chunk position is the swizzled one
+        const int j = (int)(i & 7), cpos = (int)((i >> 3) & 7);
+        const int r = (int)((i >> 6) & (TC_M - 1));
+        const size_t rest = i >> 13;                       // tile * (Kpad/64) + kb
+        const int kb = (int)(rest % (Kpad / 64)), tile = (int)(rest / (Kpad / 64));
+        const int m = tile * TC_M + r, k = kb * 64 + ((cpos ^ (r & 7)) << 3) + j;
         float v = 0.f;
         if (p.mode == 0) {
             if (m < p.Mtot && k < p.K) v = p.s0[(size_t)m * p.ld + k];
@@ -519,14 +515,14 @@ __global__ void k_tc_pack_w(const TcPackW p, int Mtiles, int Kpad, __nv_bfloat16
     }
 }
 
-// activation image from a row-major fp32 matrix [B, K] (ld): element (kc, b, j) <- X[b, kc*8 + j]
+// activation image from a row-major fp32 matrix [B, K] (ld): element (k-block, b, swizzled k) <- X[b, k]
 __global__ void k_tc_pack_x(const float *__restrict__ X, int B, int K, int ld, int NPAD, int Kpad, __nv_bfloat16 *__restrict__ img) {
     const size_t total = (size_t)Kpad * NPAD;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int j = (int)(i & 7);
-        const size_t rest = i >> 3;
-        const int b = (int)(rest % NPAD), kc = (int)(rest / NPAD);
-        const int k = kc * 8 + j;
+        const int j = (int)(i & 7), cpos = (int)((i >> 3) & 7);
+        const size_t rest = i >> 6;
+        const int b = (int)(rest % NPAD), kb = (int)(rest / NPAD);
+        const int k = kb * 64 + ((cpos ^ (b & 7)) << 3) + j;
         img[i] = __float2bfloat16((b < B && k < K) ? X[(size_t)b * ld + k] : 0.f);
     }
 }
