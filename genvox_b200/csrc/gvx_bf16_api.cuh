@@ -660,6 +660,7 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     pa.CUMS = s + S.CUMS; pa.DCTX = x + W.DCTX; pa.PRE1 = s + S.PRE1; pa.FR = s + S.FR;
     pa.DPM = x + W.DPM; pa.PART1 = x + W.PART1; pa.PART2 = x + W.PART2; pa.DZ2 = x + W.DZ2; pa.DZ1 = x + W.DZ1;
     pa.post_blocks = W.post_blocks;
+    pa.bf16_mode = 1;
     return bwd_post_common(d, w, memory, B, N, T, pa, g, d_memory, st);
 }
 

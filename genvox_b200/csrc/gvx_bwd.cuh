@@ -142,6 +142,111 @@ __global__ void __launch_bounds__(512, (FMAX <= 32 ? 2 : 1)) k_attn_post_dense(c
     }
 }
 
+
+// Post-pass 1 on tensor cores (bf16 mode, att_dim 128 / 32 location filters).  The FFMA kernel above issues ~47
+// instructions per (token, frame, d) and reaches ~0.9 TB/s of the 5 GB it streams (ncu, T = 800: 5.4 ms); the outer
+// product  d Wld[d, f] += sum_t d s[t, d] * conv[t, f]  is a [128 x 16] . [16 x 32] contraction per 16 frames of a token:
+//   thread = attention dim d: loads th[t0..t0+15][d] (16 independent coalesced loads), forms d s, keeps the d pm / d v
+//   sums in fp32, packs frame pairs to bf16x2 and stores them as the A operand ([d][t], padded rows: conflict-free
+//   fragment reads); the conv rows of the chunk become the B operand ([f][t]) the same way;
+//   warp w contracts d rows [32w, 32w+32) x all 32 filters: 8 mma.sync.m16n8k16 per chunk, fp32 accumulators.
+// Operands are rounded to bf16 (as in every contraction of bf16 mode); accumulation and the d pm / d v sums stay fp32.
+constexpr int PDM_TC = 16;         // frames per chunk = one MMA k-step
+constexpr int PDM_LDA = 12;        // 32-bit words per operand row (8 used): bank = 12 g + tig is conflict-free
+__device__ __forceinline__ void pdm_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pdm_pack(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&v);
+}
+__global__ void __launch_bounds__(128, 5) k_attn_post_dense_mma(const float *__restrict__ TH, const float *__restrict__ DE,
+                                                                const float *__restrict__ CONVS, const float *__restrict__ v, int T,
+                                                                int B, int N, float *__restrict__ DPM,
+                                                                float *__restrict__ part /* [grid][128*32 + 128] */) {
+    constexpr int D = 128, F = 32;
+    __shared__ __align__(16) uint32_t sA[2][D * PDM_LDA];      // [d][frame pair] bf16x2
+    __shared__ __align__(16) uint32_t sB[2][F * PDM_LDA];      // [f][frame pair] bf16x2
+    const int d = threadIdx.x, warp = d >> 5, lane = d & 31, g = lane >> 2, tig = lane & 3;
+    const float vd = v[d];
+    const size_t tok_stride = (size_t)B * N;
+    float acc[2][4][4];                                        // [m-tile][n-tile][fragment]
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[m][n][i] = 0.f;
+    float vacc = 0.f;
+    // conv staging: thread -> (frame pair p, filter pair q): conv[2p..2p+1][2q..2q+1]
+    const int cp_ = d >> 4, cq = d & 15;
+    int buf = 0;
+    for (int tok = blockIdx.x; tok < B * N; tok += gridDim.x) {
+        float pacc = 0.f;
+        for (int t0 = 0; t0 < T; t0 += PDM_TC) {
+            float th[PDM_TC], de[PDM_TC];
+#pragma unroll
+            for (int i = 0; i < PDM_TC; ++i) {
+                const bool in = t0 + i < T;
+                const size_t row = (size_t)(in ? t0 + i : 0) * tok_stride + tok;
+                th[i] = in ? __ldcs(TH + row * D + d) : 0.f;
+                de[i] = in ? __ldg(DE + row) : 0.f;
+            }
+            float2 c0 = make_float2(0.f, 0.f), c1 = make_float2(0.f, 0.f);
+            {
+                const int ta = t0 + 2 * cp_;
+                if (ta < T) c0 = __ldcs(reinterpret_cast<const float2 *>(CONVS + ((size_t)ta * tok_stride + tok) * F + 2 * cq));
+                if (ta + 1 < T) c1 = __ldcs(reinterpret_cast<const float2 *>(CONVS + ((size_t)(ta + 1) * tok_stride + tok) * F + 2 * cq));
+            }
+            uint32_t pk[PDM_TC / 2];
+#pragma unroll
+            for (int i = 0; i < PDM_TC; i += 2) {
+                const float ds0 = de[i] * vd * (1.f - th[i] * th[i]), ds1 = de[i + 1] * vd * (1.f - th[i + 1] * th[i + 1]);
+                pacc += ds0 + ds1;
+                vacc = fmaf(de[i], th[i], vacc);
+                vacc = fmaf(de[i + 1], th[i + 1], vacc);
+                pk[i / 2] = pdm_pack(ds0, ds1);
+            }
+            uint4 *arow = reinterpret_cast<uint4 *>(&sA[buf][d * PDM_LDA]);
+            arow[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            arow[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            sB[buf][(2 * cq) * PDM_LDA + cp_] = pdm_pack(c0.x, c1.x);
+            sB[buf][(2 * cq + 1) * PDM_LDA + cp_] = pdm_pack(c0.y, c1.y);
+            __syncthreads();          // the other buffer is free again once every warp has passed this barrier twice
+            uint32_t bfr[4][2];
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                bfr[n][0] = sB[buf][(8 * n + g) * PDM_LDA + tig];
+                bfr[n][1] = sB[buf][(8 * n + g) * PDM_LDA + tig + 4];
+            }
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const int r0 = 32 * warp + 16 * m + g;
+                const uint32_t a0 = sA[buf][r0 * PDM_LDA + tig], a1 = sA[buf][(r0 + 8) * PDM_LDA + tig];
+                const uint32_t a2 = sA[buf][r0 * PDM_LDA + tig + 4], a3 = sA[buf][(r0 + 8) * PDM_LDA + tig + 4];
+#pragma unroll
+                for (int n = 0; n < 4; ++n) pdm_mma(acc[m][n], a0, a1, a2, a3, bfr[n][0], bfr[n][1]);
+            }
+            buf ^= 1;
+        }
+        DPM[(size_t)tok * D + d] = pacc;
+    }
+    float *p = part + (size_t)blockIdx.x * (D * F + D);
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            const int r0 = 32 * warp + 16 * m + g, c0 = 8 * n + 2 * tig;
+            p[r0 * F + c0] = acc[m][n][0];
+            p[r0 * F + c0 + 1] = acc[m][n][1];
+            p[(r0 + 8) * F + c0] = acc[m][n][2];
+            p[(r0 + 8) * F + c0 + 1] = acc[m][n][3];
+        }
+    p[D * F + d] = vacc;
+}
+
 // Post-pass 2: d Wlc[f,c,k] = sum_{t,b,n} d conv[t,b,n,f] * wcat[t,b,c,n+k-pad]
 //   wcat channel 0 = alignments of step t-1 (zeros at t = 0), channel 1 = cum before step t.
 // One thread = (filter f, channel c, block of 8 taps); the 8-tap window slides over the tokens in registers
@@ -229,6 +334,7 @@ struct BwdPostArgs {
     const float *TH, *DE, *CONVS, *DCONV, *ALIGN, *CUMS, *DCTX, *PRE1, *FR;
     float *DPM, *PART1, *PART2, *DZ2, *DZ1;
     int post_blocks;
+    int bf16_mode;            // 1: bf16-operand tensor-core post-pass for d location_dense (gvx_bf16_api.cuh), 0: exact fp32
 };
 inline int bwd_post_common(const Dims &d, const gvx_weights *w, const float *memory, int B, int N, int T, const BwdPostArgs &p,
                            const gvx_grads *g, float *d_memory, cudaStream_t st) {
@@ -237,7 +343,9 @@ inline int bwd_post_common(const Dims &d, const gvx_weights *w, const float *mem
         const int nblk = p.post_blocks;
         const int threads = (d.D + 31) & ~31;
         GVX_CHECK(threads <= 512, "att_dim too large");
-        if (d.F <= 32) {
+        if (p.bf16_mode && d.D == 128 && d.F == 32) {
+            k_attn_post_dense_mma<<<nblk, 128, 0, st>>>(p.TH, p.DE, p.CONVS, w->v_w, T, B, N, p.DPM, p.PART1);
+        } else if (d.F <= 32) {
             k_attn_post_dense<32><<<nblk, threads, 0, st>>>(p.TH, p.DE, p.CONVS, w->v_w, T, B, N, d.D, d.F, p.DPM, p.PART1);
         } else {
             k_attn_post_dense<64><<<nblk, threads, 0, st>>>(p.TH, p.DE, p.CONVS, w->v_w, T, B, N, d.D, d.F, p.DPM, p.PART1);
@@ -448,6 +556,7 @@ static int train_bwd_body(const gvx_dims *dd, const gvx_weights *w, const void *
     pa.CUMS = s + S.CUMS; pa.DCTX = x + W.DCTX; pa.PRE1 = s + S.PRE1; pa.FR = s + S.FR;
     pa.DPM = x + W.DPM; pa.PART1 = x + W.PART1; pa.PART2 = x + W.PART2; pa.DZ2 = x + W.DZ2; pa.DZ1 = x + W.DZ1;
     pa.post_blocks = W.post_blocks;
+    pa.bf16_mode = 0;
     return bwd_post_common(d, w, memory, B, N, T, pa, g, d_memory, st);
 }
 
