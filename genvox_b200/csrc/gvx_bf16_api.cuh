@@ -490,6 +490,38 @@ inline int run_bf_lstm_bwd(const Dims &d, int which, const SrcSum &s0, const Src
     return 0;
 }
 
+// attention-LSTM cell backward of one step with d q . W_query computed inside (k_bf_lstm_bwd_q)
+inline int run_bf_lstm_bwd_q(const Dims &d, const bf16 *dq_rm, const float *WqT, const SrcSum &s1, const SrcSum &s2, const float *gates,
+                             const float *c_prev, const float *c_new, float *dc, const BfDsts &dg, int B, uint64_t seed, int t,
+                             int training, int row_offset, const SrcSum *dpre_src, const float *pre2, float *dz2, cudaStream_t st) {
+    BfLstmBwdQ q;
+    memset(&q, 0, sizeof(q));
+    BfLstmBwd &a = q.p;
+    a.s1 = s1; a.s2 = s2;
+    a.drop = make_drop(seed, d.p_att, training);
+    a.site = SITE_ATT;
+    a.t = (uint32_t)t; a.row_offset = row_offset; a.B = B; a.HID = d.A;
+    a.gates = gates; a.c_prev = c_prev; a.c_new = c_new; a.dc = dc; a.dg_dst = dg;
+    a.main_blocks = (d.A + LBQ_UB - 1) / LBQ_UB;
+    int extra = 0;
+    if (dpre_src) {
+        a.dpre_src = *dpre_src; a.pre2 = pre2; a.dz2 = dz2; a.P = d.P;
+        extra = grid_for((size_t)B * d.P);
+        if (extra > 64) extra = 64;
+    }
+    q.dq_rm = dq_rm; q.WqT = WqT; q.D = d.D;
+    const size_t smem = ((size_t)((LBQ_UB * (d.D + 1) + 3) & ~3) + (size_t)d.D * (((B + 1) & ~1) + 2)) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > configured) {
+        GVX_CUDA(cudaFuncSetAttribute(k_bf_lstm_bwd_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    GVX_CUDA(launch_pdl(k_bf_lstm_bwd_q, dim3(a.main_blocks + extra), dim3(LBQ_THREADS), smem, st, q));
+    GVX_LAUNCHED(1);
+    GVX_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ======================================================================================= backward (BPTT)
 int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, const float *memory, const int64_t *mem_lengths,
                    int B, int N, int T, uint64_t seed, int training, int row_offset, const float *d_mel, const float *d_gate,
@@ -549,6 +581,10 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
         }
     }
 
+    // OPT-IN (GVX_S4_FUSED=1): measured on B200 at configs[2] the folded kernel is SLOWER than GEMM + pointwise (phase 13.3 ms
+    // vs 10.6 ms per train step, whole step 73.1 vs 65.8 ms): its 128 blocks serialise staging, contraction and the
+    // latency-bound cell backward, while the two-launch version overlaps them through programmatic dependent launch
+    static const bool s4_fused = getenv("GVX_S4_FUSED") && getenv("GVX_S4_FUSED")[0] == '1';
     pdl_barrier_next();
     for (int t = T - 1; t >= 0; --t) {
         const bool last = t == T - 1;
@@ -592,17 +628,25 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
         }
         {   // S4: d h_att = d q . W_query + (from decoder-LSTM input) + (from step t+1), attention-LSTM pointwise backward
             ProfScope ps(PS_BWD_ATT_POINT, st);
-            GVX_TRY(run_tc(WqTI, DQI, x + W.PS4, gm.TqT, gm.Dp, W.KSs4, B, err, st));
             BfDsts dg;
             memset(&dg, 0, sizeof(dg));
             add_img(dg, GAI, 0, NPAD); add_rm(dg, DGARM + (size_t)t * B * 4 * d.A, 0, 4 * d.A);
             SrcSum dpre = last ? src_none() : src_split(pdxa_n, lda, W.KSaT, sa);
-            GVX_TRY(run_bf_lstm_bwd(d, 0, src_split(x + W.PS4, lds4, W.KSs4, (long long)B * lds4),
-                                    pc ? src_plain(dxd_t, AE) : src_split(pdxd, ldd, W.KSdT, sd),
-                                    last ? src_none() : src_split(pdxa_n + d.P + d.E, lda, W.KSaT, sa),
-                                    s + S.GA + (size_t)t * 4 * BA, s + S.CA + t * BA, s + S.CA + (t + 1) * BA, x + W.DCA, dg, B, seed,
-                                    t, training, row_offset, last ? nullptr : &dpre, last ? nullptr : s + S.PRE2 + (size_t)(t + 1) * B * d.P,
-                                    last ? nullptr : x + W.DZ2 + (size_t)(t + 1) * B * d.P, st));
+            const SrcSum s1 = pc ? src_plain(dxd_t, AE) : src_split(pdxd, ldd, W.KSdT, sd);
+            const SrcSum s2 = last ? src_none() : src_split(pdxa_n + d.P + d.E, lda, W.KSaT, sa);
+            if (s4_fused) {
+                // d q . W_query inside the pointwise kernel: one launch instead of a K = 128 engine GEMM + pointwise
+                GVX_TRY(run_bf_lstm_bwd_q(d, DQRM + (size_t)t * B * d.D, packed + PL.WqT, s1, s2, s + S.GA + (size_t)t * 4 * BA,
+                                          s + S.CA + t * BA, s + S.CA + (t + 1) * BA, x + W.DCA, dg, B, seed, t, training, row_offset,
+                                          last ? nullptr : &dpre, last ? nullptr : s + S.PRE2 + (size_t)(t + 1) * B * d.P,
+                                          last ? nullptr : x + W.DZ2 + (size_t)(t + 1) * B * d.P, st));
+            } else {
+                GVX_TRY(run_tc(WqTI, DQI, x + W.PS4, gm.TqT, gm.Dp, W.KSs4, B, err, st));
+                GVX_TRY(run_bf_lstm_bwd(d, 0, src_split(x + W.PS4, lds4, W.KSs4, (long long)B * lds4), s1, s2,
+                                        s + S.GA + (size_t)t * 4 * BA, s + S.CA + t * BA, s + S.CA + (t + 1) * BA, x + W.DCA, dg, B, seed,
+                                        t, training, row_offset, last ? nullptr : &dpre, last ? nullptr : s + S.PRE2 + (size_t)(t + 1) * B * d.P,
+                                        last ? nullptr : x + W.DZ2 + (size_t)(t + 1) * B * d.P, st));
+            }
         }
         {   // S5: d x_att = d gates_att . W_att
             ProfScope ps(PS_BWD_ATT_GEMM, st);
