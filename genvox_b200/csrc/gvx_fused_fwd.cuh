@@ -318,6 +318,8 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                     umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
                     umma_commit(sh->empty + slot);
                     if (++slot == FA_RING) { slot = 0; ph ^= 1u; }
+                    if (c == 0 && t > 0) pc_stamp(a.dbg, j, t - 1, 16);              // first h_att slab of step t has landed
+                    if (c == FA_HSLAB - 1 && t > 0) pc_stamp(a.dbg, j, t - 1, 17);   // h_att part issued (during step t-1's attention)
                 }
                 if (ok) umma_commit(&sh->tmem_full);
                 pc_stamp(a.dbg, j, t, 1);
@@ -564,6 +566,7 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                 }
             }
             fa_bar_workers();
+            if (tid == 0) pc_stamp(a.dbg, j, t, 13);
             // local softmax statistics (every warp computes the same max: no extra barrier)
             float mloc = -INFINITY;
             for (int n = lane; n < n_own; n += 32) mloc = fmaxf(mloc, es[n]);
@@ -613,10 +616,12 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                 dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
             }
             fa_bar_workers();
+            if (tid == 0) pc_stamp(a.dbg, j, t, 14);
             for (int e = wtid; e < FA_E; e += FA_NW)
                 ctxp[e] = ((part[e] + part[FA_E + e]) + (part[2 * FA_E + e] + part[3 * FA_E + e])) +
                           ((part[4 * FA_E + e] + part[5 * FA_E + e]) + part[6 * FA_E + e]);
             fa_bar_workers();
+            if (tid == 0) pc_stamp(a.dbg, j, t, 15);
             if (tid == 0) mbar_arrive_cluster(peer_sbar);    // release: this CTA's max / sum / exp / partial context are complete
             fa_wait_cluster(&sh->sbar, (uint32_t)t & 1u, &sh->dead, a.err, 39);
             if (tid == 0) { pc_stamp(a.dbg, j, t, 6); fa_mark(a.prog, 0, j, 8 * t + 4); }
@@ -739,6 +744,7 @@ inline int launch_att_chain_fwd(const FaArgs &a_in, cudaStream_t st) {
     FaArgs a = a_in;
     a.dbg = pc_dbg_buffer() ? pc_dbg_buffer() + 3 * 32 * 1024 : nullptr;                // fourth plane: fused-chain stamps
     a.prog = pc_dbg_buffer() ? (int *)(pc_dbg_buffer() + 2 * 32 * 1024) : nullptr;     // third plane of the debug buffer
+    if (getenv("GVX_DEBUG_NO_TH")) a.th_stash = nullptr;      // experiment only: the backward pass needs this stash
     const size_t smem = FaSmem(a.N).total;
     static size_t configured = 0;
     if (configured < smem) {
