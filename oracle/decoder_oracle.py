@@ -28,18 +28,25 @@ from . import philox
 # ---- optional bf16 semantics of the product's bf16 mode (gate / query / projection GEMM operands rounded to
 # bf16, gradients of those GEMM outputs rounded to bf16 in backward; everything else in the working dtype)
 _BF16 = False
+_BF16_MEMORY = False
 
 
 class bf16_semantics:
-    """with O.bf16_semantics(): ...  — the oracle then mirrors genvox_b200's bf16 mode rounding points."""
+    """with O.bf16_semantics(): ...  — the oracle then mirrors genvox_b200's bf16 mode rounding points.
+    round_memory=True adds the one extra rounding point of the fused persistent attention chain
+    (genvox_b200/csrc/gvx_fused_fwd.cuh): the context bmm (tacotron2.py:127) reads a bf16 copy of the encoder memory."""
+
+    def __init__(self, round_memory: bool = False):
+        self.round_memory = round_memory
 
     def __enter__(self):
-        global _BF16
-        self.prev, _BF16 = _BF16, True
+        global _BF16, _BF16_MEMORY
+        self.prev, _BF16 = (_BF16, _BF16_MEMORY), True
+        _BF16_MEMORY = self.round_memory
 
     def __exit__(self, *exc):
-        global _BF16
-        _BF16 = self.prev
+        global _BF16, _BF16_MEMORY
+        _BF16, _BF16_MEMORY = self.prev
 
 
 class _RoundFwd(torch.autograd.Function):
@@ -143,7 +150,7 @@ def attention(P, h_att, memory, processed_memory, w_prev, w_cum, mask):
     if mask is not None:
         e = e.masked_fill(mask, float("-inf"))      # :125 (done on .data there: no grad through masked slots either way)
     w = F.softmax(e, dim=1)                          # :126
-    ctx = torch.bmm(w.unsqueeze(1), memory).squeeze(1)   # :127-128
+    ctx = torch.bmm(w.unsqueeze(1), _rf(memory) if _BF16_MEMORY else memory).squeeze(1)   # :127-128
     return ctx, w
 
 

@@ -4,7 +4,8 @@ location-sensitive attention of ALL teacher-forced frames in one launch (tacotro
 Yardstick 1: the per-step kernel chain of the same library on the same inputs (gvx_debug_option("fused", 0)) - the two
 paths share every rounding point except that the fused path contracts the context with a bf16 copy of the encoder
 memory (the context is rounded to bf16 right afterwards in both), so they agree to a few bf16 ulps.
-Yardstick 2: the CPU oracle with bf16 rounding points (bounds of tests/test_cuda_bf16.py)."""
+Yardstick 2: the CPU oracle with the same bf16 rounding points, including the bf16 memory operand of the context
+(oracle.decoder_oracle.bf16_semantics(round_memory=True)); bounds of tests/test_cuda_bf16.py."""
 import numpy as np
 import pytest
 import torch
@@ -61,7 +62,7 @@ def test_fused_chain_matches_per_step_chain_and_oracle(cuda_device, B, N, T, tra
     assert float((fa.sum(-1) - 1).abs().max()) < 1e-5
 
     if T <= 12:
-        with O.bf16_semantics():
+        with O.bf16_semantics(round_memory=True):
             (om, og, oa), ograds, omem = O.loss_and_grads(O.as_params(W), torch.from_numpy(mem), torch.from_numpy(mel), lens, r_mel,
                                                           r_gate, seed, training, dims.p_attention_dropout, dims.p_decoder_dropout)
         oerrs = {"mel": rel_err(fm, om), "gate": rel_err(fg, og), "align": rel_err(fa, oa)}
