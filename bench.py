@@ -29,7 +29,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-TRAIN = dict(B=64, N=150, T=800)          # BASELINE.json configs[2] (per GPU)
+TRAIN = dict(B=64, N=150, T=int(os.environ.get("GVX_BENCH_T", "800")))     # BASELINE.json configs[2] (per GPU); the env
+                                                                           # override is for debugging runs only
 INFER = dict(B=64, N=150, steps=1000)     # BASELINE.json configs[1]
 CPU_SAMPLE_T = 8                          # frames of the training workload the CPU legs run per step
 METRIC = "Tacotron2 train mel-frames/s"
@@ -161,6 +162,11 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------ GPU arm
+def _stage(rank, msg):
+    if os.environ.get("GVX_BENCH_TRACE"):
+        print(f"[rank {rank}] {time.strftime('%H:%M:%S')} {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -213,8 +219,12 @@ def run_ours(args, rank, world, local_rank):
         return float(loss_h[0])
 
     # ---- value: inputs resident in HBM
-    for _ in range(Wm):
+    _stage(rank, "setup done")
+    for i in range(Wm):
         step_resident()
+        if os.environ.get("GVX_BENCH_SYNC"):
+            torch.cuda.synchronize()
+        _stage(rank, f"warm-up step {i} enqueued")
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     if sampler:
@@ -230,6 +240,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     launches = lib.gvx_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
+    _stage(rank, "timed region done")
     ms = max_over_ranks(e0.elapsed_time(e1)) / K
     value = world * B * T / (ms * 1e-3)
     final_loss = float(loss)
@@ -242,6 +253,7 @@ def run_ours(args, rank, world, local_rank):
         step_e2e()
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / K
+    _stage(rank, "e2e done")
     h2d = sum(t.numel() * t.element_size() for t in (memory_h, mel_h, gate_h, lengths_h))
     e2e = {"value": world * B * T / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
@@ -360,6 +372,10 @@ def main():
                     help="arithmetic of the recurrent GEMMs (BASELINE configs[2] is bf16; fp32 = parity mode)")
     args = ap.parse_args()
 
+    # watchdog: a run that has not finished after 15 minutes (the default run takes about one) dumps every thread's Python
+    # stack and exits instead of hanging its caller; GVX_BENCH_TRACE=1 adds per-stage progress lines on stderr
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("GVX_BENCH_TRACE_AFTER", "900")), exit=True)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1 and "RANK" not in os.environ:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",

@@ -79,6 +79,34 @@ def decoder_train_step(decoder, optimizer, memory, mel_padded, gate_padded, memo
     return loss.detach(), grad_norm
 
 
+def model_train_step(model, batch, criterion, optimizer, group=None, bucket_mb=32.0, grad_clip_thresh=None):
+    """Data-parallel drop-in for `Tacotron2.train_step` (tacotron2.py:515-522) on a reference
+    Tacotron2 whose decoder was swapped by `genvox_b200.install`: same sequence of calls, plus the one exchange the
+    reference lacks - the bucketed asynchronous gradient all-reduce over ALL parameters (encoder, decoder, postnet)
+    between `loss.backward()` (:520) and `clip_grad_norm_` (:521).  `criterion` / `optimizer` are the dictionaries of
+    `get_criterion` / `get_optimizer` (:500-513).  The two `.item()` host syncs of the reference (:519, :521) are kept
+    as attributes only when asked for: `model.loss_items` / `model.grad_norm_val` hold 0-dim device tensors here, so
+    a step enqueues without waiting for the GPU; the Trainer's logging converts them when it prints."""
+    optimizer["optimizer"].zero_grad(set_to_none=True)
+    outputs = model.forward(batch=batch)
+    loss = criterion["loss"](batch, outputs)
+    loss["loss"].backward()
+    params = [p for p in model.parameters() if p.requires_grad]
+    allreduce_gradients(params, group, bucket_mb)
+    thresh = grad_clip_thresh if grad_clip_thresh is not None else model.model_config.grad_clip_thresh
+    model.grad_norm_val = torch.nn.utils.clip_grad_norm_(params, thresh)
+    optimizer["optimizer"].step()
+    model.loss_items = {key: val.detach() for key, val in loss.items()}
+    return model.loss_items
+
+
+def rank_batch_rows(batch_size, rank):
+    """First row of rank `rank` in the global batch: set `model.decoder.dropout_row_offset` to it so that the ranks
+    draw disjoint rows of ONE dropout stream (a run on N GPUs with per-rank batch B then uses the masks of a
+    single-GPU run with batch N*B)."""
+    return rank * batch_size
+
+
 def make_optimizer(decoder, learning_rate=1e-3, weight_decay=1e-6):
     """Adam with the reference's hyper-parameters (tacotron2.py:506-513, configs/models.py)."""
     return torch.optim.Adam(decoder.parameters(), lr=learning_rate, weight_decay=weight_decay)

@@ -1,0 +1,121 @@
+"""GPU tests of the batched synthesis wrapper (genvox_b200/synthesis.py) and of the model-level train
+step (genvox_b200/training.py::model_train_step, N2) on a stand-in for the reference Tacotron2: the reference's own
+embedding / encoder / postnet are outside the hot path and absent on the GPU box, so small deterministic torch modules
+with the same call signatures (tacotron2.py:462, :483-499) take their place around the real B200-native decoder."""
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+import genvox_b200
+from genvox_b200 import synthesis
+from genvox_b200.training import model_train_step
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+class _Encoder(nn.Module):
+    """[B, sym, n_tok] -> [B, n_tok, enc]; `inference` ignores lengths like the reference (tacotron2.py:248-256)."""
+
+    def __init__(self, sym, enc):
+        super().__init__()
+        self.conv = nn.Conv1d(sym, enc, 5, padding=2)
+
+    def forward(self, x, lengths=None):
+        return torch.tanh(self.conv(x)).transpose(1, 2)
+
+    inference = forward
+
+
+class _Model(nn.Module):
+    def __init__(self, dims, n_tokens=40, sym=32):
+        super().__init__()
+        self.embedding = nn.Embedding(n_tokens, sym)
+        self.encoder = _Encoder(sym, dims.encoder_embedding_dim)
+        self.decoder = genvox_b200.Decoder(**dims.kwargs())
+        self.postnet = nn.Sequential(nn.Conv1d(dims.n_mels, 64, 5, padding=2), nn.Tanh(), nn.Conv1d(64, dims.n_mels, 5, padding=2))
+        self.model_config = types.SimpleNamespace(grad_clip_thresh=1.0)
+
+    def forward(self, batch):      # tacotron2.py:450-481
+        emb = self.embedding(batch["token_padded"]).transpose(1, 2)
+        enc = self.encoder(emb, batch["token_lengths"])
+        mel, gate, align = self.decoder(enc, batch["mel_padded"], memory_lengths=batch["token_lengths"])
+        return {"mel_outputs": mel, "mel_outputs_postnet": mel + self.postnet(mel), "gate_outputs": gate, "alignments": align}
+
+    @torch.no_grad()
+    def inference(self, inputs):   # tacotron2.py:483-499 (B = 1)
+        emb = self.embedding(inputs["tokens"]).transpose(1, 2)
+        enc = self.encoder.inference(emb)
+        mel, gate, align = self.decoder.inference(enc)
+        return {"mel_outputs": mel, "mel_outputs_postnet": mel + self.postnet(mel), "gate_outputs": gate, "alignments": align}
+
+
+def _model(device, max_steps):
+    dims = synth.DecoderDims()
+    torch.manual_seed(3)
+    m = _Model(dims).to(device).eval()
+    W = synth.make_decoder_weights(11, dims)
+    m.decoder.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in W.items()})
+    m.decoder.to(device)
+    m.decoder.max_decoder_steps = max_steps
+    return m
+
+
+def test_batched_inference_equals_one_utterance_at_a_time(cuda_device):
+    m = _model(cuda_device, max_steps=24)
+    g = torch.Generator().manual_seed(5)
+    rows = [torch.randint(0, 40, (n,), generator=g).tolist() for n in (37, 9, 64, 23, 50, 12, 64)]
+    m.decoder.gate_layer.linear_layer.bias.data.fill_(-0.2)       # rows stop at different steps with random weights
+    batched = synthesis.batched_inference(m, rows, max_batch=4)
+    stops = []
+    for i, r in enumerate(rows):
+        single = m.inference({"tokens": torch.tensor(r, dtype=torch.int32, device=cuda_device).unsqueeze(0)})
+        stops.append(single["mel_outputs"].shape[2])
+        for k, v in single.items():
+            assert batched[i][k].shape == v.shape, (i, k, batched[i][k].shape, v.shape)
+            err = float((batched[i][k] - v).abs().max() / v.abs().max().clamp_min(1e-30))
+            assert err < 1e-4, (i, k, err)
+    assert len(set(stops)) > 1 or stops[0] == 24                   # the per-row stop really is per row
+
+
+def test_sharded_inference_covers_every_utterance_once(cuda_device):
+    m = _model(cuda_device, max_steps=6)
+    rows = [[1 + (i * 7 + k) % 39 for k in range(5 + i)] for i in range(7)]
+    full = synthesis.batched_inference(m, rows, ignore_gate=True)
+    seen = 0
+    for rank in range(3):
+        lo, part = synthesis.sharded_inference(m, rows, rank, 3, ignore_gate=True)
+        for j, o in enumerate(part):
+            assert torch.equal(o["mel_outputs"], full[lo + j]["mel_outputs"])
+        seen += len(part)
+    assert seen == len(rows)
+
+
+def test_model_train_step_updates_every_parameter(cuda_device):
+    dims = synth.DecoderDims()
+    torch.manual_seed(4)
+    m = _Model(dims).to(cuda_device).train()
+    m.decoder.precision = "bf16"
+    B, N, T = 8, 30, 12
+    g = torch.Generator().manual_seed(6)
+    batch = {"token_padded": torch.randint(0, 40, (B, N), generator=g).to(cuda_device),
+             "token_lengths": torch.full((B,), N, dtype=torch.int64, device=cuda_device),
+             "mel_padded": torch.randn(B, dims.n_mels, T, generator=g).to(cuda_device),
+             "gate_padded": torch.zeros(B, T, device=cuda_device)}
+
+    def criterion(batch, outputs):     # Tacotron2Loss, tacotron2.py:598-615
+        mel_loss = nn.functional.mse_loss(outputs["mel_outputs"], batch["mel_padded"]) + \
+            nn.functional.mse_loss(outputs["mel_outputs_postnet"], batch["mel_padded"])
+        gate_loss = nn.functional.binary_cross_entropy_with_logits(outputs["gate_outputs"].reshape(-1, 1),
+                                                                   batch["gate_padded"].reshape(-1, 1))
+        return {"loss": mel_loss + gate_loss, "mel_loss": mel_loss, "gate_loss": gate_loss}
+
+    opt = {"optimizer": torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-6)}
+    before = {k: v.detach().clone() for k, v in m.named_parameters()}
+    losses = [float(model_train_step(m, batch, {"loss": criterion}, opt)["loss"]) for _ in range(3)]
+    assert all(np.isfinite(v) for v in losses) and losses[-1] < losses[0]
+    for k, v in m.named_parameters():
+        assert not torch.equal(v.detach(), before[k]), k
