@@ -372,10 +372,10 @@ def main():
                     help="arithmetic of the recurrent GEMMs (BASELINE configs[2] is bf16; fp32 = parity mode)")
     args = ap.parse_args()
 
-    # watchdog: a run that has not finished after 15 minutes (the default run takes about one) dumps every thread's Python
+    # watchdog: a run that has not finished after 10 minutes (the default run takes about one) dumps every thread's Python
     # stack and exits instead of hanging its caller; GVX_BENCH_TRACE=1 adds per-stage progress lines on stderr
     import faulthandler
-    faulthandler.dump_traceback_later(int(os.environ.get("GVX_BENCH_TRACE_AFTER", "900")), exit=True)
+    faulthandler.dump_traceback_later(int(os.environ.get("GVX_BENCH_TRACE_AFTER", "600")), exit=True)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1 and "RANK" not in os.environ:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",

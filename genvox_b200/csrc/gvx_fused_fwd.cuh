@@ -725,7 +725,16 @@ inline bool fa_supported(const Dims &d, int B, int N) {
     if (d.A != FA_A || d.E != FA_E || d.D != AF_D || d.F != AF_F || d.KS != AF_KS) return false;
     if (B < 1 || B > PC_ROWS || N < 1 || N > FA_MAXN || sms < 128) return false;
     if (d.P % 8 != 0 || d.H % 8 != 0) return false;
-    return FaSmem(N).total <= 227 * 1024;
+    const size_t smem = FaSmem(N).total;
+    if (smem > 227 * 1024) return false;
+    // all 128 CTAs (64 clusters of 2) must be resident at once: ask the occupancy calculator for this shared-memory size
+    static size_t cached_smem = 0;
+    static bool cached = false;
+    if (cached_smem != smem) {
+        cached = 2 * max_resident_clusters(k_att_chain_fwd, FA_THREADS, smem, FA_CLUSTER, 128) >= 128;
+        cached_smem = smem;
+    }
+    return cached;
 }
 inline int &fa_mode() {        // -1 = not yet read from the environment, 0 = off, 1 = on
     static int on = -1;

@@ -509,7 +509,36 @@ inline size_t pc_smem_bytes(int H, bool bwd) {
     return (size_t)R * PC_CHUNK_BYTES + (size_t)nchunk * 4096 + (bwd ? PC_N * PC_ROWS * 4 : 0) + sizeof(PcShared) + 8192 + 1024;
 }
 
-// can the persistent chain run for this shape on the current device?
+// how many clusters of `cluster` CTAs (block size / dynamic shared memory given) the device keeps resident at once
+template <class Kern>
+inline int max_resident_clusters(Kern kern, int threads, size_t smem, int cluster, int grid) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// can the persistent chain run for this shape on the current device?  (every CTA of the grid must be resident at once: the
+// kernels synchronise through grid-wide barriers)
+inline bool pc_coresident(int H);
 inline bool pc_supported(int H, int B) {
     static int sms = -1;
     if (sms < 0) {
@@ -520,7 +549,7 @@ inline bool pc_supported(int H, int B) {
     if (H % 32 != 0 || H < 32 || B < 1 || B > PC_ROWS) return false;
     if (H / 8 > sms || (H + 63) / 64 > PC_MAXRING) return false;
     if (pc_smem_bytes(H, true) > 227 * 1024) return false;
-    return true;
+    return pc_coresident(H);
 }
 inline int &pc_mode() {        // -1 = not yet read from the environment, 0 = off, 1 = on
     static int on = -1;
@@ -538,6 +567,19 @@ inline bool pc_enabled() {
 inline long long *&pc_dbg_buffer() {
     static long long *p = nullptr;
     return p;
+}
+
+inline bool pc_coresident(int H) {
+    static int cached_H = -1;
+    static bool cached = false;
+    if (cached_H != H) {
+        const int grid = H / 8;
+        const int fwd = max_resident_clusters(k_lstm_chain_fwd, PCF_THREADS, pc_smem_bytes(H, false), 1, grid);
+        const int bwd = max_resident_clusters(k_lstm_chain_bwd, PCF_THREADS, pc_smem_bytes(H, true), 4, grid);
+        cached = fwd >= grid && 4 * bwd >= grid;
+        cached_H = H;
+    }
+    return cached;
 }
 
 inline int launch_lstm_chain_fwd(const PcFwdArgs &a_in, cudaStream_t st) {
