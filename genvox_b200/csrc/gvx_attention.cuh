@@ -10,6 +10,7 @@
 // Backward recomputes conv / loc / tanh from the stashed (w_{t-1}, cum_{t-1}, q) instead of
 // saving the [N, D] activations (1168*N bytes per sample-step in the reference).
 #pragma once
+#include <cuda_bf16.h>
 #include "gvx_common.cuh"
 #include "gvx_io.cuh"
 
@@ -247,6 +248,10 @@ struct AttnBwdArgs {
     float *dq_out;             // [B, D] d processed query (fp32) or null
     BfDsts dq_bf;              // bf16 copies of d q (bf16 mode)
     float *dconv_out;          // [B, N, F] d conv output
+    // optional (2-CTA cluster kernel only): d h_att from the query projection, dhq_out[b, u] = sum_d bf16(d q[b, d]) * WqB[d, u]
+    const __nv_bfloat16 *WqB;  // [D, A] row-major bf16 W_query, or null
+    float *dhq_out;            // [B, A]
+    int A;
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_bwd(const AttnBwdArgs a) {

@@ -409,10 +409,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
         sm[L.dqp + tid] = q;
     }
     cluster.sync();          // both CTAs' d conv rows and partial d q are complete
-    if (rank == 0 && tid < AF_D) {
-        const float q = sm[L.dqp + tid] + peer_sm[L.dqp + tid];
-        if (a.dq_out) a.dq_out[(size_t)b * AF_D + tid] = q;
-        if (a.dq_bf.n) bf_store1(a.dq_bf, b, tid, q);
+    if (tid < AF_D) {
+        const float mine = sm[L.dqp + tid], other = peer_sm[L.dqp + tid];
+        const float q = rank == 0 ? mine + other : other + mine;      // always rank 0 + rank 1
+        if (rank == 0) {
+            if (a.dq_out) a.dq_out[(size_t)b * AF_D + tid] = q;
+            if (a.dq_bf.n) bf_store1(a.dq_bf, b, tid, q);
+        }
+        // operand of the folded query-projection transpose below (rounded to bf16 like the GEMM engine's operands);
+        // the per-warp d q partials that lived here are consumed
+        if (a.dhq_out) sm[L.dq + tid] = __bfloat162float(__float2bfloat16(q));
     }
     // ---- 15-token halo of d conv from the peer: rank 0 needs the peer's first tokens, rank 1 the peer's last
     for (int i = tid; i < AF_F * AF_PAD; i += AF_THREADS) {
@@ -453,6 +459,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
             dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
             dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
+        // ---- d h_att through the query projection (tacotron2.py:98 transposed), folded in here: the conv transpose above
+        // keeps only ntask <= 192 threads busy, the others contract d q with W_query - each CTA of the pair half of the
+        // units, a thread two of them (bf16x2 weight loads, coalesced along the unit axis, all D loads independent).
+        // This used to be a separate K = 128 launch of the GEMM engine (two k-blocks on 8 CTAs, ~6 us per step).
+        if (a.dhq_out && tid >= 192) {
+            const int halfA = a.A / 2;
+            for (int u2 = tid - 192; 2 * u2 < halfA; u2 += AF_THREADS - 192) {
+                const int u = rank * halfA + 2 * u2;
+                const __nv_bfloat16 *wp = a.WqB + u;
+                float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 16
+                for (int dd = 0; dd < AF_D; ++dd) {
+                    const __nv_bfloat162 w2 = *reinterpret_cast<const __nv_bfloat162 *>(wp + (size_t)dd * a.A);
+                    const float qv = sm[L.dq + dd];
+                    acc0 = fmaf(qv, __bfloat162float(w2.x), acc0);
+                    acc1 = fmaf(qv, __bfloat162float(w2.y), acc1);
+                }
+                *reinterpret_cast<float2 *>(a.dhq_out + (size_t)b * a.A + u) = make_float2(acc0, acc1);
+            }
+        }
     }
     __syncthreads();
     for (int idx = tid; idx < 2 * n_own; idx += AF_THREADS) {
@@ -492,10 +518,16 @@ inline int launch_attention_fwd_best(const AttnFwdArgs &a, cudaStream_t stream) 
     return 0;
 }
 
+inline bool attention_bwd_uses_c2(const AttnShape &s) {
+    const AttnC2BwdSmem L(s.N, s.E);
+    const size_t bytes = (size_t)L.total * sizeof(float);
+    return attention_c2_enabled() && attention_fast_ok(s) && s.B <= 74 && s.N >= 32 && s.E % 8 == 0 && bytes <= 200 * 1024;
+}
+
 inline int launch_attention_bwd_best(const AttnBwdArgs &a, cudaStream_t stream) {
     const AttnC2BwdSmem L(a.s.N, a.s.E);
     const size_t bytes = (size_t)L.total * sizeof(float);
-    if (!attention_c2_enabled() || !attention_fast_ok(a.s) || a.s.B > 74 || a.s.N < 32 || a.s.E % 8 != 0 || bytes > 200 * 1024)
+    if (!attention_bwd_uses_c2(a.s))
         return launch_attention_bwd_any(a, stream);
     static size_t configured = 0;
     if (bytes > configured) {

@@ -101,11 +101,12 @@ int pack_weights_bf16(const Dims &d, const gvx_weights *w, float *packed, cudaSt
         k_pc_pack_w<<<grid_for(pc_wimg_elems(d.H)), 256, 0, st>>>(w->dec_w_hh, d.H, d.H, 1, (bf16 *)(packed + BL.WdhhTI));
         GVX_LAUNCHED(2);
     }
+    k_to_bf16<<<grid_for((size_t)d.D * d.A), 256, 0, st>>>(w->query_w, d.A, (size_t)d.D, d.A, (bf16 *)(packed + BL.WqB), d.A);
+    GVX_LAUNCHED(1);
     if (d.A == FA_A && d.E == FA_E) {
         k_fa_pack_w<<<grid_for(fa_wimg_elems()), 256, 0, st>>>(packed + PL.Wa, d.Ka, d.P, (bf16 *)(packed + BL.WaRecI));
         k_to_bf16<<<grid_for((size_t)4 * d.A * d.P), 256, 0, st>>>(packed + PL.Wa, d.Ka, (size_t)4 * d.A, d.P, (bf16 *)(packed + BL.WaPRM), d.P);
-        k_to_bf16<<<grid_for((size_t)d.D * d.A), 256, 0, st>>>(w->query_w, d.A, (size_t)d.D, d.A, (bf16 *)(packed + BL.WqB), d.A);
-        GVX_LAUNCHED(3);
+        GVX_LAUNCHED(2);
     }
     GVX_CUDA(cudaGetLastError());
     return 0;
@@ -585,6 +586,10 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     // vs 10.6 ms per train step, whole step 73.1 vs 65.8 ms): its 128 blocks serialise staging, contraction and the
     // latency-bound cell backward, while the two-launch version overlaps them through programmatic dependent launch
     static const bool s4_fused = getenv("GVX_S4_FUSED") && getenv("GVX_S4_FUSED")[0] == '1';
+    // d q . W_query folded into the 2-CTA cluster attention-backward kernel (its conv-transpose phase leaves 320 threads idle):
+    // one launch less per step.  GVX_DHQ_FOLDED=0 restores the separate engine GEMM.
+    static const bool dhq_env = !(getenv("GVX_DHQ_FOLDED") && getenv("GVX_DHQ_FOLDED")[0] == '0');
+    const bool dhq_folded = dhq_env && !s4_fused && d.A % 4 == 0 && attention_bwd_uses_c2(AttnShape{B, N, d.D, d.E, d.F, d.KS});
     pdl_barrier_next();
     for (int t = T - 1; t >= 0; --t) {
         const bool last = t == T - 1;
@@ -624,6 +629,7 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
             a.dq_out = nullptr;
             add_img(a.dq_bf, DQI, 0, NPAD); add_rm(a.dq_bf, DQRM + (size_t)t * B * d.D, 0, d.D);
             a.dconv_out = x + W.DCONV + (size_t)t * B * N * d.F;
+            if (dhq_folded) { a.WqB = (const bf16 *)(packed + BL.WqB); a.dhq_out = x + W.PS4; a.A = d.A; }
             GVX_TRY(launch_attention_bwd_best(a, st));
         }
         {   // S4: d h_att = d q . W_query + (from decoder-LSTM input) + (from step t+1), attention-LSTM pointwise backward
@@ -641,8 +647,8 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
                                           last ? nullptr : &dpre, last ? nullptr : s + S.PRE2 + (size_t)(t + 1) * B * d.P,
                                           last ? nullptr : x + W.DZ2 + (size_t)(t + 1) * B * d.P, st));
             } else {
-                GVX_TRY(run_tc(WqTI, DQI, x + W.PS4, gm.TqT, gm.Dp, W.KSs4, B, err, st));
-                GVX_TRY(run_bf_lstm_bwd(d, 0, src_split(x + W.PS4, lds4, W.KSs4, (long long)B * lds4), s1, s2,
+                if (!dhq_folded) GVX_TRY(run_tc(WqTI, DQI, x + W.PS4, gm.TqT, gm.Dp, W.KSs4, B, err, st));
+                GVX_TRY(run_bf_lstm_bwd(d, 0, dhq_folded ? src_plain(x + W.PS4, d.A) : src_split(x + W.PS4, lds4, W.KSs4, (long long)B * lds4), s1, s2,
                                         s + S.GA + (size_t)t * 4 * BA, s + S.CA + t * BA, s + S.CA + (t + 1) * BA, x + W.DCA, dg, B, seed,
                                         t, training, row_offset, last ? nullptr : &dpre, last ? nullptr : s + S.PRE2 + (size_t)(t + 1) * B * d.P,
                                         last ? nullptr : x + W.DZ2 + (size_t)(t + 1) * B * d.P, st));
