@@ -252,6 +252,9 @@ struct AttnBwdArgs {
     const __nv_bfloat16 *WqB;  // [D, A] row-major bf16 W_query, or null
     float *dhq_out;            // [B, A]
     int A;
+    const __nv_bfloat16 *memb; // optional bf16 copy of `memory` [B, N, E] (2-CTA cluster kernel: operand of d w in bf16 mode)
+    long long *dbg;            // optional clock64 stamps of CTA 0 (gvx_debug_timeline), row dbg_t
+    int dbg_t;
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_bwd(const AttnBwdArgs a) {

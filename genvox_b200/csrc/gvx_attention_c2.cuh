@@ -264,7 +264,7 @@ struct AttnC2BwdSmem {
         dconvT = take(AF_F * g.NDS);
         dq = take(AF_WARPS * AF_D);
         dqp = take(AF_D);       // this CTA's partial d q, read by rank 0
-        part = take(8 * 2 * g.NH);
+        part = take(AF_F * 2 * g.NH > 4096 ? AF_F * 2 * g.NH : 4096);      // conv-transpose partials, then [8][A/2] d h_q partials (A <= 1024)
         xch = take(8);
         scratch = take(64);
         ths = take(g.NH * AF_D);    // stashed tanh rows of the own tokens, prefetched with cp.async in the PDL prologue
@@ -285,6 +285,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
     const int n_own = max(0, min(N, n_lo + G.NH) - n_lo);
     const int own_len = max(0, min(len, n_lo + n_own) - n_lo);     // unmasked own tokens
 
+    if (a.dbg && blockIdx.x == 0 && tid == 0 && a.dbg_t < 1024) a.dbg[a.dbg_t * 32 + 0] = clock64();
     pdl_trigger();
     {   // the forward pass wrote the tanh stash long ago: asynchronous prefetch of the own tokens' rows
         const float *src = a.th + ((size_t)b * N + n_lo) * AF_D;
@@ -299,6 +300,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
     for (int i = tid; i < AF_F * 2 * AF_KS; i += AF_THREADS) sm[L.wlc + i] = a.wlc[i];
     for (int i = tid; i < AF_F * G.NDS; i += AF_THREADS) sm[L.dconvT + i] = 0.f;
     pdl_wait();
+    if (a.dbg && blockIdx.x == 0 && tid == 0 && a.dbg_t < 1024) a.dbg[a.dbg_t * 32 + 1] = clock64();
     for (int e = tid; e < E; e += AF_THREADS) {
         float x = src_get(a.dctx1, b, e);
         if (a.dctx2.nsplit) x += src_get(a.dctx2, b, e);
@@ -309,29 +311,115 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
     for (int n = tid; n < G.NH; n += AF_THREADS) sm[L.w + n] = n < n_own ? a.w_t[(size_t)b * a.w_bstride + n_lo + n] : 0.f;
     cp_async_wait<0>();
     __syncthreads();
+    if (a.dbg && blockIdx.x == 0 && tid == 0 && a.dbg_t < 1024) a.dbg[a.dbg_t * 32 + 2] = clock64();
 
     // ---- d w of the own tokens
     {
         const float *mem_b = a.memory + ((size_t)b * N + n_lo) * E;
-        for (int n = wid; n < G.NH; n += AF_WARPS) {
-            float dw = 0.f;
-            if (n < own_len) {
-                float part = 0.f;
-                for (int e = lane * 4; e < E; e += 128) {
-                    const float4 m = *reinterpret_cast<const float4 *>(mem_b + (size_t)n * E + e);
-                    const float4 g4 = *reinterpret_cast<const float4 *>(sm + L.dctx + e);
-                    part = fmaf(m.x, g4.x, part); part = fmaf(m.y, g4.y, part);
-                    part = fmaf(m.z, g4.z, part); part = fmaf(m.w, g4.w, part);
+        // a warp owns tokens wid, wid + 16, ...; it works on up to 3 of them at a time with every memory / carry load of
+        // the batch issued before the first use (the rolled per-token loop paid one L2 round trip + one shuffle tree each)
+        constexpr int DWB = 3;
+        if (a.memb) {
+            // bf16 copy of the encoder memory (written by the fused forward chain): half the L2 traffic of the phase, which is
+            // bound by it (19.7 MB of fp32 memory per step over all CTAs = 3100 cycles at the L2 throughput cap)
+            const __nv_bfloat16 *memb_b = a.memb + ((size_t)b * N + n_lo) * E;
+            constexpr int DWQ = 5;                 // all tokens of the warp at once: 5 x 2 x 16 B per lane
+            for (int n0 = wid; n0 < G.NH; n0 += AF_WARPS * DWQ) {
+                uint4 mv[DWQ][2];
+                float carry[DWQ];
+#pragma unroll
+                for (int q = 0; q < DWQ; ++q) {
+                    const int n = n0 + q * AF_WARPS;
+                    const bool live = n < own_len;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int e = lane * 8 + 256 * i;
+                        mv[q][i] = live && e < E ? __ldg(reinterpret_cast<const uint4 *>(memb_b + (size_t)n * E + e)) : make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    carry[q] = 0.f;
+                    if (live) {
+                        const size_t gi = (size_t)b * N + n_lo + n;
+                        carry[q] = a.dw_carry[gi] + a.dcum_carry[gi];
+                        if (a.d_align) carry[q] += a.d_align[(size_t)b * a.da_bstride + n_lo + n];
+                    }
                 }
-                part = warp_sum(part);
-                const size_t gi = (size_t)b * N + n_lo + n;
-                dw = part + a.dw_carry[gi] + a.dcum_carry[gi];
-                if (a.d_align) dw += a.d_align[(size_t)b * a.da_bstride + n_lo + n];
+                float part[DWQ];
+#pragma unroll
+                for (int q = 0; q < DWQ; ++q) {
+                    part[q] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int e = lane * 8 + 256 * i;
+                        if (e < E) {
+                            const float4 g0 = *reinterpret_cast<const float4 *>(sm + L.dctx + e);
+                            const float4 g1 = *reinterpret_cast<const float4 *>(sm + L.dctx + e + 4);
+                            const uint4 m = mv[q][i];
+                            part[q] = fmaf(__uint_as_float(m.x << 16), g0.x, part[q]); part[q] = fmaf(__uint_as_float(m.x & 0xffff0000u), g0.y, part[q]);
+                            part[q] = fmaf(__uint_as_float(m.y << 16), g0.z, part[q]); part[q] = fmaf(__uint_as_float(m.y & 0xffff0000u), g0.w, part[q]);
+                            part[q] = fmaf(__uint_as_float(m.z << 16), g1.x, part[q]); part[q] = fmaf(__uint_as_float(m.z & 0xffff0000u), g1.y, part[q]);
+                            part[q] = fmaf(__uint_as_float(m.w << 16), g1.z, part[q]); part[q] = fmaf(__uint_as_float(m.w & 0xffff0000u), g1.w, part[q]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int q = 0; q < DWQ; ++q) part[q] += __shfl_xor_sync(0xffffffffu, part[q], o);
+                }
+#pragma unroll
+                for (int q = 0; q < DWQ; ++q) {
+                    const int n = n0 + q * AF_WARPS;
+                    if (lane == 0 && n < G.NH) sm[L.de + n] = n < own_len ? part[q] + carry[q] : 0.f;
+                }
             }
-            if (lane == 0) sm[L.de + n] = dw;
+        } else
+        for (int n0 = wid; n0 < G.NH; n0 += AF_WARPS * DWB) {
+            float4 mv[DWB][4];
+            float carry[DWB];
+#pragma unroll
+            for (int q = 0; q < DWB; ++q) {
+                const int n = n0 + q * AF_WARPS;
+                const bool live = n < own_len;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int e = lane * 4 + 128 * i;
+                    mv[q][i] = live && e < E ? *reinterpret_cast<const float4 *>(mem_b + (size_t)n * E + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                carry[q] = 0.f;
+                if (live) {
+                    const size_t gi = (size_t)b * N + n_lo + n;
+                    carry[q] = a.dw_carry[gi] + a.dcum_carry[gi];
+                    if (a.d_align) carry[q] += a.d_align[(size_t)b * a.da_bstride + n_lo + n];
+                }
+            }
+            float part[DWB];
+#pragma unroll
+            for (int q = 0; q < DWB; ++q) {
+                part[q] = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int e = lane * 4 + 128 * i;
+                    if (e < E) {
+                        const float4 g4 = *reinterpret_cast<const float4 *>(sm + L.dctx + e);
+                        part[q] = fmaf(mv[q][i].x, g4.x, part[q]); part[q] = fmaf(mv[q][i].y, g4.y, part[q]);
+                        part[q] = fmaf(mv[q][i].z, g4.z, part[q]); part[q] = fmaf(mv[q][i].w, g4.w, part[q]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int q = 0; q < DWB; ++q) part[q] += __shfl_xor_sync(0xffffffffu, part[q], o);
+            }
+#pragma unroll
+            for (int q = 0; q < DWB; ++q) {
+                const int n = n0 + q * AF_WARPS;
+                if (lane == 0 && n < G.NH) sm[L.de + n] = n < own_len ? part[q] + carry[q] : 0.f;
+            }
         }
     }
     __syncthreads();
+    if (a.dbg && blockIdx.x == 0 && tid == 0 && a.dbg_t < 1024) a.dbg[a.dbg_t * 32 + 3] = clock64();
     // ---- softmax backward: <w, dw> over the whole row = rank 0 part + rank 1 part
     const float *peer_sm = cluster.map_shared_rank(sm, peer);
     {
@@ -349,6 +437,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
         }
     }
     __syncthreads();
+    if (a.dbg && blockIdx.x == 0 && tid == 0 && a.dbg_t < 1024) a.dbg[a.dbg_t * 32 + 4] = clock64();
 
     // ---- d s, partial d q, d conv of the own tokens
     {
@@ -409,6 +498,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
         sm[L.dqp + tid] = q;
     }
     cluster.sync();          // both CTAs' d conv rows and partial d q are complete
+    if (a.dbg && blockIdx.x == 0 && tid == 0 && a.dbg_t < 1024) a.dbg[a.dbg_t * 32 + 5] = clock64();
     if (tid < AF_D) {
         const float mine = sm[L.dqp + tid], other = peer_sm[L.dqp + tid];
         const float q = rank == 0 ? mine + other : other + mine;      // always rank 0 + rank 1
@@ -427,19 +517,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
         else sm[L.dconvT + f * G.NDS + h] = peer_sm[L.dconvT + f * G.NDS + G.NH + h];
     }
     __syncthreads();
+    if (a.dbg && blockIdx.x == 0 && tid == 0 && a.dbg_t < 1024) a.dbg[a.dbg_t * 32 + 6] = clock64();
 
     // ---- d wcat of the own tokens
     {
-        const int ntask = 2 * G.nblk * 8;
+        // one task = (filter f, channel c, block of 8 tokens): F * 2 * nblk = 640 tasks keep all 512 threads busy (the
+        // first version looped 4 filters per task: 160 tasks, five warps' worth of work on the critical path)
+        const int ntask = 2 * G.nblk * AF_F;
         for (int task = tid; task < ntask; task += AF_THREADS) {
-            const int fg = task & 7, rest = task >> 3;
+            const int f = task & (AF_F - 1), rest = task >> 5;
             const int c = rest / G.nblk, m0 = (rest - c * G.nblk) * 8;
             float acc[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll 1
-            for (int ff = 0; ff < 4; ++ff) {
-                const int f = fg * 4 + ff;
+            {
                 float x[40];
                 const float4 *xr = reinterpret_cast<const float4 *>(sm + L.dconvT + f * G.NDS + m0);
 #pragma unroll
@@ -455,29 +546,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
                     for (int j = 0; j < 8; ++j) acc[j] = fmaf(wk, x[j - k + 30], acc[j]);
                 }
             }
-            float4 *dst = reinterpret_cast<float4 *>(sm + L.part + (fg * 2 + c) * G.NH + m0);
+            float4 *dst = reinterpret_cast<float4 *>(sm + L.part + (f * 2 + c) * G.NH + m0);
             dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
             dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-        }
-        // ---- d h_att through the query projection (tacotron2.py:98 transposed), folded in here: the conv transpose above
-        // keeps only ntask <= 192 threads busy, the others contract d q with W_query - each CTA of the pair half of the
-        // units, a thread two of them (bf16x2 weight loads, coalesced along the unit axis, all D loads independent).
-        // This used to be a separate K = 128 launch of the GEMM engine (two k-blocks on 8 CTAs, ~6 us per step).
-        if (a.dhq_out && tid >= 192) {
-            const int halfA = a.A / 2;
-            for (int u2 = tid - 192; 2 * u2 < halfA; u2 += AF_THREADS - 192) {
-                const int u = rank * halfA + 2 * u2;
-                const __nv_bfloat16 *wp = a.WqB + u;
-                float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 16
-                for (int dd = 0; dd < AF_D; ++dd) {
-                    const __nv_bfloat162 w2 = *reinterpret_cast<const __nv_bfloat162 *>(wp + (size_t)dd * a.A);
-                    const float qv = sm[L.dq + dd];
-                    acc0 = fmaf(qv, __bfloat162float(w2.x), acc0);
-                    acc1 = fmaf(qv, __bfloat162float(w2.y), acc1);
-                }
-                *reinterpret_cast<float2 *>(a.dhq_out + (size_t)b * a.A + u) = make_float2(acc0, acc1);
-            }
         }
     }
     __syncthreads();
@@ -485,11 +556,55 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
         const int c = idx / n_own, m = idx - c * n_own;
         float s = 0.f;
 #pragma unroll
-        for (int fg = 0; fg < 8; ++fg) s += sm[L.part + (fg * 2 + c) * G.NH + m];
+        for (int f = 0; f < AF_F; ++f) s += sm[L.part + (f * 2 + c) * G.NH + m];
         const size_t gi = (size_t)b * N + n_lo + m;
         if (c == 0) a.dw_carry[gi] = s;
         else a.dcum_carry[gi] += s;
     }
+    // ---- d h_att through the query projection (tacotron2.py:98 transposed), folded in here (it used to be a separate K = 128
+    // launch of the GEMM engine: two k-blocks on 8 CTAs, ~6 us per step).  Each CTA of the pair takes half of the units:
+    // thread = (unit octet tid & 63, d slice tid >> 6 of 16 dims): 16 independent 16-byte loads of the bf16 W_query rows
+    // (coalesced along the unit axis) in two batches, then the 8 d slices are summed through shared memory in slice order.
+    if (a.dhq_out) {
+        __syncthreads();                       // the conv-transpose partials in L.part are consumed
+        const int halfA = a.A / 2;             // 512 units per CTA at the default dims
+        float *red = sm + L.part;              // [8 d slices][halfA]
+        for (int u0 = 0; u0 < halfA; u0 += 512) {
+            const int uo = tid & 63, ds = tid >> 6;
+            const int u = u0 + 8 * uo;
+            float acc[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+            if (u < halfA) {
+                const __nv_bfloat16 *wp = a.WqB + (size_t)(16 * ds) * a.A + rank * halfA + u;
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    uint4 wv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) wv[i] = __ldg(reinterpret_cast<const uint4 *>(wp + (size_t)(8 * hb + i) * a.A));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float qv = sm[L.dq + 16 * ds + 8 * hb + i];
+                        acc[0] = fmaf(qv, __uint_as_float(wv[i].x << 16), acc[0]); acc[1] = fmaf(qv, __uint_as_float(wv[i].x & 0xffff0000u), acc[1]);
+                        acc[2] = fmaf(qv, __uint_as_float(wv[i].y << 16), acc[2]); acc[3] = fmaf(qv, __uint_as_float(wv[i].y & 0xffff0000u), acc[3]);
+                        acc[4] = fmaf(qv, __uint_as_float(wv[i].z << 16), acc[4]); acc[5] = fmaf(qv, __uint_as_float(wv[i].z & 0xffff0000u), acc[5]);
+                        acc[6] = fmaf(qv, __uint_as_float(wv[i].w << 16), acc[6]); acc[7] = fmaf(qv, __uint_as_float(wv[i].w & 0xffff0000u), acc[7]);
+                    }
+                }
+                float4 *dst = reinterpret_cast<float4 *>(red + ds * halfA + u);
+                dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
+            __syncthreads();
+            for (int uu = u0 + tid; uu < min(u0 + 512, halfA); uu += AF_THREADS) {
+                float v = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v += red[k * halfA + uu];
+                a.dhq_out[(size_t)b * a.A + rank * halfA + uu] = v;
+            }
+        }
+    }
+    if (a.dbg && blockIdx.x == 0 && tid == 0 && a.dbg_t < 1024) a.dbg[a.dbg_t * 32 + 7] = clock64();
     cluster.sync();
 }
 
@@ -521,7 +636,8 @@ inline int launch_attention_fwd_best(const AttnFwdArgs &a, cudaStream_t stream) 
 inline bool attention_bwd_uses_c2(const AttnShape &s) {
     const AttnC2BwdSmem L(s.N, s.E);
     const size_t bytes = (size_t)L.total * sizeof(float);
-    return attention_c2_enabled() && attention_fast_ok(s) && s.B <= 74 && s.N >= 32 && s.E % 8 == 0 && bytes <= 200 * 1024;
+    // (the d w phase of the cluster kernel covers the encoder dim with 4 x 128-wide passes)
+    return attention_c2_enabled() && attention_fast_ok(s) && s.B <= 74 && s.N >= 32 && s.E % 8 == 0 && s.E <= 512 && bytes <= 200 * 1024;
 }
 
 inline int launch_attention_bwd_best(const AttnBwdArgs &a, cudaStream_t stream) {

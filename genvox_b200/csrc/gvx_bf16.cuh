@@ -41,10 +41,20 @@ __global__ void __launch_bounds__(256) k_bf_lstm_fwd(const BfLstmFwd a) {
         const int b = idx / a.HID, u = idx - b * a.HID;
         const int col = (u >> 5) * 128 + (u & 31);
         float pre[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int s = 0; s < a.KS; ++s) {
-            const float *row = a.P + ((size_t)s * a.B + b) * a.ldp + col;
+        for (int s0 = 0; s0 < a.KS; s0 += 4) {          // 16 independent loads in flight, summed in ascending split order
+            float v[4][4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) pre[g] += row[g * 32];
+            for (int s = 0; s < 4; ++s) {
+                const float *row = a.P + ((size_t)(s0 + s < a.KS ? s0 + s : s0) * a.B + b) * a.ldp + col;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) v[s][g] = row[g * 32];
+            }
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                if (s0 + s < a.KS) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) pre[g] += v[s][g];
+                }
         }
         const float4 bi = *reinterpret_cast<const float4 *>(a.bias + 4 * u);
         const float gi = sigmoidf_(pre[0] + bi.x), gf = sigmoidf_(pre[1] + bi.y);
@@ -199,7 +209,14 @@ __global__ void k_bf_finalize(const float *__restrict__ P, int KS, int B, int ld
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int b = i / M, m = i - b * M;
         float s = bias ? bias[m] : 0.f;
-        for (int k = 0; k < KS; ++k) s += P[((size_t)k * B + b) * ldp + m];
+        for (int k0 = 0; k0 < KS; k0 += 8) {           // loads first, adds after (ascending split order)
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = k0 + k < KS ? P[((size_t)(k0 + k) * B + b) * ldp + m] : 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k0 + k < KS) s += v[k];
+        }
         out[(size_t)b * ldo + m] = s;
     }
 }

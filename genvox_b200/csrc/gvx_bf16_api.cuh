@@ -589,7 +589,9 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     // d q . W_query folded into the 2-CTA cluster attention-backward kernel (its conv-transpose phase leaves 320 threads idle):
     // one launch less per step.  GVX_DHQ_FOLDED=0 restores the separate engine GEMM.
     static const bool dhq_env = !(getenv("GVX_DHQ_FOLDED") && getenv("GVX_DHQ_FOLDED")[0] == '0');
-    const bool dhq_folded = dhq_env && !s4_fused && d.A % 4 == 0 && attention_bwd_uses_c2(AttnShape{B, N, d.D, d.E, d.F, d.KS});
+    const bool dhq_folded = dhq_env && !s4_fused && d.A % 16 == 0 && d.A <= 1024 && attention_bwd_uses_c2(AttnShape{B, N, d.D, d.E, d.F, d.KS});
+    // the fused forward chain left a bf16 copy of the encoder memory in the stash: operand of d w in the attention backward
+    const bool have_memb = pc && fa_enabled() && fa_supported(d, B, N);
     pdl_barrier_next();
     for (int t = T - 1; t >= 0; --t) {
         const bool last = t == T - 1;
@@ -629,6 +631,9 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
             a.dq_out = nullptr;
             add_img(a.dq_bf, DQI, 0, NPAD); add_rm(a.dq_bf, DQRM + (size_t)t * B * d.D, 0, d.D);
             a.dconv_out = x + W.DCONV + (size_t)t * B * N * d.F;
+            a.dbg = pc_dbg_buffer() ? pc_dbg_buffer() + 32 * 1024 : nullptr;     // plane 1, row = frame (the decoder-LSTM BPTT chain
+            a.dbg_t = t;                                                         // of the same call wrote its stamps there before)
+            if (have_memb) a.memb = (const bf16 *)(s + S.MEMB);
             if (dhq_folded) { a.WqB = (const bf16 *)(packed + BL.WqB); a.dhq_out = x + W.PS4; a.A = d.A; }
             GVX_TRY(launch_attention_bwd_best(a, st));
         }
