@@ -252,6 +252,8 @@ struct AttnBwdArgs {
     const __nv_bfloat16 *WqB;  // [D, A] row-major bf16 W_query, or null
     float *dhq_out;            // [B, A]
     int A;
+    int dctx12_static;         // 1: dctx1 / dctx2 were complete before the launch chain began (time-batched GEMMs): the cluster
+                               // kernel may read them in its PDL prologue, before griddepcontrol.wait
     const __nv_bfloat16 *memb; // optional bf16 copy of `memory` [B, N, E] (2-CTA cluster kernel: operand of d w in bf16 mode)
     long long *dbg;            // optional clock64 stamps of CTA 0 (gvx_debug_timeline), row dbg_t
     int dbg_t;

@@ -299,16 +299,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
     }
     for (int i = tid; i < AF_F * 2 * AF_KS; i += AF_THREADS) sm[L.wlc + i] = a.wlc[i];
     for (int i = tid; i < AF_F * G.NDS; i += AF_THREADS) sm[L.dconvT + i] = 0.f;
+    // forward stash (alignments of this step) and, when they come from the time-batched GEMMs that ran before the chain, the
+    // two static d ctx contributions: DRAM-resident, so their latency is taken here, under the previous kernel (E <= 512:
+    // one element per thread)
+    for (int n = tid; n < G.NH; n += AF_THREADS) sm[L.w + n] = n < n_own ? a.w_t[(size_t)b * a.w_bstride + n_lo + n] : 0.f;
+    float x12 = 0.f;
+    if (a.dctx12_static && tid < E) {
+        x12 = src_get(a.dctx1, b, tid);
+        if (a.dctx2.nsplit) x12 += src_get(a.dctx2, b, tid);
+    }
     pdl_wait();
     if (a.dbg && blockIdx.x == 0 && tid == 0 && a.dbg_t < 1024) a.dbg[a.dbg_t * 32 + 1] = clock64();
-    for (int e = tid; e < E; e += AF_THREADS) {
-        float x = src_get(a.dctx1, b, e);
-        if (a.dctx2.nsplit) x += src_get(a.dctx2, b, e);
+    if (tid < E) {
+        const int e = tid;
+        float x = x12;
+        if (!a.dctx12_static) {
+            x = src_get(a.dctx1, b, e);
+            if (a.dctx2.nsplit) x += src_get(a.dctx2, b, e);
+        }
         if (a.dctx3.nsplit) x += src_get(a.dctx3, b, e);
         sm[L.dctx + e] = x;
         if (rank == 0) a.dctx_out[(size_t)b * E + e] = x;
     }
-    for (int n = tid; n < G.NH; n += AF_THREADS) sm[L.w + n] = n < n_own ? a.w_t[(size_t)b * a.w_bstride + n_lo + n] : 0.f;
     cp_async_wait<0>();
     __syncthreads();
     if (a.dbg && blockIdx.x == 0 && tid == 0 && a.dbg_t < 1024) a.dbg[a.dbg_t * 32 + 2] = clock64();

@@ -634,6 +634,7 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
             a.dbg = pc_dbg_buffer() ? pc_dbg_buffer() + 32 * 1024 : nullptr;     // plane 1, row = frame (the decoder-LSTM BPTT chain
             a.dbg_t = t;                                                         // of the same call wrote its stamps there before)
             if (have_memb) a.memb = (const bf16 *)(s + S.MEMB);
+            a.dctx12_static = pc ? 1 : 0;      // DHC and DXDALL are complete before the per-step chain starts
             if (dhq_folded) { a.WqB = (const bf16 *)(packed + BL.WqB); a.dhq_out = x + W.PS4; a.A = d.A; }
             GVX_TRY(launch_attention_bwd_best(a, st));
         }
