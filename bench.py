@@ -310,6 +310,9 @@ def run_ours(args, rank, world, local_rank):
                 if name == "attention" and fused:
                     # SURVEY.md 8(d) attention path per step: memory (bf16 copy) + processed memory (fp32) read, alignment written
                     nbytes = B * N * (E * 2.0 + D * 4.0) + B * N * 4.0
+                elif name == "bwd_attention" and phases.get("attention", {}).get("launches") == 1:
+                    # after the fused forward chain the BPTT attention kernel reads the bf16 memory copy + the fp32 tanh stash
+                    nbytes = B * N * (E * 2.0 + D * 4.0) + B * N * 4.0
                 else:
                     nbytes = B * N * (E + D) * 4.0 + B * N * 4.0    # memory + processed memory (or stashed tanh) + weights row
                 per_step_us = 1e3 * phases[name]["ms"] / T if fused else phases[name]["avg_us"]
