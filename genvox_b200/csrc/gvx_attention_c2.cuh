@@ -260,7 +260,7 @@ struct AttnC2BwdSmem {
         v = take(AF_D);
         wld4 = take(AF_D * AF_F);
         wlc = take(AF_F * 2 * AF_KS);
-        dsb = take(AF_WARPS * 4 * AF_D);
+        dsb = take(AF_WARPS * 6 * AF_D);          // up to 6 tokens per warp group in the backward dense transpose
         dconvT = take(AF_F * g.NDS);
         dq = take(AF_WARPS * AF_D);
         dqp = take(AF_D);       // this CTA's partial d q, read by rank 0
@@ -455,20 +455,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
     {
         const float4 v4 = *reinterpret_cast<const float4 *>(sm + L.v + lane * 4);
         float4 dqa = make_float4(0.f, 0.f, 0.f, 0.f);
-        float *dsb = sm + L.dsb + wid * 4 * AF_D;
-        const int ngrp = G.NH / 4;
+        // tokens per warp group: as many as it takes for ONE balanced round over the 16 warps (80 own tokens -> 16 groups
+        // of 5); with fixed groups of 4 there were 20 groups = two rounds with 12 warps idle in the second
+        constexpr int TGM = 6;
+        const int tg = min(TGM, max(4, (G.NH + AF_WARPS - 1) / AF_WARPS));
+        float *dsb = sm + L.dsb + wid * TGM * AF_D;
+        const int ngrp = (G.NH + tg - 1) / tg;
         for (int grp = wid; grp < ngrp; grp += AF_WARPS) {
-            const int n0 = grp * 4;
+            const int n0 = grp * tg;
             if (n0 >= own_len) {
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < tg; ++j)
                     if (n0 + j < n_own) a.dconv_out[((size_t)b * N + n_lo + n0 + j) * AF_F + lane] = 0.f;
                 continue;
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < TGM; ++j) {
                 const int n = n0 + j;
                 float4 ds = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n < own_len) {
+                if (j < tg && n < own_len) {
                     const float de = sm[L.de + n];
                     const float4 th = *reinterpret_cast<const float4 *>(sm + L.ths + n * AF_D + lane * 4);
                     ds.x = de * v4.x * (1.f - th.x * th.x);
@@ -477,23 +481,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
                     ds.w = de * v4.w * (1.f - th.w * th.w);
                     dqa.x += ds.x; dqa.y += ds.y; dqa.z += ds.z; dqa.w += ds.w;
                 }
-                *reinterpret_cast<float4 *>(dsb + j * AF_D + lane * 4) = ds;
+                if (j < tg) *reinterpret_cast<float4 *>(dsb + j * AF_D + lane * 4) = ds;
             }
             __syncwarp();
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            float acc[TGM];
+#pragma unroll
+            for (int j = 0; j < TGM; ++j) acc[j] = 0.f;
 #pragma unroll 8
             for (int dq = 0; dq < AF_D / 4; ++dq) {
                 const float4 w4 = *reinterpret_cast<const float4 *>(sm + L.wld4 + (dq * AF_F + lane) * 4);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 x = *reinterpret_cast<const float4 *>(dsb + j * AF_D + dq * 4);
-                    acc[j] = fmaf(x.x, w4.x, fmaf(x.y, w4.y, fmaf(x.z, w4.z, fmaf(x.w, w4.w, acc[j]))));
+                for (int j = 0; j < TGM; ++j) {
+                    if (j < tg) {
+                        const float4 x = *reinterpret_cast<const float4 *>(dsb + j * AF_D + dq * 4);
+                        acc[j] = fmaf(x.x, w4.x, fmaf(x.y, w4.y, fmaf(x.z, w4.z, fmaf(x.w, w4.w, acc[j]))));
+                    }
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < TGM; ++j) {
                 const int n = n0 + j;
-                if (n < n_own) {
+                if (j < tg && n < n_own) {
                     sm[L.dconvT + lane * G.NDS + n + AF_PAD] = acc[j];       // local index = local token + 15
                     a.dconv_out[((size_t)b * N + n_lo + n) * AF_F + lane] = acc[j];
                 }
