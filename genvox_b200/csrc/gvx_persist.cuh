@@ -122,13 +122,19 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
-// Forward chain.  512 threads: warp 2 = TMA producer, warp 3 = MMA issuer (one elected lane each, lean single-thread
+// Forward chain.  576 threads: warp 16 = TMA producer, warp 17 = MMA issuer (one elected lane each, lean single-thread
 // loops: no per-chunk empty barriers - the whole h image fits the ring and the grid barrier of step t already implies
-// that this CTA's MMAs of step t-1 have drained), warps {0,1,4,5,8,9,12,13} = epilogue: TMEM lane quadrant = warp & 1
-// (batch rows), column quarter = warp >> 2 (two hidden units per thread).
-constexpr int PCF_THREADS = 512;
+// that this CTA's MMAs of step t-1 have drained), warps 0..15 = epilogue.  The MMA is UMMA 64 x 32 x 16: the 64 batch rows
+// are exactly the M side (no over-read of ignored rows: 3 KB of operands per MMA instead of 5 KB), and an M = 64
+// accumulator lives in lanes 0..15 of each TMEM lane quadrant: row b -> lane (b & 15) + 32 (b >> 4).  Epilogue warp w
+// therefore owns quadrant w & 3 (rows 16 (w & 3) .. +15 in its lower 16 lanes) and column quarter w >> 2 (two units).
+// Measured: the MMA phase (2.4 us of the 5.6 us step) is NOT tensor-bound - issuing every MMA 2x / 4x adds only ~22 cycles
+// per extra 64x32x16 MMA - it is the 128 KB h image per CTA arriving at the chip-wide L2 throughput cap (~4900 B/cycle over
+// 128 CTAs); a cluster multicast of the image is the remaining lever.
+constexpr int PCF_THREADS = 512;           // backward chain (UMMA M = 128)
+constexpr int PCF64_THREADS = 576;
 
-__global__ void __launch_bounds__(PCF_THREADS, 1) k_lstm_chain_fwd(const PcFwdArgs a) {
+__global__ void __launch_bounds__(PCF64_THREADS, 1) k_lstm_chain_fwd(const PcFwdArgs a) {
     extern __shared__ uint8_t smem_raw[];
     // 1 KB alignment computed as an OFFSET into the shared array: the compiler keeps the shared address space (LDS/STS,
     // not generic LD/ST) for everything derived from it
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(PCF_THREADS, 1) k_lstm_chain_fwd(const PcFwdAr
     tc_fence_after();
     const uint32_t tmem_base = sh->tmem_slot;
 
-    if (warp == 2) {
+    if (warp == 16) {
         // ------------------------------------------------ TMA producer
         if (elect_one()) {
             mbar_expect_tx(&sh->wbar, wbytes);
@@ -183,10 +189,10 @@ __global__ void __launch_bounds__(PCF_THREADS, 1) k_lstm_chain_fwd(const PcFwdAr
             }
         }
         __syncwarp();
-    } else if (warp == 3) {
+    } else if (warp == 17) {
         // ------------------------------------------------ MMA issuer
         if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, PC_N);
+            constexpr uint32_t idesc = umma_idesc_bf16(64, PC_N);
             bool ok = pc_mbar_wait(&sh->wbar, 0, &sh->dead, a.err, 13);
             const uint64_t a0 = umma_desc_sw128(smem_u32(ring)), b0 = umma_desc_sw128(smem_u32(wsm));
             for (int t = 0; t < T && ok; ++t) {
@@ -207,10 +213,10 @@ __global__ void __launch_bounds__(PCF_THREADS, 1) k_lstm_chain_fwd(const PcFwdAr
             }
         }
         __syncwarp();
-    } else if ((warp & 2) == 0) {
-        // ------------------------------------------------ epilogue: one thread = one batch row, 2 hidden units
-        const int b = (warp & 1) * 32 + lane, cq = warp >> 2;
-        const bool valid = b < a.B;
+    } else {
+        // ------------------------------------------------ epilogue: one thread (lower half-warp) = one batch row, 2 hidden units
+        const int b = (warp & 3) * 16 + (lane & 15), cq = warp >> 2;
+        const bool valid = lane < 16 && b < a.B;
         const int u0 = 8 * j + 2 * cq;
         float c[2];
         float4 bi[2];
@@ -219,7 +225,7 @@ __global__ void __launch_bounds__(PCF_THREADS, 1) k_lstm_chain_fwd(const PcFwdAr
             c[i] = valid ? a.c_stash[(size_t)b * H + u0 + i] : 0.f;
             bi[i] = a.bias ? *reinterpret_cast<const float4 *>(a.bias + 4 * (u0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 1) * 32) << 16) + (uint32_t)(8 * cq);
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(8 * cq);
         // 4-byte slot of this thread inside the 16-byte chunk (units 8j..8j+7 of row b) of the swizzled h image
         const size_t himg_off = (size_t)(j >> 3) * PC_CHUNK_BYTES + b * 128 + (((j & 7) ^ (b & 7)) << 4) + 4 * cq;
         bool ok = true;
@@ -257,7 +263,7 @@ __global__ void __launch_bounds__(PCF_THREADS, 1) k_lstm_chain_fwd(const PcFwdAr
                 fence_proxy_async_global();
             }
             if (threadIdx.x == 0) pc_stamp(a.dbg, j, t, 4);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 512;" ::: "memory");
             // release at gpu scope is cumulative over the stores ordered before it by the CTA barrier
             if (threadIdx.x == 0) { gbar_arrive(a.bar); pc_stamp(a.dbg, j, t, 6); }
             if (ok && valid) {
@@ -574,7 +580,7 @@ inline bool pc_coresident(int H) {
     static bool cached = false;
     if (cached_H != H) {
         const int grid = H / 8;
-        const int fwd = max_resident_clusters(k_lstm_chain_fwd, PCF_THREADS, pc_smem_bytes(H, false), 1, grid);
+        const int fwd = max_resident_clusters(k_lstm_chain_fwd, PCF64_THREADS, pc_smem_bytes(H, false), 1, grid);
         const int bwd = max_resident_clusters(k_lstm_chain_bwd, PCF_THREADS, pc_smem_bytes(H, true), 4, grid);
         cached = fwd >= grid && 4 * bwd >= grid;
         cached_H = H;
@@ -592,7 +598,7 @@ inline int launch_lstm_chain_fwd(const PcFwdArgs &a_in, cudaStream_t st) {
         configured = smem;
     }
     GVX_CUDA(cudaMemsetAsync(a.bar, 0, sizeof(unsigned), st));
-    k_lstm_chain_fwd<<<a.H / 8, PCF_THREADS, smem, st>>>(a);
+    k_lstm_chain_fwd<<<a.H / 8, PCF64_THREADS, smem, st>>>(a);
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     return 0;
