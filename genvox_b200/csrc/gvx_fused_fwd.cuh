@@ -753,7 +753,6 @@ inline int launch_att_chain_fwd(const FaArgs &a_in, cudaStream_t st) {
     FaArgs a = a_in;
     a.dbg = pc_dbg_buffer() ? pc_dbg_buffer() + 3 * 32 * 1024 : nullptr;                // fourth plane: fused-chain stamps
     a.prog = pc_dbg_buffer() ? (int *)(pc_dbg_buffer() + 2 * 32 * 1024) : nullptr;     // third plane of the debug buffer
-    if (getenv("GVX_DEBUG_NO_TH")) a.th_stash = nullptr;      // experiment only: the backward pass needs this stash
     const size_t smem = FaSmem(a.N).total;
     static size_t configured = 0;
     if (configured < smem) {
