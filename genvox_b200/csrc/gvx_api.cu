@@ -2,6 +2,7 @@
 // and the single-phase hooks used by the parity tests.  See include/genvox_b200.h for the
 // contract and the reference file:line each entry point replaces.
 #include "../../include/genvox_b200.h"
+#include "gvx_infer_prenet.cuh"
 #include "gvx_attention_c2.cuh"
 #include "gvx_common.cuh"
 #include "gvx_gemm.cuh"
@@ -336,10 +337,12 @@ static int infer_body(const gvx_dims *dd, const gvx_weights *w, const void *pack
     GVX_CUDA(cudaMemsetAsync(s + L.WPREV, 0, (size_t)B * N * sizeof(float), st));
     GVX_CUDA(cudaMemsetAsync(s + L.CUM, 0, (size_t)B * N * sizeof(float), st));
     GVX_CUDA(cudaMemsetAsync(s + L.ZERO, 0, (size_t)B * d.OL * sizeof(float), st));
-    GVX_CUDA(cudaMemsetAsync(flags, 0, 32 * sizeof(int), st));
+    GVX_CUDA(cudaMemsetAsync(flags, 0, 32 * sizeof(int), st));       // [0] rows still running; [32..33] hold the dropout seed (gvx_dec_infer)
+    GVX_CUDA(cudaMemsetAsync(flags + 40, 0, 2 * sizeof(int), st));   // [40] prenet grid barrier, [41] its error word
     k_fill_i32<<<grid_for(B), 256, 0, st>>>(n_frames, B, ignore_gate ? max_steps : -1, 0);
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
+    const bool fused_prenet = infer_prenet_fused_ok(d, B);
 
     int t = 0, host_running = B;
     pdl_barrier_next();
@@ -347,7 +350,12 @@ static int infer_body(const gvx_dims *dd, const gvx_weights *w, const void *pack
         const int cur = t & 1, nxt = cur ^ 1;
         // prenet on the previous mel frame, dropout on (tacotron2.py:398, :143)
         const float *prev = t == 0 ? s + L.ZERO : s + L.OUT + (size_t)(t - 1) * B * d.OL;
-        { ProfScope ps(PS_PRENET, st); GVX_TRY(run_prenet(d, w, prev, d.OL, B, B, seed, t, row_offset, s + L.PRE1, s + L.PRE2, st)); }
+        { ProfScope ps(PS_PRENET, st);
+          if (fused_prenet) {
+              GVX_TRY(run_infer_prenet(d, w, prev, d.OL, B, seed, t, row_offset, s + L.PRE1, s + L.PRE2, nullptr, (unsigned *)(flags + 40), flags + 41, st));
+          } else {
+              GVX_TRY(run_prenet(d, w, prev, d.OL, B, B, seed, t, row_offset, s + L.PRE1, s + L.PRE2, st));
+          } }
         LstmIO a;
         a.x0 = s + L.PRE2; a.w0 = d.P; a.ld0 = d.P;
         a.x1 = s + L.CTX; a.w1 = d.E; a.ld1 = d.E;

@@ -11,6 +11,7 @@
 #include "gvx_layout.cuh"
 #include "gvx_misc.cuh"
 #include "gvx_fused_fwd.cuh"
+#include "gvx_infer_prenet.cuh"
 #include "gvx_persist.cuh"
 
 namespace gvx {
@@ -738,7 +739,8 @@ int infer_bf16(const Dims &d, const gvx_weights *w, const float *packed, const f
 
     GVX_TRY(run_processed_memory(d, w, memory, B, N, s + L.PM, st));
     GVX_CUDA(cudaMemsetAsync(err, 0, 64 * sizeof(float), st));
-    GVX_CUDA(cudaMemsetAsync(flags, 0, 32 * sizeof(int), st));
+    GVX_CUDA(cudaMemsetAsync(flags, 0, 32 * sizeof(int), st));       // [0] rows still running; [32..33] hold the dropout seed (gvx_dec_infer)
+    GVX_CUDA(cudaMemsetAsync(flags + 40, 0, 2 * sizeof(int), st));   // [40] prenet grid barrier
     GVX_CUDA(cudaMemsetAsync(XAI, 0, 2 * L.xai_stride * sizeof(bf16), st));
     GVX_CUDA(cudaMemsetAsync(XDI, 0, 2 * L.xdi_stride * sizeof(bf16), st));
     GVX_CUDA(cudaMemsetAsync(XPI, 0, (size_t)g.Kpp * NPAD * sizeof(bf16), st));
@@ -762,7 +764,11 @@ int infer_bf16(const Dims &d, const gvx_weights *w, const float *packed, const f
             BfDsts bf;
             memset(&bf, 0, sizeof(bf));
             add_img(bf, xa, 0, NPAD);
-            GVX_TRY(run_prenet(d, w, prev, d.OL, B, B, seed, t, row_offset, s + L.PRE1, s + L.PRE2, st, &bf));
+            if (infer_prenet_fused_ok(d, B)) {
+                GVX_TRY(run_infer_prenet(d, w, prev, d.OL, B, seed, t, row_offset, s + L.PRE1, nullptr, &bf, (unsigned *)(flags + 40), err, st));
+            } else {
+                GVX_TRY(run_prenet(d, w, prev, d.OL, B, B, seed, t, row_offset, s + L.PRE1, s + L.PRE2, st, &bf));
+            }
         }
         {
             ProfScope ps(PS_ATT_LSTM, st);
