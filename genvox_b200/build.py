@@ -35,10 +35,13 @@ def sources():
 
 
 def _fingerprint():
+    """Hash of the sources and flags.  File NAMES only, not absolute paths: the repo is snapshotted to a different
+    directory on the GPU box, and a path-dependent stamp made every process there rebuild the library - under torchrun
+    several ranks at once, racing on the same .so (a rank then loaded a half-written file)."""
     h = hashlib.sha256()
     files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(INCLUDE, "genvox_b200.h")]
     for p in files:
-        h.update(p.encode())
+        h.update(os.path.basename(p).encode())
         with open(p, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -53,13 +56,26 @@ def is_fresh():
 
 
 def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ into one shared library.  Returns the library path."""
+    """Compile every .cu under csrc/ into one shared library.  Returns the library path.
+    Safe against concurrent callers (one process per GPU under torchrun): an exclusive file lock serialises builders, the
+    freshness check is repeated under the lock, objects and the library are written to process-private names and the
+    library is moved into place atomically."""
     if not force and is_fresh():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
+    import fcntl
+    with open(os.path.join(LIB_DIR, "build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and is_fresh():        # another process built it while this one waited
+            return LIB_PATH
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose):
+    tag = f".{os.getpid()}"
     objs = []
     for src in sources():
-        obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + tag + ".o")
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-c", src, "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)
@@ -69,12 +85,21 @@ def build(force=False, verbose=False):
         if verbose:
             print(r.stderr)
         objs.append(obj)
-    cmd = [_nvcc(), "-shared", "--cudart", "shared", "-o", LIB_PATH] + objs + ["-L/usr/local/cuda/lib64", "-lcublas"]
+    tmp_lib = LIB_PATH + tag
+    cmd = [_nvcc(), "-shared", "--cudart", "shared", "-o", tmp_lib] + objs + ["-L/usr/local/cuda/lib64", "-lcublas"]
     r = subprocess.run(cmd, capture_output=True, text=True)
+    for obj in objs:
+        try:
+            os.remove(obj)
+        except OSError:
+            pass
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    with open(STAMP, "w") as fh:
+    os.replace(tmp_lib, LIB_PATH)           # atomic: a concurrent loader sees the old or the new library, never a partial one
+    tmp_stamp = STAMP + tag
+    with open(tmp_stamp, "w") as fh:
         fh.write(_fingerprint())
+    os.replace(tmp_stamp, STAMP)
     return LIB_PATH
 
 
