@@ -85,3 +85,22 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_build_stamp_does_not_depend_on_the_checkout_path(tmp_path, monkeypatch):
+    """The repo is snapshotted to another directory on the GPU box: the prebuilt library must still count as fresh there
+    (a path-dependent stamp made every rank rebuild it concurrently under torchrun)."""
+    import shutil
+
+    from genvox_b200 import build
+    assert build.is_fresh()                                   # the in-tree library matches the sources it ships with
+    here = build._fingerprint()
+    moved = tmp_path / "elsewhere"
+    shutil.copytree(build.CSRC, moved / "csrc")
+    shutil.copytree(build.INCLUDE, moved / "include")
+    monkeypatch.setattr(build, "CSRC", str(moved / "csrc"))
+    monkeypatch.setattr(build, "INCLUDE", str(moved / "include"))
+    assert build._fingerprint() == here
+    with open(moved / "csrc" / "gvx_common.cuh", "a") as fh:  # ... and it does depend on the contents
+        fh.write("\n// touched\n")
+    assert build._fingerprint() != here
