@@ -5,7 +5,7 @@
 // (:98) and mel/gate projections (:361-362, inference) run on tcgen05 with bf16 operands and fp32
 // accumulation.  Everything pointwise stays fp32: the engine leaves split-K fp32 partials in L2 and the
 // kernels below add them (fixed order), apply the LSTM cell / its backward, and emit the next GEMM's
-// operand directly in the engine's shared-memory image ([K/8][NPAD][8] bf16, 16-byte vector stores)
+// operand directly in the engine's shared-memory image ([K/64][NPAD][64] bf16, SWIZZLE_128B, 16-byte vector stores)
 // and, for the time-batched weight-gradient GEMMs, as row-major bf16 rows.
 #pragma once
 #include <cuda_bf16.h>

@@ -96,10 +96,10 @@ struct PcOut {
 
 // ================================================================================================ forward
 struct PcFwdArgs {
-    const __nv_bfloat16 *Wimg;   // [H/8][H/8][32][8]   CTA, k-chunk, local gate row 4*lu+g, k in chunk  (W_hh)
+    const __nv_bfloat16 *Wimg;   // [H/8 CTAs][K/64 slabs][32 rows][64] SWIZZLE_128B; row = local gate row 4*lu+g  (W_hh, k_pc_pack_w mode 0)
     const float *pre;            // [T][B][4H]  unit-major columns 4u+g: input contribution (may alias gates_stash)
     const float *bias;           // [4H] unit-major b_ih + b_hh, or null
-    __nv_bfloat16 *himg;         // [2][H/8][64][8]  ping-pong operand image of h; half 0 = h_{-1} (zeros), pad rows zero
+    __nv_bfloat16 *himg;         // [2][K/64 slabs][64 rows][64] SWIZZLE_128B ping-pong operand image of h; half 0 = h_{-1} (zeros), pad rows zero
     float *c_stash;              // [T+1][B][H]  row 0 = c_{-1} (caller), row t+1 written at step t
     float *gates_stash;          // [T][B][4H] gate activations (i,f,g,o per unit) or null
     PcOut out[2];
@@ -290,8 +290,8 @@ __global__ void __launch_bounds__(PCF64_THREADS, 1) k_lstm_chain_fwd(const PcFwd
 
 // ================================================================================================ backward
 struct PcBwdArgs {
-    const __nv_bfloat16 *Wimg;   // [H/8][H/8][32][8]   CTA j = 4r+s: row n = output unit 32r+n, k = gate row s*H + kk (unit-major)
-    __nv_bfloat16 *gimg;         // [2][4H/8][64][8]  ping-pong d-gates image (k = 4u+g); half 0 zero at launch
+    const __nv_bfloat16 *Wimg;   // [H/8 CTAs][K/64 slabs][32 rows][64] SWIZZLE_128B; CTA j = 4r+s: row n = output unit 32r+n, k = gate row s*H + kk (unit-major)
+    __nv_bfloat16 *gimg;         // [2][4 K-quarters][H/64 slabs][64 rows][64] SWIZZLE_128B ping-pong d-gates image (k = 4u+g); half 0 zero at launch
     const float *dh_ext;         // d h (dropped) of frame t from everything but the recurrence: dh_ext[t*dh_tstride + b*dh_ld + u]
     int dh_ld;
     long long dh_tstride;

@@ -13,7 +13,8 @@
 //   W image  [Mtiles][Kpad/64][128 rows][64] bf16    (row tile, k-block, row in tile, swizzled k in block)
 //   X image  [Kpad/64][NPAD rows][64]        bf16    (k-block, batch row, swizzled k in block)
 // UMMA descriptors: SWIZZLE_128B, stride byte offset 1 KB; a K = 16 step inside the block advances the start address by
-// 32 B.  (The first version used the no-swizzle interleaved layout: ~180 cycles per 128 x 32 x 16 MMA, measured.)
+// 32 B.  (The first version used the no-swizzle interleaved layout; in the persistent chain kernels the MMA issuer then
+// advanced one 4-MMA slab every ~730 cycles against ~495 with SWIZZLE_128B in the same loop.)
 //
 // Mapping: the weights are the M side (UMMA_M = 128 rows per CTA, full TMEM lane use), the batch is
 // the N side (UMMA_N = NPAD <= 256); grid = (Mtiles, KS): the K range is split over KS CTAs so that
@@ -96,7 +97,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 // K-major SWIZZLE_128B descriptor: rows of 128 B (64 bf16 along K), 8-row groups of 1 KB (stride byte offset), the
 // 16-byte chunk c of row r stored at chunk position c ^ (r & 7); the tile base is 1 KB aligned and a K = 16 step
 // inside the 64-element slab advances the start address by 32 B.  The tensor core reads this layout at full
-// shared-memory bandwidth; the no-swizzle layout above costs ~180 cycles per 128 x 32 x 16 MMA (measured).
+// shared-memory bandwidth (measured in the persistent chain kernels: one 4-MMA slab per ~495 cycles against ~730 with
+// the no-swizzle layout above, same issue loop).
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
@@ -135,8 +137,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
 }
 
 struct TcGemmArgs {
-    const __nv_bfloat16 *Wimg;   // [Mtiles][Kpad/8][128][8]
-    const __nv_bfloat16 *Ximg;   // [Kpad/8][NPAD][8]
+    const __nv_bfloat16 *Wimg;   // [Mtiles][Kpad/64][128][64]  SWIZZLE_128B
+    const __nv_bfloat16 *Ximg;   // [Kpad/64][NPAD][64]         SWIZZLE_128B
     float *P;                    // [KS][B][ldp]   partial sums, m = tile*128 + row
     int Kpad;                    // multiple of 64
     int B;                       // valid batch rows (<= NPAD)
