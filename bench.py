@@ -146,8 +146,58 @@ def cpu_train_leg(steps, warmup, sample_T=CPU_SAMPLE_T):
                 ms_per_step=dt * 1e3)
 
 
+def torch_gpu_train_leg(steps, warmup, sample_T=100):
+    """Optional (--impl reference --reference-device cuda; never part of the default run): the oracle port's torch ops
+    executed on the GPU - the stock PyTorch eager path the reference itself takes on a CUDA device (nn.LSTMCell math,
+    conv1d, bmm, autograd BPTT), with torch's own dropout instead of the Philox stream (mask values do not matter for
+    timing) - on a bounded sample of the workload: the full batch, `sample_T` teacher-forced frames per step."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import decoder_oracle as O
+    import genvox_b200
+    from genvox_b200.training import decoder_loss
+    dev = torch.device("cuda:0")
+    B, N = TRAIN["B"], TRAIN["N"]
+    torch.manual_seed(0)
+    dec = genvox_b200.Decoder(**decoder_dims())          # parameter container only: same init as the other arms
+    P = {k: v.detach().clone().to(dev).requires_grad_(True) for k, v in dec.named_parameters()}
+    opt = torch.optim.Adam(list(P.values()), lr=1e-3, weight_decay=1e-6)
+    memory, mel, gate, lengths = synthetic_batch(torch, B, N, sample_T)
+    memory, mel, gate = memory.to(dev), mel.to(dev), gate.to(dev)
+    O.philox_dropout = lambda x, p, on, *a, **k: F.dropout(x, p, on)          # tacotron2.py:143,:341,:358
+    O.get_mask_from_lengths = lambda lengths, max_len=None: (
+        torch.arange(max_len if max_len is not None else int(lengths.max()), device=dev)[None, :] >= lengths.to(dev)[:, None])
+
+    def step(i):
+        opt.zero_grad(set_to_none=True)
+        m, g, _ = O.forward_teacher(P, memory, mel, lengths, seed=123 + i, training=True)
+        loss, _, _ = decoder_loss(m, g, mel, gate)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(P.values()), 1.0)
+        opt.step()
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(warmup + i)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return dict(value=B * sample_T / dt, unit=UNIT, cores=os.cpu_count() or 1, kind="port",
+                sample=f"oracle/decoder_oracle.py train step on cuda:0 (stock PyTorch eager ops, fp32), B={B}, N={N}, {sample_T} of "
+                       f"{TRAIN['T']} frames per step, {steps} timed steps after {warmup} warm-up",
+                ms_per_step=dt * 1e3)
+
+
 def run_reference(args, rank):
     if rank != 0:
+        return
+    if args.reference_device == "cuda":
+        leg = torch_gpu_train_leg(args.steps, args.warmup)
+        print(json.dumps({"impl": "reference", "device": "cuda", "metric": METRIC, "value": leg["value"], "unit": UNIT, "n_gpus": 1,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["ms_per_step"], "higher_is_better": True,
+                          "dtype": "f32", "data": "synthetic", "config": {"workload": leg["sample"]}}), flush=True)
         return
     leg = cpu_train_leg(args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": leg["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -371,6 +421,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--reference-device", choices=["cpu", "cuda"], default="cpu",
+                    help="--impl reference only: 'cuda' times the same torch ops on the GPU (stock PyTorch eager path); "
+                         "the contract's reference arm is the CPU one")
     ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16",
                     help="arithmetic of the recurrent GEMMs (BASELINE configs[2] is bf16; fp32 = parity mode)")
     args = ap.parse_args()
