@@ -48,11 +48,22 @@ def _fingerprint():
     return h.hexdigest()
 
 
+def _marker(fingerprint):
+    return ("GVXFP:" + fingerprint).encode()
+
+
 def is_fresh():
+    """True when the in-tree library was compiled from exactly the sources in the tree: the source fingerprint is
+    compiled INTO the library (-DGVX_BUILD_FINGERPRINT, gvx_api.cu) and looked up in the file, so a library left over
+    from other sources (e.g. after `git checkout` of the sources and of build.stamp) is never mistaken for a fresh one."""
     if not (os.path.isfile(LIB_PATH) and os.path.isfile(STAMP)):
         return False
+    fp = _fingerprint()
     with open(STAMP) as fh:
-        return fh.read().strip() == _fingerprint()
+        if fh.read().strip() != fp:
+            return False
+    with open(LIB_PATH, "rb") as fh:
+        return _marker(fp) in fh.read()
 
 
 def build(force=False, verbose=False):
@@ -74,9 +85,10 @@ def build(force=False, verbose=False):
 def _build_locked(verbose):
     tag = f".{os.getpid()}"
     objs = []
+    fp_define = f'-DGVX_BUILD_FINGERPRINT="{_fingerprint()}"'
     for src in sources():
         obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + tag + ".o")
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-c", src, "-o", obj]
+        cmd = [_nvcc()] + NVCC_FLAGS + [fp_define] + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-c", src, "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)

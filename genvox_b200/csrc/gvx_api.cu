@@ -167,6 +167,12 @@ using namespace gvx;
 
 extern "C" {
 
+// fingerprint of the sources this library was compiled from (genvox_b200/build.py looks the marker up in the file)
+#ifndef GVX_BUILD_FINGERPRINT
+#define GVX_BUILD_FINGERPRINT "unknown"
+#endif
+extern "C" __attribute__((used, visibility("default"))) const char gvx_build_marker[] = "GVXFP:" GVX_BUILD_FINGERPRINT;
+
 int gvx_abi_version(void) { return GVX_ABI_VERSION; }
 const char *gvx_last_error(void) { return g_err; }
 
