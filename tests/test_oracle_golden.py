@@ -115,3 +115,26 @@ def test_fp32_reference_noise_floor_is_far_below_parity_tolerance():
     meta, z = load_golden("fwd_default_train")
     assert rel_err(z["mel_f32"], z["mel_f64"]) < 1e-5
     assert rel_err(z["align_f32"], z["align_f64"]) < 1e-5
+
+
+def test_bf16_semantics_memory_rounding_is_opt_in_and_small():
+    """bf16_semantics(round_memory=True) mirrors the fused attention chain's extra rounding point (bf16 memory operand of
+    the context, tacotron2.py:127); the default bf16 semantics and the fp32 oracle are untouched by it."""
+    import torch
+
+    from oracle import decoder_oracle as O
+    from oracle import synth
+    dims = synth.SMALL_DIMS
+    W = O.as_params(synth.make_decoder_weights(5, dims))
+    mem, mel, lens = synth.make_inputs(9, 3, 11, 4, dims)
+    args = (W, torch.from_numpy(mem), torch.from_numpy(mel), lens)
+    plain = O.forward_teacher(*args, seed=3, training=True)
+    with O.bf16_semantics():
+        b0 = O.forward_teacher(*args, seed=3, training=True)
+    with O.bf16_semantics(round_memory=True):
+        b1 = O.forward_teacher(*args, seed=3, training=True)
+    again = O.forward_teacher(*args, seed=3, training=True)
+    assert all(torch.equal(x, y) for x, y in zip(plain, again))               # the context managers restore the fp32 oracle
+    d01 = float((b0[0] - b1[0]).abs().max() / b0[0].abs().max())
+    assert 0.0 < d01 < 5e-3                                                    # one more bf16 rounding: visible but small
+    assert float((b0[0] - plain[0]).abs().max() / plain[0].abs().max()) < 3e-2
