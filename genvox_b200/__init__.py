@@ -9,5 +9,6 @@ Only what the hot path needs:
 """
 from .decoder import Decoder, install, decoder_kwargs_from  # noqa: F401
 from . import _native  # noqa: F401
+from ._native import check_device_errors  # noqa: F401
 
-__all__ = ["Decoder", "install", "decoder_kwargs_from"]
+__all__ = ["Decoder", "install", "decoder_kwargs_from", "check_device_errors"]

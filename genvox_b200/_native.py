@@ -50,6 +50,7 @@ class GvxGrads(C.Structure):
 _SIGNATURES = {
     "gvx_abi_version": (C.c_int, []),
     "gvx_last_error": (C.c_char_p, []),
+    "gvx_device_error": (C.c_int, [C.c_int]),
     "gvx_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "gvx_launch_count": (C.c_ulonglong, []),
     "gvx_profile_enable": (C.c_int, [C.c_int]),
@@ -109,6 +110,15 @@ def load():
         raise RuntimeError("genvox_b200: ABI version mismatch")
     _lib = lib
     return lib
+
+
+def check_device_errors(clear=True):
+    """Raise if a kernel of an earlier (asynchronous) call aborted on the device.  Meaningful after the stream has been
+    synchronised (e.g. where the loss is read); training entry points also refuse to run once the latch is set."""
+    code = load().gvx_device_error(1 if clear else 0)
+    if code:
+        raise RuntimeError(f"genvox_b200: a device kernel aborted (entry {code // 1000}, wait code {code % 1000}); "
+                           "the outputs of that call are invalid")
 
 
 def check(status, what):

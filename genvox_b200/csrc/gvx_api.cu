@@ -424,6 +424,7 @@ int gvx_dec_train_fwd(const gvx_dims *dd, const gvx_weights *w, const void *pack
     GVX_TRY(check_dims(dd));
     GVX_CHECK(w && packed_ && memory && mel_in && mel_out && gate_out && align_out && stash_, "null argument");
     GVX_CHECK(B > 0 && N > 0 && T > 0, "B, N, T must be positive");
+    GVX_TRY(latch_check());
     cudaStream_t user = (cudaStream_t)stream;
     uint32_t *slot = seed_slot_train(dd, stash_, B, N, T);
     GVX_TRY(put_seed(slot, seed, user));
@@ -447,6 +448,7 @@ int gvx_dec_infer(const gvx_dims *dd, const gvx_weights *w, const void *packed_,
     GVX_CHECK(w && packed_ && memory && mel_out && gate_out && align_out && n_frames && steps_run && workspace,
               "null argument");
     GVX_CHECK(B > 0 && N > 0 && max_steps > 0, "B, N, max_steps must be positive");
+    GVX_TRY(latch_check());
     cudaStream_t user = (cudaStream_t)stream;
     const Dims d(*dd);
     const bool bf = dd->precision == GVX_BF16;
@@ -473,7 +475,16 @@ int gvx_dec_infer(const gvx_dims *dd, const gvx_weights *w, const void *packed_,
     if (rc == 0 && bf)
         rc = check_tc_err_public(reinterpret_cast<int *>((float *)workspace + infer_err_off_bf16(d, B, N, max_steps)), user,
                                  "gvx_dec_infer");
+    if (rc == 0 && !bf)      // error word of the fused inference prenet's grid barrier (gvx_infer_prenet.cuh)
+        rc = check_tc_err_public(reinterpret_cast<int *>((float *)workspace + flags_off) + 41, user, "gvx_dec_infer (prenet barrier)");
     return rc;
+}
+
+int gvx_device_error(int clear) {
+    if (latch_ready()) return -1;
+    const int e = *reinterpret_cast<volatile int *>(err_latch_host());
+    if (clear) *reinterpret_cast<volatile int *>(err_latch_host()) = 0;
+    return e;
 }
 
 int gvx_graph_stats(unsigned long long *out4) {

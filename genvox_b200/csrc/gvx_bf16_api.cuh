@@ -11,6 +11,7 @@
 #include "gvx_layout.cuh"
 #include "gvx_misc.cuh"
 #include "gvx_fused_fwd.cuh"
+#include "gvx_fused_bwd.cuh"
 #include "gvx_infer_prenet.cuh"
 #include "gvx_persist.cuh"
 
@@ -48,7 +49,7 @@ inline int tc_pick_ks(int mtiles, int nkb) {
 
 // ---- bf16 part of the packed weights, appended after the fp32 PackedL block (offsets in floats) ----
 struct PackedBfL {
-    size_t WaI, WdI, WaTI, WdTI, WqI, WqTI, WpgI, WpgRM, WdRM, WdhhI, WdhhTI, WaRecI, WaPRM, WqB, total;
+    size_t WaI, WdI, WaTI, WdTI, WqI, WqTI, WpgI, WpgRM, WdRM, WdhhI, WdhhTI, WaRecI, WaPRM, WqB, WaRecTI, total;
     PackedBfL(const Dims &d, size_t base) {
         const BfGeom g(d);
         Carver c;
@@ -69,6 +70,8 @@ struct PackedBfL {
         WaRecI = c.take(fa_wimg_elems() / 2);
         WaPRM = c.take(((size_t)4 * d.A * d.P + 1) / 2);
         WqB = c.take(((size_t)d.D * d.A + 1) / 2);
+        // persistent BPTT of the attention chain (gvx_fused_bwd.cuh): resident [ctx | h_att] columns of W_att^T
+        WaRecTI = c.take(fb_wimg_elems() / 2);
         total = c.o;
     }
 };
@@ -107,7 +110,8 @@ int pack_weights_bf16(const Dims &d, const gvx_weights *w, float *packed, cudaSt
     if (d.A == FA_A && d.E == FA_E) {
         k_fa_pack_w<<<grid_for(fa_wimg_elems()), 256, 0, st>>>(packed + PL.Wa, d.Ka, d.P, (bf16 *)(packed + BL.WaRecI));
         k_to_bf16<<<grid_for((size_t)4 * d.A * d.P), 256, 0, st>>>(packed + PL.Wa, d.Ka, (size_t)4 * d.A, d.P, (bf16 *)(packed + BL.WaPRM), d.P);
-        GVX_LAUNCHED(2);
+        k_fb_pack_w<<<grid_for(fb_wimg_elems()), 256, 0, st>>>(packed + PL.Wa, d.Ka, d.P, (bf16 *)(packed + BL.WaRecTI));
+        GVX_LAUNCHED(3);
     }
     GVX_CUDA(cudaGetLastError());
     return 0;
@@ -116,7 +120,7 @@ int pack_weights_bf16(const Dims &d, const gvx_weights *w, float *packed, cudaSt
 // ---- bf16 training stash -----------------------------------------------------------------------------
 struct StashBfL {
     size_t FR, PRE1, PRE2, PM, CA, GA, CD, GD, ALIGN, CUMS, TH, CONVS, OUT, WPREV, CUM, XAI, XDI, XARM, XDRM, HCRM, PA, PD, PQ, ERR,
-        SEED, HIMG, BAR, XIMG, MEMB, BAR2, QBUF, total;
+        SEED, HIMG, BAR, XIMG, MEMB, BAR2, QBUF, CTX32, total;
     size_t xai_stride, xdi_stride;     // bf16 elements per frame image
     int NPAD, KSa, KSd, KSq;
     StashBfL(const Dims &d, int B, int N, int T) {
@@ -146,13 +150,14 @@ struct StashBfL {
         MEMB = c.take(((size_t)B * N * d.E + 1) / 2);     // bf16 copy of the encoder memory (context operand)
         BAR2 = c.take(32 * 18);                    // 2 grid barriers + 16 row-group counters, one 128-byte line each
         QBUF = c.take((size_t)2 * 2 * 64 * d.D);   // 64-bit (value, tag) words
+        CTX32 = c.take(TB * d.E);                  // fp32 attention context per frame (softmax backward of the persistent BPTT)
         total = c.o;
     }
 };
 
 struct BwdBfL {
     size_t DOUT, DOUTB, DHC, GDI, GAI, DQI, DGDRM, DGARM, DQRM, PDXD, PDXA, PS4, DCD, DCA, DCTX, DE, DCONV, DZ2, DZ1, DPM, DW, DCUM,
-        DWA, DWD, DBIAS, PART1, PART2, ONES, TMP, COLP, ERR, GIMG, DXDALL, BAR, total;
+        DWA, DWD, DBIAS, PART1, PART2, ONES, TMP, COLP, ERR, GIMG, DXDALL, BAR, GIMGA, DCTXX, DQX, BARA, total;
     size_t pdxd_stride, pdxa_stride;   // floats per ping-pong half
     int NPAD, KSdT, KSaT, KSs4, post_blocks, colchunks;
     BwdBfL(const Dims &d, int B, int N, int T) {
@@ -187,6 +192,10 @@ struct BwdBfL {
         GIMG = c.take(pc_gimg_elems(d.H) / 2);     // [2][4][H/64][64][64] bf16 ping-pong d-gates image of the persistent BPTT chain
         DXDALL = c.take(TB * (d.A + d.E));   // [T][B][A+E] d [h_att | ctx] from the decoder-LSTM input, all frames
         BAR = c.take(64);
+        GIMGA = c.take(fb_gimg_bytes() / 4);       // d-gates image of the persistent attention-chain BPTT
+        DCTXX = c.take(2 * fb_dctxx_words());      // 64-bit (value, tag) words
+        DQX = c.take(2 * fb_dqx_words());
+        BARA = c.take(32 * 4);
         total = c.o;
     }
 };
@@ -317,6 +326,11 @@ __global__ void k_add_bias_rows(float *x, size_t rows, int cols, int ld, const f
     }
 }
 
+// the fused persistent attention chains (forward + BPTT) go together: they share the bf16 / swizzled tanh stash
+inline bool fused_chains_ok(const Dims &d, int B, int N) {
+    return pc_enabled() && pc_supported(d.H, B) && fa_enabled() && fa_supported(d, B, N) && fb_supported(d, B, N);
+}
+
 // ======================================================================================= forward (training)
 int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, const float *memory, const float *mel_in,
                           const int64_t *mem_lengths, int B, int N, int T, uint64_t seed, int training, int row_offset,
@@ -336,7 +350,7 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     // attention chain runs first for all frames and the decoder-LSTM recurrence follows in ONE launch (gvx_persist.cuh)
     const bool pc = pc_enabled() && pc_supported(d.H, B);
     // fused attention chain: attention LSTM + query + attention of all frames in ONE persistent launch (gvx_fused_fwd.cuh)
-    const bool fa = pc && fa_enabled() && fa_supported(d, B, N);
+    const bool fa = fused_chains_ok(d, B, N);
 
     ProfScope *ps_setup = new ProfScope(PS_SETUP, st);
     GVX_CUDA(cudaMemsetAsync(err, 0, 64 * sizeof(float), st));
@@ -385,7 +399,7 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
         f.Wq = (const bf16 *)(packed + BL.WqB);
         f.pm = s + S.PM; f.memb = (const bf16 *)(s + S.MEMB);
         f.wlc = w->loc_conv_w; f.wldT = packed + PL.wldT; f.v = w->v_w; f.lengths = mem_lengths;
-        f.align_out = s + S.ALIGN; f.cum_stash = s + S.CUMS; f.th_stash = s + S.TH; f.conv_stash = s + S.CONVS;
+        f.align_out = s + S.ALIGN; f.cum_stash = s + S.CUMS; f.th_stash = s + S.TH; f.th_bf16 = 1; f.conv_stash = s + S.CONVS; f.ctx32_stash = s + S.CTX32;
         f.bar = (unsigned *)(s + S.BAR2); f.qbuf = (unsigned long long *)(s + S.QBUF); f.err = err;
         f.drop = make_drop(seed, d.p_att, training);
         f.row_offset = row_offset; f.B = B; f.N = N; f.T = T;
@@ -467,6 +481,8 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     GVX_CUDA(cudaMemcpyAsync(align_out, s + S.ALIGN, (size_t)B * T * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    GVX_TRY(latch_record(err, 1, 1, st));
+    GVX_LAUNCHED(1);
     return 0;
 }
 
@@ -592,9 +608,30 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     static const bool dhq_env = !(getenv("GVX_DHQ_FOLDED") && getenv("GVX_DHQ_FOLDED")[0] == '0');
     const bool dhq_folded = dhq_env && !s4_fused && d.A % 16 == 0 && d.A <= 1024 && attention_bwd_uses_c2(AttnShape{B, N, d.D, d.E, d.F, d.KS});
     // the fused forward chain left a bf16 copy of the encoder memory in the stash: operand of d w in the attention backward
-    const bool have_memb = pc && fa_enabled() && fa_supported(d, B, N);
+    const bool fb = fused_chains_ok(d, B, N);
+    const bool have_memb = fb;
+    if (fb) {   // BPTT of the attention chain for all frames in one persistent launch (gvx_fused_bwd.cuh)
+        ProfScope ps(PS_BWD_ATTENTION, st);
+        FbArgs f;
+        memset(&f, 0, sizeof(f));
+        f.Wimg = (const bf16 *)(packed + BL.WaRecTI);
+        f.gimg = (uint8_t *)(x + W.GIMGA);
+        f.WqB = (const bf16 *)(packed + BL.WqB);
+        f.gates_stash = s + S.GA; f.c_stash = s + S.CA;
+        f.dxdall = x + W.DXDALL; f.dhc = x + W.DHC; f.Kp = d.Kp; f.H = d.H;
+        f.d_align = d_align; f.align = s + S.ALIGN; f.ctx32 = s + S.CTX32;
+        f.th = (const bf16 *)(s + S.TH); f.memb = (const bf16 *)(s + S.MEMB);
+        f.wlc = w->loc_conv_w; f.wldT = packed + PL.wldT; f.v = w->v_w; f.lengths = mem_lengths;
+        f.dg_rm = DGARM; f.dq_rm = DQRM;
+        f.de_out = x + W.DE; f.dconv_out = x + W.DCONV; f.dctx_out = x + W.DCTX;
+        f.dctxx = (unsigned long long *)(x + W.DCTXX); f.dqx = (unsigned long long *)(x + W.DQX);
+        f.bar = (unsigned *)(x + W.BARA); f.err = err;
+        f.drop = make_drop(seed, d.p_att, training);
+        f.row_offset = row_offset; f.B = B; f.N = N; f.T = T; f.RS = fb_row_split(B, N);
+        GVX_TRY(launch_att_chain_bwd(f, st));
+    }
     pdl_barrier_next();
-    for (int t = T - 1; t >= 0; --t) {
+    for (int t = T - 1; t >= 0 && !fb; --t) {
         const bool last = t == T - 1;
         float *pdxd = x + W.PDXD + (size_t)(t & 1) * W.pdxd_stride, *pdxd_n = x + W.PDXD + (size_t)((t + 1) & 1) * W.pdxd_stride;
         float *pdxa = x + W.PDXA + (size_t)(t & 1) * W.pdxa_stride, *pdxa_n = x + W.PDXA + (size_t)((t + 1) & 1) * W.pdxa_stride;
@@ -667,7 +704,12 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
         }
     }
     ProfScope ps_batched(PS_BWD_BATCHED, st);
-    {   // prenet gradient of frame 0 from the last d x_att partials (ping-pong half 0)
+    if (fb) {   // prenet columns of d x_att for all frames: d gates_att . W_ih[:, prenet], then the relu / dropout mask (:143)
+        GVX_TRY(gemm_nn_bf16(st, TB, d.P, 4 * d.A, DGARM, 4 * d.A, (const bf16 *)(packed + BL.WaPRM), d.P, x + W.DZ1, d.P));
+        k_prenet_bwd_mask<<<grid_for((size_t)TB * d.P), 256, 0, st>>>(x + W.DZ1, d.P, s + S.PRE2, TB, d.P, x + W.DZ2);
+        GVX_LAUNCHED(1);
+        GVX_CUDA(cudaGetLastError());
+    } else {   // prenet gradient of frame 0 from the last d x_att partials (ping-pong half 0)
         const int total = B * d.P;
         BfLstmBwd a;
         memset(&a, 0, sizeof(a));
@@ -718,7 +760,11 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     pa.DPM = x + W.DPM; pa.PART1 = x + W.PART1; pa.PART2 = x + W.PART2; pa.DZ2 = x + W.DZ2; pa.DZ1 = x + W.DZ1;
     pa.post_blocks = W.post_blocks;
     pa.bf16_mode = 1;
-    return bwd_post_common(d, w, memory, B, N, T, pa, g, d_memory, st);
+    pa.th_bf16 = fb ? 1 : 0;
+    GVX_TRY(bwd_post_common(d, w, memory, B, N, T, pa, g, d_memory, st));
+    GVX_TRY(latch_record(err, 1, 2, st));
+    GVX_LAUNCHED(1);
+    return 0;
 }
 
 // ======================================================================================= inference

@@ -162,6 +162,7 @@ __device__ __forceinline__ uint32_t pdm_pack(float lo, float hi) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const uint32_t *>(&v);
 }
+template <bool THBF>     // THBF: the tanh stash is bf16 with 16-byte chunks swizzled by (token & 7) (written by k_att_chain_fwd)
 __global__ void __launch_bounds__(128, 5) k_attn_post_dense_mma(const float *__restrict__ TH, const float *__restrict__ DE,
                                                                 const float *__restrict__ CONVS, const float *__restrict__ v, int T,
                                                                 int B, int N, float *__restrict__ DPM,
@@ -183,15 +184,18 @@ __global__ void __launch_bounds__(128, 5) k_attn_post_dense_mma(const float *__r
     // conv staging: thread -> (frame pair p, filter pair q): conv[2p..2p+1][2q..2q+1]
     const int cp_ = d >> 4, cq = d & 15;
     int buf = 0;
+    const unsigned short *THB = reinterpret_cast<const unsigned short *>(TH);
     for (int tok = blockIdx.x; tok < B * N; tok += gridDim.x) {
         float pacc = 0.f;
+        const int dsw = ((((d >> 3) ^ ((tok % N) & 7)) << 3) | (d & 7));
         for (int t0 = 0; t0 < T; t0 += PDM_TC) {
             float th[PDM_TC], de[PDM_TC];
 #pragma unroll
             for (int i = 0; i < PDM_TC; ++i) {
                 const bool in = t0 + i < T;
                 const size_t row = (size_t)(in ? t0 + i : 0) * tok_stride + tok;
-                th[i] = in ? __ldcs(TH + row * D + d) : 0.f;
+                if (THBF) th[i] = in ? __uint_as_float((unsigned)__ldcs(THB + row * D + dsw) << 16) : 0.f;
+                else th[i] = in ? __ldcs(TH + row * D + d) : 0.f;
                 de[i] = in ? __ldg(DE + row) : 0.f;
             }
             float2 c0 = make_float2(0.f, 0.f), c1 = make_float2(0.f, 0.f);
@@ -335,6 +339,7 @@ struct BwdPostArgs {
     float *DPM, *PART1, *PART2, *DZ2, *DZ1;
     int post_blocks;
     int bf16_mode;            // 1: bf16-operand tensor-core post-pass for d location_dense (gvx_bf16_api.cuh), 0: exact fp32
+    int th_bf16 = 0;          // the tanh stash is bf16 / chunk-swizzled (fused persistent chains)
 };
 inline int bwd_post_common(const Dims &d, const gvx_weights *w, const float *memory, int B, int N, int T, const BwdPostArgs &p,
                            const gvx_grads *g, float *d_memory, cudaStream_t st) {
@@ -344,7 +349,8 @@ inline int bwd_post_common(const Dims &d, const gvx_weights *w, const float *mem
         const int threads = (d.D + 31) & ~31;
         GVX_CHECK(threads <= 512, "att_dim too large");
         if (p.bf16_mode && d.D == 128 && d.F == 32) {
-            k_attn_post_dense_mma<<<nblk, 128, 0, st>>>(p.TH, p.DE, p.CONVS, w->v_w, T, B, N, p.DPM, p.PART1);
+            if (p.th_bf16) k_attn_post_dense_mma<true><<<nblk, 128, 0, st>>>(p.TH, p.DE, p.CONVS, w->v_w, T, B, N, p.DPM, p.PART1);
+            else k_attn_post_dense_mma<false><<<nblk, 128, 0, st>>>(p.TH, p.DE, p.CONVS, w->v_w, T, B, N, p.DPM, p.PART1);
         } else if (d.F <= 32) {
             k_attn_post_dense<32><<<nblk, threads, 0, st>>>(p.TH, p.DE, p.CONVS, w->v_w, T, B, N, d.D, d.F, p.DPM, p.PART1);
         } else {
@@ -572,6 +578,7 @@ extern "C" int gvx_dec_train_bwd(const gvx_dims *dd, const gvx_weights *w, const
     GVX_TRY(check_dims(dd));
     GVX_CHECK(w && packed_ && memory && d_mel && d_gate && stash_ && workspace && g && d_memory, "null argument");
     GVX_CHECK(B > 0 && N > 0 && T > 0, "B, N, T must be positive");
+    GVX_TRY(latch_check());
     cudaStream_t user = (cudaStream_t)stream;
     const Dims d(*dd);
     const size_t off = dd->precision == GVX_BF16 ? stash_seed_off_bf16(d, B, N, T) : StashL(d, B, N, T).SEED;

@@ -42,6 +42,46 @@ inline int fail(const char *msg) {
         if (r__) return r__;                                                                   \
     } while (0)
 
+// ---------------------------------------------------------------- device-side abort latch
+// The persistent / tcgen05 kernels never hang: a wait that times out writes a code into the call's device error word and
+// the grid drains.  Training calls are fully asynchronous (no host sync), so that word is latched - by a one-thread kernel
+// at the end of every call - into a sticky word in mapped pinned host memory; the NEXT entry point (or an explicit
+// gvx_device_error()) sees it without synchronising and fails loudly.  where: 1 train_fwd, 2 train_bwd, 3 infer.
+inline int *&err_latch_host() { static int *p = nullptr; return p; }
+inline int *&err_latch_dev() { static int *p = nullptr; return p; }
+__global__ void k_latch_err(const int *__restrict__ err, int nwords, int *host_latch, int where) {
+    for (int i = 0; i < nwords; ++i) {
+        const int e = err[i];
+        if (e != 0 && *reinterpret_cast<volatile int *>(host_latch) == 0) *reinterpret_cast<volatile int *>(host_latch) = where * 1000 + e;
+    }
+}
+inline int latch_ready() {
+    if (err_latch_host()) return 0;
+    int *h = nullptr, *dv = nullptr;
+    if (cudaHostAlloc(&h, 64, cudaHostAllocMapped) != cudaSuccess || cudaHostGetDevicePointer(&dv, h, 0) != cudaSuccess)
+        return fail("could not allocate the pinned error latch");
+    *h = 0;
+    err_latch_host() = h;
+    err_latch_dev() = dv;
+    return 0;
+}
+// refuse to enqueue more work once a previous call of this process aborted on the device
+inline int latch_check() {
+    if (latch_ready()) return 1;
+    const int e = *reinterpret_cast<volatile int *>(err_latch_host());
+    if (e != 0) {
+        snprintf(g_err, sizeof(g_err), "a previous launch aborted on the device (entry %d, wait code %d: a persistent chain lost its "
+                 "co-resident CTAs or a pipeline stalled); its outputs are invalid", e / 1000, e % 1000);
+        return 1;
+    }
+    return 0;
+}
+inline int latch_record(const int *err_dev, int nwords, int where, cudaStream_t st) {
+    if (latch_ready()) return 1;
+    k_latch_err<<<1, 1, 0, st>>>(err_dev, nwords, err_latch_dev(), where);
+    return cudaGetLastError() == cudaSuccess ? 0 : fail("latch kernel launch failed");
+}
+
 // ---------------------------------------------------------------- launch accounting / phase profiler
 // g_launches counts every kernel this library launches (bench.py's `gpu_launches`).  The profiler,
 // when enabled, brackets each phase launch with CUDA events on the launching stream so bench.py can

@@ -106,7 +106,11 @@ struct FaArgs {
     const int64_t *lengths;
     float *align_out;            // [B][T][N]
     float *cum_stash;            // [B][T][N]
-    float *th_stash;             // [T][B][N][D]
+    float *th_stash;             // [T][B][N][D] fp32, or (th_bf16) bf16 rows of 256 B whose 16-byte chunks are swizzled by
+                                 // (token & 7): the layout the persistent BPTT kernel (gvx_fused_bwd.cuh) reads conflict-free
+    int th_bf16;
+    float *ctx32_stash;          // [T][B][E] fp32 attention context (before the bf16 rounding of the operand images) or null:
+                                 // the persistent BPTT kernel gets <w, d w> of the softmax backward from <ctx, d ctx>
     float *conv_stash;           // [T][B][N][F]
     unsigned *bar;               // counters 128 B apart, zero at launch: [0] h_att complete, [1] ctx complete, [2 + g] query
                                  // slices of row group g delivered
@@ -157,7 +161,9 @@ __device__ __forceinline__ bool fa_spin(F ready, volatile int *dead, int *err, i
     for (unsigned it = 1;; ++it) {
         if (ready()) return true;
         if (*dead) return false;
-        if ((it & 63u) == 0u) {
+        // the global error word and the clock are looked at rarely: hundreds of threads spin here, and a volatile load of ONE
+        // address from every one of them, every few iterations, keeps a single L2 slice busy for the whole grid
+        if ((it & 2047u) == 0u) {
             if (*reinterpret_cast<volatile int *>(err) != 0) { *dead = 1; return false; }
             if (clock64() - t0 > FA_WAIT_CYCLES) {
                 *dead = 1;
@@ -548,8 +554,17 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                             th.y = tanh_fast(q4.y + l4.y);
                             th.z = tanh_fast(q4.z + l4.z);
                             th.w = tanh_fast(q4.w + l4.w);
-                            if (rvalid && a.th_stash)
-                                __stcs(reinterpret_cast<float4 *>(a.th_stash + (((size_t)t * B + row) * N + n_lo + n0 + jj) * AF_D + lane * 4), th);
+                            if (rvalid && a.th_stash) {
+                                const size_t trow = ((size_t)t * B + row) * N + n_lo + n0 + jj;
+                                if (a.th_bf16) {
+                                    const int nn = n_lo + n0 + jj;
+                                    __stcs(reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(a.th_stash) + trow * (AF_D * 2) +
+                                                                     (((lane >> 1) ^ (nn & 7)) << 4) + (lane & 1) * 8),
+                                           make_uint2(pack_bf2(th.x, th.y), pack_bf2(th.z, th.w)));
+                                } else {
+                                    __stcs(reinterpret_cast<float4 *>(a.th_stash + trow * AF_D + lane * 4), th);
+                                }
+                            }
                             pe[jj] = fmaf(v4.x, th.x, fmaf(v4.y, th.y, fmaf(v4.z, th.z, v4.w * th.w)));
                         }
                     }
@@ -659,6 +674,7 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
 #pragma unroll
                     for (int k = 0; k < 8; ++k) oth[k] = ld_cluster_f32(peer_ctxp + 4 * (e0 + k));
                     uint32_t pk[4];
+                    float cxs[8];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         float cx[2];
@@ -666,6 +682,7 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                         for (int q2 = 0; q2 < 2; ++q2) {
                             const float mine = ctxp[e0 + 2 * k + q2] * a_s, other = oth[2 * k + q2] * a_p;
                             cx[q2] = (half == 0 ? mine + other : other + mine) / S;
+                            cxs[2 * k + q2] = cx[q2];
                         }
                         pk[k] = pack_bf2(cx[0], cx[1]);
                     }
@@ -678,6 +695,11 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                         *reinterpret_cast<uint4 *>(a.xdrm + ((size_t)t * B + row) * a.Kd + FA_A + e0) = v;
                         *reinterpret_cast<uint4 *>(a.hcrm + ((size_t)t * B + row) * a.Kp + a.H + e0) = v;
                         if (t + 1 < T) *reinterpret_cast<uint4 *>(a.xarm + ((size_t)(t + 1) * B + row) * a.Ka + a.P + e0) = v;
+                        if (a.ctx32_stash) {
+                            float4 *cd = reinterpret_cast<float4 *>(a.ctx32_stash + ((size_t)t * B + row) * FA_E + e0);
+                            cd[0] = make_float4(cxs[0], cxs[1], cxs[2], cxs[3]);
+                            cd[1] = make_float4(cxs[4], cxs[5], cxs[6], cxs[7]);
+                        }
                     }
                 }
             }

@@ -89,6 +89,14 @@ typedef struct gvx_grads {
 int gvx_abi_version(void);
 const char *gvx_last_error(void);
 
+/* Device-side abort latch.  gvx_dec_train_fwd / gvx_dec_train_bwd never synchronise with the host, so a persistent or
+ * tcgen05 kernel that aborted (a bounded wait timed out: the chain lost its co-resident CTAs, a pipeline stalled) cannot
+ * fail the call that launched it.  Its error word is latched into pinned host memory by the last kernel of the call;
+ * every later entry point returns non-zero once the latch is set, and this function returns the latched code
+ * (entry * 1000 + wait code; 0 = none) without synchronising.  Call it after a stream / device synchronisation to
+ * learn whether the outputs just produced are valid.  clear != 0 resets the latch.  (Python: genvox_b200.check_device_errors.) */
+int gvx_device_error(int clear);
+
 /* Number of SMs / device name the library sees on the current device (diagnostics). */
 int gvx_device_info(int *sm_count, int *cc_major, int *cc_minor);
 

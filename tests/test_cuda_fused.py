@@ -29,6 +29,8 @@ def _run(dec, mem, mel, lens, r_mel, r_gate, seed, dev, fused):
         m, g, a = dec(memory, torch.from_numpy(mel).to(dev), torch.from_numpy(lens).to(dev))
         ((m * r_mel.to(dev)).sum() + (g * r_gate.to(dev)).sum()).backward()
         torch.cuda.synchronize()
+        import genvox_b200
+        genvox_b200.check_device_errors()
         grads = {k: p.grad.detach().cpu().clone() for k, p in dec.named_parameters()}
         grads["memory"] = memory.grad.detach().cpu().clone()
         return m.detach().cpu(), g.detach().cpu(), a.detach().cpu(), grads
