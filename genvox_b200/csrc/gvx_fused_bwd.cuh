@@ -61,27 +61,30 @@ struct FbGeom {
 };
 
 struct FbShared {
-    uint64_t full[FB_RING], empty[FB_RING], tmem_full, wbar, thbar, xb[4];
+    uint64_t full[FB_RING], empty[FB_RING], tmem_full, wbar, thbar, xb[4];     // xb: [0] carry dots, [1] gathered d q rows, [2] d conv halos, [3] partial tiles
     uint32_t tmem_slot;
     volatile int dead;
 };
 
 struct FbSmem {      // byte offsets from the 1 KB aligned base
-    int ring, ths, dqw, wsm, pin, cpart, dconvT, wlc, wldh, dctx, ctx32, w, de, dal, dwc, dcumc, v, dqp, dqin, xch, sh, total;
+    int ring, ths, dhqp, dqs, pdw, wsm, pin, cpart, dconvT, wlc, wldh, dctx, ctx32, w, de, dal, dwc, dcumc, v, xch, sh, total;
     __host__ __device__ FbSmem(int N, int RS) {
         const FbGeom g(N, RS);
         int o = 0;
         auto take = [&](int bytes) { int r = o; o += (bytes + 127) & ~127; return r; };
-        // TMA ring of the d-gates image; its upper half is time-shared with the tanh tile and the d q / d h_q partials,
-        // which are dead between the cell backward and the end of the GEMM
+        // The TMA ring of the d-gates image (8 slots, in use between the image barrier and the end of the GEMM) is time-shared
+        // with everything only the attention / cell phases of a step touch:
+        //   tanh -> d s tile (lands before the step, dead after the d conv contraction), the gathered d q rows and the d h_q
+        //   partials of the cell phase, the per-warp d w partials.
         ring = 0;
-        ths = 4 * PC_CHUNK_BYTES;
-        dqw = ths + ((g.NHP * AF_D * 2 + 127) & ~127);        // [16 warps][128] d q partials; also [RS][4][64][8] ... see kernel
-        const int region = dqw + 16 * AF_D * 4;
-        o = region > FB_RING * PC_CHUNK_BYTES ? ((region + 1023) & ~1023) : FB_RING * PC_CHUNK_BYTES;
+        ths = take(g.NHP * AF_D * 2);
+        dqs = take(PC_ROWS * AF_D * 2);                       // [64 rows][128] bf16 d q of all rows (chunk-swizzled), pushed by the 4 ranks
+        dhqp = take(4 * PC_ROWS * 8 * 4);                     // [4 k quarters][64 rows][8 units]
+        pdw = take(16 * g.NHP * 4);                           // [16 warps][tokens] d w partials
+        o = o > FB_RING * PC_CHUNK_BYTES ? ((o + 1023) & ~1023) : FB_RING * PC_CHUNK_BYTES;
         wsm = take(FB_KSLAB * FB_WSLAB_BYTES);
-        pin = take(4 * 12 * FB_PLD * 4);                     // partial tiles pushed by the 4 ranks: [src rank][8 h_att + 4 ctx columns][68: 64 rows + pad]
-        cpart = take(16 * 2 * g.NHP * 4);                     // conv-transpose partials; also the per-warp d w partials
+        pin = take(4 * 12 * FB_PLD * 4);                      // partial tiles pushed by the 4 ranks: [src rank][8 h_att + 4 ctx columns][68: 64 rows + pad]
+        cpart = take(16 * 2 * g.NHP * 4);                     // conv-transpose partials
         dconvT = take(AF_F * g.NDS * 4);
         wlc = take(AF_F * 2 * AF_KS * 4);
         wldh = take(AF_F * FB_WLD_LD * 2);
@@ -93,8 +96,6 @@ struct FbSmem {      // byte offsets from the 1 KB aligned base
         dwc = take(g.NHP * 4);
         dcumc = take(g.NHP * 4);
         v = take(AF_D * 4);
-        dqp = take(AF_D * 4);
-        dqin = take(3 * AF_D * 4);                            // d q partials pushed by parts 1..RS-1 (part 0 only)
         xch = take(64);                                       // [0..3] carry dots pushed by the parts of the row
         sh = take((int)sizeof(FbShared));
         total = o + 1024;
@@ -124,7 +125,8 @@ struct FbArgs {
     float *dctx_out;                 // [T][B][E]
     unsigned long long *dctxx;       // [2][64][E]   (value, tag) exchange of the recurrent d ctx part, zero at launch
     unsigned long long *dqx;         // [2][64][4 parts][D/2] (bf16x2, tag) exchange of the per-part d q, zero at launch
-    unsigned *bar;                   // 4 counters 128 B apart, zero at launch: d gates of K quarter q complete
+    unsigned *bar;                   // [4 K quarters][16 slabs] counters (one 64-byte line per quarter, zero at launch): the two CTAs
+                                     // that own the 16 hidden units of a 64-row K slab of the d-gates image have written it
     int *err;
     DropCfg drop;
     int row_offset, B, N, T, RS;
@@ -132,6 +134,9 @@ struct FbArgs {
     long long *dbg;
 };
 
+__device__ __forceinline__ void fb_gstamp(long long *dbg, int cta, int i, int k) {
+    if (dbg && i == 20) dbg[32 * 1024 + cta * 16 + k] = fa_globaltimer();
+}
 __device__ __forceinline__ void fb_bar_w14() { asm volatile("bar.sync 2, 448;" ::: "memory"); }
 // Push into another CTA's shared memory with the arrival folded into the store: the 4 / 8 bytes are counted on the
 // receiver's mbarrier (complete_tx), which the receiver arms with the byte count of the phase (expect_tx).  No fence on
@@ -171,13 +176,14 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
     const FbGeom G(N, RS);
     const FbSmem L(N, RS);
     uint8_t *ring = smem + L.ring, *wsm = smem + L.wsm, *ths = smem + L.ths;
-    float *pin = (float *)(smem + L.pin), *cpart = (float *)(smem + L.cpart), *pdw = cpart;     // pdw: per-warp d w partials [16][NHP]
+    float *pin = (float *)(smem + L.pin), *cpart = (float *)(smem + L.cpart), *pdw = (float *)(smem + L.pdw);
+    uint8_t *dqs = smem + L.dqs;
     float *dconvT = (float *)(smem + L.dconvT), *wlc = (float *)(smem + L.wlc);
     __nv_bfloat16 *wldh = (__nv_bfloat16 *)(smem + L.wldh);
     float *dctx = (float *)(smem + L.dctx), *ctx32 = (float *)(smem + L.ctx32);
     float *ws = (float *)(smem + L.w), *des = (float *)(smem + L.de), *dals = (float *)(smem + L.dal);
     float *dwc = (float *)(smem + L.dwc), *dcumc = (float *)(smem + L.dcumc), *vs = (float *)(smem + L.v);
-    float *dqw = (float *)(smem + L.dqw), *dhqp = dqw, *dqp = (float *)(smem + L.dqp), *dqin = (float *)(smem + L.dqin);
+    float *dhqp = (float *)(smem + L.dhqp);
     float *xch = (float *)(smem + L.xch);
     FbShared *sh = (FbShared *)(smem + L.sh);
 
@@ -208,7 +214,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
         mbar_init(&sh->wbar, 1);
         mbar_init(&sh->thbar, 1);
         // exchange barriers: one local arrive.expect_tx per phase, the remote st.async pushes complete the byte count
-        for (int k = 0; k < 4; ++k) mbar_init(sh->xb + k, 1);       // [0] carry dots, [1] d q partials (part 0), [2] d conv halos, [3] partial tiles
+        for (int k = 0; k < 4; ++k) mbar_init(sh->xb + k, 1);
         sh->dead = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -253,7 +259,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
     // DSMEM addresses
     const uint32_t my_xch = smem_u32(xch), my_xb0 = smem_u32(sh->xb + 0), my_xb3 = smem_u32(sh->xb + 3), my_pin = smem_u32(pin);
     const uint32_t halo_bytes = (uint32_t)(min(AF_PAD, G.NH) * AF_F * 4) * (uint32_t)((has_left ? 1 : 0) + (has_right ? 1 : 0));
-    const uint32_t p0_dqin = mapa_u32(smem_u32(dqin), (uint32_t)gbase), p0_xb1 = mapa_u32(smem_u32(sh->xb + 1), (uint32_t)gbase);
+    const uint32_t my_dqs = smem_u32(dqs), my_xb1 = smem_u32(sh->xb + 1);
     const uint32_t nbl_dconv = mapa_u32(smem_u32(dconvT), (uint32_t)(gbase + max(prt - 1, 0)));
     const uint32_t nbr_dconv = mapa_u32(smem_u32(dconvT), (uint32_t)(gbase + min(prt + 1, RS - 1)));
     const uint32_t nbl_xb2 = mapa_u32(smem_u32(sh->xb + 2), (uint32_t)(gbase + max(prt - 1, 0)));
@@ -269,7 +275,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
     const int kk0 = 4 * uu - 1024 * quarter;                     // k inside the quarter of gate row 4 * uu
     const size_t gimg_off = (size_t)quarter * FB_QBYTES + (size_t)(kk0 >> 6) * PC_CHUNK_BYTES + ub * 128 +
                             ((((kk0 & 63) >> 3) ^ (ub & 7)) << 4) + (kk0 & 7) * 2;
-    unsigned *bq_own = a.bar + 32 * quarter, *bq_need = a.bar + 32 * r;
+    unsigned *bq_own = a.bar + 16 * quarter + ((j & 31) >> 1);      // slab of the image the own 8 units belong to
+    const unsigned *bq_need = a.bar + 16 * r;                      // the 16 slab counters of the K quarter this CTA contracts
     const size_t AE = FA_A + FA_E;
 
     // static inputs of the first attention step
@@ -306,7 +313,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
     for (int i = 0; i < T; ++i) {
         const int t = T - 1 - i;
         const uint32_t par = (uint32_t)i & 1u;
-        if (tid == 0) pc_stamp(a.dbg, j, i, 0);
+        if (tid == 0) { pc_stamp(a.dbg, j, i, 0); fb_gstamp(a.dbg, j, i, 0); }
         if ((a.flags & 1) && i > 0) load_mem(0);
         // ============================================================ attention backward of step t: the critical path is local
         if (i > 0 && tid < FA_E) {
@@ -322,8 +329,9 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
         __syncthreads();
         if (tid == 0) {
             pc_stamp(a.dbg, j, i, 1);
+            fb_gstamp(a.dbg, j, i, 1);
             // arm this iteration's exchange phases (the pushes may already be on their way: the byte count is signed)
-            if (prt == 0 && RS > 1) mbar_expect_tx(sh->xb + 1, (uint32_t)(RS - 1) * AF_D * 4);
+            mbar_expect_tx(sh->xb + 1, (uint32_t)PC_ROWS * AF_D * 2);
             if (halo_bytes) mbar_expect_tx(sh->xb + 2, halo_bytes);
             if (i + 1 < T) {
                 mbar_expect_tx(sh->xb + 0, (uint32_t)RS * 4);
@@ -419,11 +427,9 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
                 if (rvalid)
                     st_relaxed_u64(a.dqx + (((size_t)par * PC_ROWS + row) * 4 + prt) * (AF_D / 2) + d2,
                                    ((unsigned long long)(unsigned)(i + 1) << 32) | pack_bf2(q0, q1));
-                if (prt == 0) *reinterpret_cast<float2 *>(dqp + 2 * d2) = make_float2(q0, q1);
-                else st_async_f32x2(p0_dqin + 4 * ((prt - 1) * AF_D + 2 * d2), q0, q1, p0_xb1);
             }
         }
-        if (tid == 0) pc_stamp(a.dbg, j, i, 2);
+        if (tid == 0) { pc_stamp(a.dbg, j, i, 2); fb_gstamp(a.dbg, j, i, 2); }
         // ---- static inputs of the cell backward (unit side): requested now, used after the d q rows have arrived
         float4 ga = make_float4(0.f, 0.f, 0.f, 0.f);
         float c_prev = 0.f, dxd = 0.f;
@@ -481,59 +487,68 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
         }
         if (tid == 0) pc_stamp(a.dbg, j, i, 15);
         __syncthreads();
-        if (tid == 0) pc_stamp(a.dbg, j, i, 3);
+        if (tid == 0) { pc_stamp(a.dbg, j, i, 3); fb_gstamp(a.dbg, j, i, 3); }
 
         // ============================================================ attention-LSTM cell backward of step t (unit side)
-        {   // d h_q[64 rows][8 units] = d q . W_query^T: the per-part d q rows arrive as (bf16x2, tag) words
-            const int rA = 16 * qm + g4, rB = rA + 8;
-            const unsigned long long *qsrc = a.dqx + (size_t)par * PC_ROWS * 4 * (AF_D / 2);
-            float cf[4] = {0.f, 0.f, 0.f, 0.f};
-            // One optimistic read of the (data, tag) words first.  If a row is late, the warp spins on ONE representative word
-            // per publisher it depends on (lane <-> (row of its tile, part)) instead of re-reading everything: with every CTA
-            // polling all rows, full re-reads alone would keep the L2 busier than the data exchange itself.
-            const int prow = 16 * qm + (lane & 15), ppart = lane >> 4;                  // publisher watched by this lane (RS <= 2: all 32 lanes)
-            for (int p = 0; p < RS; ++p) {
-                uint32_t af[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};
-                auto read_all = [&] {
+        {   // d q of all rows.  The per-part rows arrive as (bf16x2, tag) words in global memory; every CTA needs all of them, but the
+            // four CTAs of a cluster share the work: rank r polls and reads rows [16 r, 16 r + 16) only (both parts), adds the parts and
+            // pushes the bf16 rows into the shared memory of all four ranks (st.async).  A quarter of the L2 / LSU traffic of every
+            // CTA reading everything, and the row-major d q stash of the time-batched query-layer gradient falls out of it.
+            const int grow = 16 * r + (tid >> 5);
+            const unsigned long long *qsrc = a.dqx + ((size_t)par * PC_ROWS + grow) * 4 * (AF_D / 2) + 2 * lane;
+            float q4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (grow < B) {
+                unsigned long long wv[4][2];
+                fa_spin([&] {
                     bool all = true;
 #pragma unroll
-                    for (int s = 0; s < 2; ++s)
+                    for (int p = 0; p < 4; ++p) {
+                        if (p < RS) {
 #pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            const int cp = 8 * (2 * kq + s) + tig + 4 * hh;
-                            if (rA < B) {
-                                const unsigned long long wv = ld_relaxed_u64(qsrc + ((size_t)rA * 4 + p) * (AF_D / 2) + cp);
-                                all = all && (unsigned)(wv >> 32) == (unsigned)(i + 1);
-                                af[s][2 * hh] = (uint32_t)wv;
+                            for (int k = 0; k < 2; ++k) {
+                                wv[p][k] = ld_relaxed_u64(qsrc + (size_t)p * (AF_D / 2) + k);
+                                all = all && (unsigned)(wv[p][k] >> 32) == (unsigned)(i + 1);
                             }
-                            if (rB < B) {
-                                const unsigned long long wv = ld_relaxed_u64(qsrc + ((size_t)rB * 4 + p) * (AF_D / 2) + cp);
-                                all = all && (unsigned)(wv >> 32) == (unsigned)(i + 1);
-                                af[s][2 * hh + 1] = (uint32_t)wv;
-                            }
-                        }
-                    return __all_sync(0xffffffffu, all) != 0;
-                };
-                bool got = read_all();
-                while (!got) {
-                    bool alive = true;
-                    for (int pp = ppart; pp < RS && alive; pp += 2) {
-                        if (prow < B) {
-                            const unsigned long long *wsrc = qsrc + ((size_t)prow * 4 + pp) * (AF_D / 2) + (lane & 15) * 4 + kq;
-                            alive = fa_spin([&] { return (unsigned)(ld_relaxed_u64(wsrc) >> 32) == (unsigned)(i + 1); }, &sh->dead, a.err, 57);
                         }
                     }
-                    if (!__all_sync(0xffffffffu, alive)) break;
-                    got = read_all();
+                    return all;
+                }, &sh->dead, a.err, 57);
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    if (p < RS) {
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            q4[2 * k] += bf_lo((uint32_t)wv[p][k]);
+                            q4[2 * k + 1] += bf_hi((uint32_t)wv[p][k]);
+                        }
+                    }
                 }
-                mma_bf16_16816(cf, af[0][0], af[0][1], af[0][2], af[0][3], wqf[0][0], wqf[0][1]);
-                mma_bf16_16816(cf, af[1][0], af[1][1], af[1][2], af[1][3], wqf[1][0], wqf[1][1]);
+            }
+            const uint32_t w0 = pack_bf2(q4[0], q4[1]), w1 = pack_bf2(q4[2], q4[3]);
+            if (grow < B) *reinterpret_cast<uint2 *>(a.dq_rm + ((size_t)t * B + grow) * AF_D + 4 * lane) = make_uint2(w0, w1);
+            const uint32_t doff = (uint32_t)(grow * 256 + (((lane >> 1) ^ (grow & 7)) << 4) + (lane & 1) * 8);
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                st_async_f32x2(mapa_u32(my_dqs + doff, (uint32_t)p), __uint_as_float(w0), __uint_as_float(w1), mapa_u32(my_xb1, (uint32_t)p));
+            fb_wait_warp(sh->xb + 1, par, &sh->dead, a.err, 55);
+            // d h_q[64 rows][8 units] = d q . W_query^T on mma.sync: warp (row tile qm, k quarter kq)
+            const int rA = 16 * qm + g4, rB = rA + 8;
+            const uint8_t *ra = dqs + rA * 256 + 4 * tig, *rb = dqs + rB * 256 + 4 * tig;
+            float cf[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const int ch = 2 * (2 * kq + s2);
+                const uint32_t a0 = *reinterpret_cast<const uint32_t *>(ra + ((ch ^ (rA & 7)) << 4));
+                const uint32_t a1 = *reinterpret_cast<const uint32_t *>(rb + ((ch ^ (rB & 7)) << 4));
+                const uint32_t a2 = *reinterpret_cast<const uint32_t *>(ra + (((ch + 1) ^ (rA & 7)) << 4));
+                const uint32_t a3 = *reinterpret_cast<const uint32_t *>(rb + (((ch + 1) ^ (rB & 7)) << 4));
+                mma_bf16_16816(cf, a0, a1, a2, a3, wqf[s2][0], wqf[s2][1]);
             }
             *reinterpret_cast<float2 *>(dhqp + ((size_t)(kq * PC_ROWS + rA)) * 8 + 2 * tig) = make_float2(cf[0], cf[1]);
             *reinterpret_cast<float2 *>(dhqp + ((size_t)(kq * PC_ROWS + rB)) * 8 + 2 * tig) = make_float2(cf[2], cf[3]);
         }
         __syncthreads();
-        if (tid == 0) pc_stamp(a.dbg, j, i, 4);
+        if (tid == 0) { pc_stamp(a.dbg, j, i, 4); fb_gstamp(a.dbg, j, i, 4); }
         {
             uint2 dgp = make_uint2(0u, 0u);
             if (uvalid) {
@@ -549,21 +564,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
                 fence_proxy_async_global();
             }
             __syncthreads();
-            if (tid == 0) { gbar_arrive(bq_own); pc_stamp(a.dbg, j, i, 5); }
+            if (tid == 0) { gbar_arrive(bq_own); pc_stamp(a.dbg, j, i, 5); fb_gstamp(a.dbg, j, i, 5); }
             if (uvalid) *reinterpret_cast<uint2 *>(a.dg_rm + ((size_t)t * B + ub) * 4 * FA_A + 4 * uu) = dgp;
-        }
-        if (wid == 3 && prt == 0 && rvalid) {   // d q of the whole row for the time-batched query-layer gradient
-            if (RS > 1) fb_wait_warp(sh->xb + 1, par, &sh->dead, a.err, 55);
-#pragma unroll
-            for (int k2 = 0; k2 < 2; ++k2) {
-                const int d2 = lane + 32 * k2;
-                float2 q = *reinterpret_cast<const float2 *>(dqp + 2 * d2);
-                for (int p = 1; p < RS; ++p) {
-                    const float2 o = *reinterpret_cast<const float2 *>(dqin + (p - 1) * AF_D + 2 * d2);
-                    q.x += o.x; q.y += o.y;
-                }
-                *reinterpret_cast<uint32_t *>(a.dq_rm + ((size_t)t * B + row) * AF_D + 2 * d2) = pack_bf2(q.x, q.y);
-            }
         }
         if (i + 1 == T) break;
 
@@ -584,33 +586,66 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
         // restart at 0 every step, no state is carried in registers.)
         if (wid == 0) {
             if (elect_one()) {      // TMA producer: this CTA's K quarter of the d-gates image
-                int ring_slot = 0;
-                uint32_t ring_ph = 0;
-                bool ok = okw && fa_wait_gbar(bq_need, 32u * (unsigned)(i + 1), &sh->dead, a.err, 58);
-                pc_stamp(a.dbg, j, i, 8);
-                if (ok) {
-                    fence_proxy_async_global();
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // ring slots 4.. were used through the generic proxy
-                    const uint8_t *src = a.gimg + (size_t)par * 4 * FB_QBYTES + (size_t)r * FB_QBYTES;
-                    for (int s = 0; s < FB_KSLAB; ++s) {
-                        if (!fa_wait_mbar(sh->empty + ring_slot, ring_ph ^ 1u, &sh->dead, a.err, 59)) break;
-                        mbar_expect_tx(sh->full + ring_slot, PC_CHUNK_BYTES);
-                        tma_bulk_g2s(ring + (size_t)ring_slot * PC_CHUNK_BYTES, src + (size_t)s * PC_CHUNK_BYTES, PC_CHUNK_BYTES, sh->full + ring_slot);
-                        if (++ring_slot == FB_RING) { ring_slot = 0; ring_ph ^= 1u; }
+                // A slab is fetched as soon as ITS two producer CTAs have arrived (per-slab counters, read 16 at a time with relaxed
+                // vector loads + one fence): the stream starts under the skew of the 32 producers instead of after the last one.
+                // Slabs 0..7 go to their ring slots in any order; slab s >= 8 needs slot s - 8 back from the MMA issuer, which
+                // consumes in order (fixed accumulation order: bit-exact run to run).
+                const unsigned target = 2u * (unsigned)(i + 1);
+                const uint8_t *src = a.gimg + (size_t)par * 4 * FB_QBYTES + (size_t)r * FB_QBYTES;
+                uint32_t pending = okw ? 0xffffu : 0u;
+                bool first = true;
+                const long long t0 = clock64();
+                while (pending) {
+                    unsigned cnt[16];
+#pragma unroll
+                    for (int q4 = 0; q4 < 3; ++q4)
+                        asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(cnt[4 * q4]), "=r"(cnt[4 * q4 + 1]), "=r"(cnt[4 * q4 + 2]), "=r"(cnt[4 * q4 + 3])
+                                     : "l"(bq_need + 4 * q4)
+                                     : "memory");
+                    // (the last one is an acquire: everything this thread issues afterwards - the TMA reads - is ordered behind it;
+                    // a separate fence.acq_rel.gpu here is a MEMBAR.ALL.GPU on the critical path)
+                    asm volatile("ld.acquire.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(cnt[12]), "=r"(cnt[13]), "=r"(cnt[14]), "=r"(cnt[15])
+                                 : "l"(bq_need + 12)
+                                 : "memory");
+                    uint32_t ready = 0;
+#pragma unroll
+                    for (int s = 0; s < 16; ++s)
+                        if (cnt[s] >= target) ready |= 1u << s;
+                    ready &= pending;
+                    if (ready) {
+                        fence_proxy_async_global();
+                        if (first) {
+                            pc_stamp(a.dbg, j, i, 8);
+                            fb_gstamp(a.dbg, j, i, 8);
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the ring was used through the generic proxy
+                            first = false;
+                        }
+#pragma unroll 1
+                        for (int s = 0; s < 16; ++s) {
+                            if (!(ready >> s & 1u)) continue;
+                            const int slot = s & 7;
+                            if (s >= 8 && !mbar_try_wait(sh->empty + slot, 0u)) continue;      // slab s - 8 not consumed yet
+                            mbar_expect_tx(sh->full + slot, PC_CHUNK_BYTES);
+                            tma_bulk_g2s(ring + (size_t)slot * PC_CHUNK_BYTES, src + (size_t)s * PC_CHUNK_BYTES, PC_CHUNK_BYTES, sh->full + slot);
+                            pending &= ~(1u << s);
+                        }
                     }
+                    if (sh->dead) break;
+                    if (clock64() - t0 > FA_WAIT_CYCLES) { sh->dead = 1; atomicCAS(a.err, 0, 58); break; }
                 }
                 pc_stamp(a.dbg, j, i, 9);
             }
             __syncwarp();
         } else if (wid == 1) {
             if (elect_one()) {      // MMA issuer
-                int ring_slot = 0;
-                uint32_t ring_ph = 0;
                 constexpr uint32_t idesc = umma_idesc_bf16(64, FB_NCOL);
                 const uint64_t a0 = umma_desc_sw128(smem_u32(ring)), b0 = umma_desc_sw128(smem_u32(wsm));
                 bool ok = okw;
                 for (int s = 0; s < FB_KSLAB && ok; ++s) {
-                    if (!fa_wait_mbar(sh->full + ring_slot, ring_ph, &sh->dead, a.err, 60)) { ok = false; break; }
+                    const int ring_slot = s & 7;                 // slab s lives in slot s % 8: phase parity 0 for s < 8, 1 for s >= 8
+                    if (!fa_wait_mbar(sh->full + ring_slot, (uint32_t)(s >> 3), &sh->dead, a.err, 60)) { ok = false; break; }
                     if (s == 0) pc_stamp(a.dbg, j, i, 10);
                     tc_fence_after();
                     const uint64_t ad = a0 + (uint64_t)(ring_slot * (PC_CHUNK_BYTES >> 4)), bd = b0 + (uint64_t)(s * (FB_WSLAB_BYTES >> 4));
@@ -619,7 +654,6 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
                     umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
                     umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
                     umma_commit(sh->empty + ring_slot);
-                    if (++ring_slot == FB_RING) { ring_slot = 0; ring_ph ^= 1u; }
                 }
                 if (ok) umma_commit(&sh->tmem_full);
                 pc_stamp(a.dbg, j, i, 11);
@@ -683,7 +717,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
         if (uvalid) mult = drop_mult(drop, SITE_ATT, (uint32_t)(t - 1), (uint32_t)(ub + a.row_offset), (uint32_t)uu);
         __syncthreads();
         const bool okt = sh->dead == 0;
-        if (tid == 0) pc_stamp(a.dbg, j, i, 6);
+        if (tid == 0) { pc_stamp(a.dbg, j, i, 6); fb_gstamp(a.dbg, j, i, 6); }
         if (wid == 0 && elect_one()) {
             if (th_live) {      // tanh tile of step t-1 (lands in ring slots the MMAs have finished reading)
                 mbar_expect_tx(&sh->thbar, (uint32_t)n_own * AF_D * 2);
@@ -719,7 +753,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
                                    ((unsigned long long)(unsigned)(i + 1) << 32) | (unsigned long long)__float_as_uint(cx));
             }
         }
-        if (tid == 0) pc_stamp(a.dbg, j, i, 7);
+        if (tid == 0) { pc_stamp(a.dbg, j, i, 7); fb_gstamp(a.dbg, j, i, 7); }
     }
     __syncthreads();
     cluster.sync();          // peers may still be writing into / reading this CTA's shared memory
@@ -778,7 +812,7 @@ inline int launch_att_chain_bwd(const FbArgs &a_in, cudaStream_t st) {
         GVX_CUDA(cudaFuncSetAttribute(k_att_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    GVX_CUDA(cudaMemsetAsync(a.bar, 0, 32 * 4 * sizeof(unsigned), st));
+    GVX_CUDA(cudaMemsetAsync(a.bar, 0, 64 * sizeof(unsigned), st));
     GVX_CUDA(cudaMemsetAsync(a.dctxx, 0, fb_dctxx_words() * sizeof(unsigned long long), st));
     GVX_CUDA(cudaMemsetAsync(a.dqx, 0, fb_dqx_words() * sizeof(unsigned long long), st));
     GVX_CUDA(cudaMemsetAsync(a.gimg, 0, fb_gimg_bytes(), st));

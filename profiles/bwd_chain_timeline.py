@@ -52,3 +52,13 @@ for i, n in enumerate(names):
     d = np.median(x[2:-1, i] - x[2:-1, 0])
     print(f"  {i} {n:48s} +{d:7.0f} cyc  ({(d - prev) / 1.965e3:5.2f} us)")
     prev = d
+
+# ---- per-CTA skew at reverse-time iteration 20 (%globaltimer, ns): when did each of the 128 CTAs reach each event?
+g = dbg[2].reshape(-1)[: 128 * 16].cpu().numpy().astype(np.float64).reshape(128, 16)
+ev = {0: "iter start", 1: "d ctx assembled", 2: "d q published", 3: "d conv done", 4: "d q rows arrived", 5: "image barrier arrive",
+      8: "image barrier passed", 6: "tmem_full", 7: "d ctx published"}
+t0 = g[:, 0].min()
+print("per-CTA event times at iteration 20, ns after the first CTA started it: min / median / max (argmax CTA)")
+for k in (0, 1, 2, 3, 4, 5, 8, 6, 7):
+    col = g[:, k] - t0
+    print(f"  {ev[k]:24s} {col.min():8.0f} {np.median(col):8.0f} {col.max():8.0f}   (CTA {int(col.argmax())}; CTA 0: {col[0]:.0f})")
