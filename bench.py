@@ -9,11 +9,15 @@ the decoder: zero_grad, Decoder.forward, loss, BPTT, [gradient all-reduce], clip
 `value` = mel-frames/s with inputs resident in HBM, CUDA-event timed, max over ranks;
 `e2e`   = the same step through genvox_b200.Decoder with HOST (pinned) inputs: H2D of memory/mel/gate
           and a D2H read of the loss inside the timed region;
-`infer` = BASELINE.json configs[1] (batch 64, 1000 fixed decoder steps, fp32) in decoder steps/s;
+`infer` = BASELINE.json configs[1] (batch 64, 1000 fixed decoder steps, fp32) in decoder steps/s, with its own e2e
+          (host memory in, mel out) and weight-streaming roofline;
 `roofline` for the dominant kernel of the step, from CUDA events the library records around every
-phase launch during one extra profiled step (gvx_profile_*), `cpu_baseline` = the oracle port
-(torch CPU, all host threads) on a bounded sample of the same workload.
---impl reference times that CPU implementation alone (rank 0 only under torchrun).
+phase launch during one extra profiled step (gvx_profile_*);
+`cpu_baseline` = the UNMODIFIED reference Decoder (oracle/_ref, staged by oracle/build_ref.py; "kind": "reference") - or the
+          oracle port when that tree is absent ("port") - on the host cores, on a bounded sample of the same workload;
+`gpu_torch_baseline` = the same reference modules executed by stock PyTorch on the SAME GPU (fp32 and bf16 autocast; training
+          and the batched decode loop): the number north_star asks to beat.
+--impl reference times the CPU implementation alone (rank 0 only under torchrun), on this arm's config.
 """
 import argparse
 import ctypes as C
@@ -32,7 +36,9 @@ if ROOT not in sys.path:
 TRAIN = dict(B=64, N=150, T=int(os.environ.get("GVX_BENCH_T", "800")))     # BASELINE.json configs[2] (per GPU); the env
                                                                            # override is for debugging runs only
 INFER = dict(B=64, N=150, steps=1000)     # BASELINE.json configs[1]
-CPU_SAMPLE_T = 8                          # frames of the training workload the CPU legs run per step
+CPU_SAMPLE_T = 64                         # frames of the training workload the CPU legs run per step (fixed costs of a
+                                          # step - zero_grad, clip, Adam over 18 M parameters - are then < 5 % of it)
+GPU_TORCH_SAMPLE_T = 100                  # frames per step of the stock-PyTorch-on-GPU baseline
 METRIC = "Tacotron2 train mel-frames/s"
 UNIT = "mel-frames/s"
 
@@ -108,107 +114,213 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------ CPU legs (oracle port)
+# ------------------------------------------------------------------------------------ baseline legs (reference / oracle port)
+def workload_config(world, precision, B, N, T):
+    return {"workload": f"BASELINE configs[2]: decoder train step (fwd + loss + BPTT + allreduce + clip + Adam), "
+                        f"batch {B}/GPU, {N} tokens, {T}x80 mel frames, "
+                        + ("bf16 tcgen05 gate GEMMs with fp32 accumulation, fp32 pointwise/attention"
+                           if precision == "bf16" else "fp32 arithmetic"),
+            "global_batch": world * B, "parallelism": f"dp{world}",
+            "l2": "per-step working set (stash + workspace, several GB) is far larger than the 126 MB L2"}
+
+
+def _baseline_decoder(device):
+    """The UNMODIFIED reference Decoder (models/tts/tacotron2.py:258-414, imported from /root/reference or from the copy
+    oracle/build_ref.py staged under oracle/_ref) with the same init as the GPU arm; None when no reference tree exists."""
+    import torch
+    from oracle import ref_import as R
+    if not R.reference_available():
+        return None
+    ref = R.import_reference()
+    torch.manual_seed(0)
+    return ref.Decoder(**decoder_dims()).to(device).train()
+
+
+def _train_step_fn(torch, dec, P, opt, memory, mel, gate, lengths, autocast=None):
+    """One decoder train step (tacotron2.py:515-522 restricted to the decoder) of the reference module `dec`, or of the oracle
+    port over the parameter dict `P` when the reference tree is absent."""
+    from genvox_b200.training import decoder_loss
+    from oracle import decoder_oracle as O
+    params = list(dec.parameters()) if dec is not None else list(P.values())
+
+    def step(i):
+        opt.zero_grad(set_to_none=True)
+        ctx = torch.autocast("cuda", dtype=autocast) if autocast is not None else __import__("contextlib").nullcontext()
+        with ctx:
+            if dec is not None:
+                m, g, _ = dec(memory, mel, lengths)
+            else:
+                m, g, _ = O.forward_teacher(P, memory, mel, lengths, seed=123 + i, training=True)
+        loss, _, _ = decoder_loss(m.float(), g.float(), mel, gate)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        return loss
+
+    return step
+
+
 def cpu_train_leg(steps, warmup, sample_T=CPU_SAMPLE_T):
-    """The oracle port of the same train step on the host cores, on a bounded sample of the workload:
+    """The reference's own CPU implementation of the same train step on the host cores, on a bounded sample of the workload:
     the full batch (64 x 150 tokens) but `sample_T` teacher-forced frames per step."""
     import torch
-    from oracle import decoder_oracle as O
     import genvox_b200
-    from genvox_b200.training import decoder_loss
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     B, N = TRAIN["B"], TRAIN["N"]
-    torch.manual_seed(0)
-    dec = genvox_b200.Decoder(**decoder_dims())          # parameter container only: same init as the GPU arm
-    P = {k: v.detach().clone().requires_grad_(True) for k, v in dec.named_parameters()}
-    opt = torch.optim.Adam(list(P.values()), lr=1e-3, weight_decay=1e-6)
+    dec = _baseline_decoder("cpu")
+    P = None
+    if dec is None:
+        torch.manual_seed(0)
+        cont = genvox_b200.Decoder(**decoder_dims())          # parameter container only: same init as the GPU arm
+        P = {k: v.detach().clone().requires_grad_(True) for k, v in cont.named_parameters()}
+    opt = torch.optim.Adam(list(dec.parameters()) if dec is not None else list(P.values()), lr=1e-3, weight_decay=1e-6)
     memory, mel, gate, lengths = synthetic_batch(torch, B, N, sample_T)
-
-    def step(i):
-        opt.zero_grad(set_to_none=True)
-        m, g, _ = O.forward_teacher(P, memory, mel, lengths, seed=123 + i, training=True)
-        loss, _, _ = decoder_loss(m, g, mel, gate)
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(list(P.values()), 1.0)
-        opt.step()
-        return float(loss.detach())
-
+    step = _train_step_fn(torch, dec, P, opt, memory, mel, gate, lengths)
     for i in range(warmup):
         step(i)
     t0 = time.perf_counter()
     for i in range(steps):
         step(warmup + i)
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return dict(value=B * sample_T / dt, unit=UNIT, cores=cores, threads=torch.get_num_threads(), kind="port",
-                sample=f"oracle/decoder_oracle.py train step (fwd+loss+BPTT+clip+Adam), B={B}, N={N}, {sample_T} of "
+    what = ("the unmodified reference Decoder (models/tts/tacotron2.py via oracle/_ref)" if dec is not None
+            else "oracle/decoder_oracle.py (port: no reference tree staged)")
+    return dict(value=B * sample_T / dt, unit=UNIT, cores=cores, threads=torch.get_num_threads(),
+                kind="reference" if dec is not None else "port",
+                sample=f"{what}, train step (fwd+loss+BPTT+clip+Adam) on CPU fp32, B={B}, N={N}, {sample_T} of "
                        f"{TRAIN['T']} frames per step, {steps} timed steps after {warmup} warm-up",
                 ms_per_step=dt * 1e3)
 
 
-def torch_gpu_train_leg(steps, warmup, sample_T=100):
-    """Optional (--impl reference --reference-device cuda; never part of the default run): the oracle port's torch ops
-    executed on the GPU - the stock PyTorch eager path the reference itself takes on a CUDA device (nn.LSTMCell math,
-    conv1d, bmm, autograd BPTT), with torch's own dropout instead of the Philox stream (mask values do not matter for
-    timing) - on a bounded sample of the workload: the full batch, `sample_T` teacher-forced frames per step."""
+def torch_gpu_legs(dev, steps=2, warmup=1, sample_T=GPU_TORCH_SAMPLE_T, infer_steps=100):
+    """Stock PyTorch on the SAME GPU: the reference modules (eager kernels: cuBLAS GEMMs, ATen LSTM-cell pointwise, cuDNN
+    conv, autograd BPTT) on a bounded sample of the training workload - fp32 as the reference runs it, and under bf16
+    autocast - plus the batched decode loop (initialize_decoder_states / prenet / decode driven for B rows, as the public
+    inference is B = 1 only).  This is the "cuDNN/PyTorch GPU path" north_star asks to beat."""
     import torch
-    import torch.nn.functional as F
-    from oracle import decoder_oracle as O
     import genvox_b200
-    from genvox_b200.training import decoder_loss
-    dev = torch.device("cuda:0")
     B, N = TRAIN["B"], TRAIN["N"]
-    torch.manual_seed(0)
-    dec = genvox_b200.Decoder(**decoder_dims())          # parameter container only: same init as the other arms
-    P = {k: v.detach().clone().to(dev).requires_grad_(True) for k, v in dec.named_parameters()}
-    opt = torch.optim.Adam(list(P.values()), lr=1e-3, weight_decay=1e-6)
-    memory, mel, gate, lengths = synthetic_batch(torch, B, N, sample_T)
-    memory, mel, gate = memory.to(dev), mel.to(dev), gate.to(dev)
-    O.philox_dropout = lambda x, p, on, *a, **k: F.dropout(x, p, on)          # tacotron2.py:143,:341,:358
-    O.get_mask_from_lengths = lambda lengths, max_len=None: (
-        torch.arange(max_len if max_len is not None else int(lengths.max()), device=dev)[None, :] >= lengths.to(dev)[:, None])
-
-    def step(i):
-        opt.zero_grad(set_to_none=True)
-        m, g, _ = O.forward_teacher(P, memory, mel, lengths, seed=123 + i, training=True)
-        loss, _, _ = decoder_loss(m, g, mel, gate)
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(list(P.values()), 1.0)
-        opt.step()
-
-    for i in range(warmup):
-        step(i)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(steps):
-        step(warmup + i)
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    return dict(value=B * sample_T / dt, unit=UNIT, cores=os.cpu_count() or 1, kind="port",
-                sample=f"oracle/decoder_oracle.py train step on cuda:0 (stock PyTorch eager ops, fp32), B={B}, N={N}, {sample_T} of "
-                       f"{TRAIN['T']} frames per step, {steps} timed steps after {warmup} warm-up",
-                ms_per_step=dt * 1e3)
+    out = {"device": torch.cuda.get_device_name(dev), "sample": f"B={B}, N={N}, {sample_T} of {TRAIN['T']} frames per train step; "
+                                                               f"{infer_steps} of {INFER['steps']} decode steps"}
+    memory, mel, gate, lengths = (t.to(dev) for t in synthetic_batch(torch, B, N, sample_T))
+    for name, ac in (("train_fp32", None), ("train_bf16_autocast", torch.bfloat16)):
+        dec = _baseline_decoder(dev)
+        P = None
+        if dec is None:
+            torch.manual_seed(0)
+            cont = genvox_b200.Decoder(**decoder_dims())
+            P = {k: v.detach().clone().to(dev).requires_grad_(True) for k, v in cont.named_parameters()}
+            import torch.nn.functional as F
+            from oracle import decoder_oracle as O
+            O.philox_dropout = lambda x, p, on, *a, **k: F.dropout(x, p, on)
+            O.get_mask_from_lengths = lambda lengths, max_len=None: (
+                torch.arange(max_len if max_len is not None else int(lengths.max()), device=dev)[None, :] >= lengths.to(dev)[:, None])
+        opt = torch.optim.Adam(list(dec.parameters()) if dec is not None else list(P.values()), lr=1e-3, weight_decay=1e-6)
+        step = _train_step_fn(torch, dec, P, opt, memory, mel, gate, lengths, autocast=ac)
+        for i in range(warmup):
+            step(i)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            step(warmup + i)
+        torch.cuda.synchronize(dev)
+        dt = (time.perf_counter() - t0) / steps
+        out[name] = {"mel_frames_per_s": B * sample_T / dt, "ms_per_step": dt * 1e3, "kind": "reference" if dec is not None else "port"}
+        del opt, step, dec, P
+    dec = _baseline_decoder(dev)
+    if dec is not None:
+        dec.eval()
+        mem_i = memory[:INFER["B"]]
+        for name, ac in (("infer_fp32", None), ("infer_bf16_autocast", torch.bfloat16)):
+            def run(n):
+                with torch.no_grad(), (torch.autocast("cuda", dtype=ac) if ac is not None else __import__("contextlib").nullcontext()):
+                    dec.initialize_decoder_states(mem_i, mask=None)
+                    x = mem_i.new_zeros(mem_i.shape[0], 80)
+                    for _ in range(n):
+                        m, _, _ = dec.decode(dec.prenet(x))
+                        x = m.float()
+            run(10)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            run(infer_steps)
+            torch.cuda.synchronize(dev)
+            dt = (time.perf_counter() - t0) / infer_steps
+            out[name] = {"decoder_steps_per_s": 1.0 / dt, "us_per_step": dt * 1e6, "kind": "reference"}
+    return out
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    if args.reference_device == "cuda":
-        leg = torch_gpu_train_leg(args.steps, args.warmup)
-        print(json.dumps({"impl": "reference", "device": "cuda", "metric": METRIC, "value": leg["value"], "unit": UNIT, "n_gpus": 1,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["ms_per_step"], "higher_is_better": True,
-                          "dtype": "f32", "data": "synthetic", "config": {"workload": leg["sample"]}}), flush=True)
-        return
     leg = cpu_train_leg(args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": leg["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"decoder train step, batch {TRAIN['B']}, {TRAIN['N']} tokens, {CPU_SAMPLE_T} of "
-                                   f"{TRAIN['T']}x80 mel frames per step (bounded sample), CPU"},
+            "config": workload_config(args.gpus, args.precision, TRAIN["B"], TRAIN["N"], TRAIN["T"]),
             "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ roofline accounting
+def slot_rooflines(phases, B, N, T, pk, precision):
+    """One roofline entry per profiler slot; the algorithmic FLOPs / bytes of an entry are those of the kernels THAT slot
+    brackets (DESIGN.md section 5 lists them).  Tensor-bound entries: 2 * MACs of the contractions in the slot over the slot's
+    device time against the measured sustained bf16 rate; HBM-bound entries (the attention chains): SURVEY.md 8(d)'s
+    per-step attention bytes over the chain's time per step against the measured copy bandwidth."""
+    H = A = 1024
+    E, D, P, M, F = 512, 128, 256, 80, 32
+    Kd, Ka, Kp = A + E + H, P + E + A, H + E
+    TB = float(T) * B
+    fused = phases.get("attention", {}).get("launches") == 1          # persistent chains: ONE launch for all T steps
+    roofs = {}
+
+    def tensor(name, flops, kernels, burst=False):
+        if name not in phases or phases[name]["ms"] <= 0:
+            return
+        ach = flops / (phases[name]["ms"] * 1e-3) / 1e12
+        # a slot that is ONE short library-shaped GEMM is a kernel timed alone: the burst figure is its peak (B200_PROFILING.md);
+        # the persistent chains run for milliseconds: sustained
+        peak = pk["tf_burst"] if burst else pk["tf_sustained"]
+        roofs[name] = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                       "traffic": None, "avg_us": phases[name]["avg_us"], "us_per_step": 1e3 * phases[name]["ms"] / T,
+                       "launches": phases[name]["launches"], "algorithmic_flops": flops, "kernels": kernels,
+                       "peak_source": pk["source"] + (" (bf16 burst)" if burst else " (bf16 sustained)")
+                                      + ("" if precision == "bf16" else "; fp32 mode runs FFMA")}
+
+    def hbm(name, bytes_per_step, kernels, note=None):
+        if name not in phases or phases[name]["ms"] <= 0:
+            return
+        per_step_us = 1e3 * phases[name]["ms"] / T
+        ach = bytes_per_step / (per_step_us * 1e-6) / 1e9
+        roofs[name] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                       "traffic": None, "avg_us": phases[name]["avg_us"], "us_per_step": per_step_us,
+                       "launches": phases[name]["launches"], "algorithmic_bytes_per_step": bytes_per_step, "kernels": kernels,
+                       "peak_source": pk["source"]}
+        if note:
+            roofs[name]["note"] = note
+
+    if fused:
+        tensor("att_lstm", 2.0 * TB * P * 4 * A, "time-batched GEMM: prenet part of the attention-LSTM gates, all frames", burst=True)
+        hbm("attention", B * N * (E * 2.0 + D * 4.0) + B * N * 4.0, "k_att_chain_fwd (attention LSTM + query + attention, all T steps)",
+            "latency-bound persistent chain (2 grid barriers + 2 exchanges per step); operands L2 resident")
+        tensor("dec_lstm_input_gemm", 2.0 * TB * (A + E) * 4 * H, "time-batched GEMM: input part of the decoder-LSTM gates", burst=True)
+        tensor("dec_lstm", 2.0 * TB * H * 4 * H, "k_lstm_chain_fwd (recurrent part, all T steps)")
+        tensor("output", 2.0 * TB * (M + 1) * Kp, "time-batched GEMM: mel / gate projections")
+        tensor("bwd_dec_pointwise", 2.0 * TB * H * 4 * H, "k_lstm_chain_bwd (decoder-LSTM BPTT, all T steps)")
+        tensor("bwd_dec_gemm", 2.0 * TB * (A + E) * 4 * H, "time-batched GEMM: d [h_att | ctx] from the decoder-LSTM input", burst=True)
+        hbm("bwd_attention", B * N * (E * 2.0 + D * 2.0) + B * N * 4.0, "k_att_chain_bwd (attention-chain BPTT, all T steps)",
+            "latency-bound persistent chain (3 inter-SM exchanges per step); bf16 memory + bf16 tanh stash read, d e written")
+        tensor("bwd_time_batched", 2.0 * TB * (4 * H * Kd + 4 * A * Ka + 4 * A * P + D * A + (M + 1) * Kp + 2 * P * P + P * M)
+               + 2.0 * TB * N * (D * F + 2 * F * 31) + 4.0 * B * N * D * E,
+               "weight-gradient / prenet GEMMs, attention-parameter reductions, d memory")
+    else:
+        for name, Kc in (("dec_lstm", Kd), ("att_lstm", Ka), ("bwd_dec_gemm", Kd), ("bwd_att_gemm", Ka)):
+            tensor(name, 2.0 * TB * Kc * 4 * H, "gate GEMM of every step (per-step launch chain)")
+        for name in ("attention", "bwd_attention"):
+            hbm(name, B * N * (E + D) * 4.0 + B * N * 4.0, "per-step attention kernel")
+    return roofs
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -311,12 +423,7 @@ def run_ours(args, rank, world, local_rank):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[2]: decoder train step (fwd + loss + BPTT + allreduce + clip + Adam), "
-                                   f"batch {B}/GPU, {N} tokens, {T}x80 mel frames, "
-                                   + ("bf16 tcgen05 gate GEMMs with fp32 accumulation, fp32 pointwise/attention"
-                                      if args.precision == "bf16" else "fp32 arithmetic"),
-                       "global_batch": world * B, "parallelism": f"dp{world}",
-                       "l2": "per-step working set (stash + workspace, several GB) is far larger than the 126 MB L2"},
+            "config": workload_config(world, args.precision, B, N, T),
             "e2e": e2e, "gpu_launches": int(launches), "final_loss": final_loss, "host_enqueue_ms_per_step": host_enqueue_ms}
     if clocks is not None:
         line["clocks"] = clocks
@@ -343,45 +450,15 @@ def run_ours(args, rank, world, local_rank):
             slot += 1
         line["phases_ms"] = {k: round(v["ms"], 3) for k, v in phases.items()}
         pk = peaks()
-        H, Kd, Ka, E, D = 1024, 2560, 1792, 512, 128
-        roofs = {}
-        for name, Kc in (("dec_lstm", Kd), ("att_lstm", Ka), ("bwd_dec_gemm", Kd), ("bwd_att_gemm", Ka)):
-            if name in phases:
-                flops = 2.0 * B * Kc * 4 * H * T                # algorithmic FLOPs of the gate GEMMs of all T steps
-                ach = flops / (phases[name]["ms"] * 1e-3) / 1e12     # (one launch per step, or one persistent launch)
-                roofs[name] = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                               "frac": ach / pk["tf_sustained"], "traffic": None, "avg_us": phases[name]["avg_us"],
-                               "us_per_step": 1e3 * phases[name]["ms"] / T, "launches": phases[name]["launches"],
-                               "peak_source": pk["source"] + " (bf16 sustained)"
-                               + ("" if args.precision == "bf16" else "; this kernel runs fp32 FFMA")}
-        for name in ("attention", "bwd_attention"):
-            if name in phases:
-                fused = phases[name]["launches"] == 1          # the persistent attention chain: ONE launch for all T steps
-                if name == "attention" and fused:
-                    # SURVEY.md 8(d) attention path per step: memory (bf16 copy) + processed memory (fp32) read, alignment written
-                    nbytes = B * N * (E * 2.0 + D * 4.0) + B * N * 4.0
-                elif name == "bwd_attention" and phases.get("attention", {}).get("launches") == 1:
-                    # after the fused forward chain the BPTT attention kernel reads the bf16 memory copy + the fp32 tanh stash
-                    nbytes = B * N * (E * 2.0 + D * 4.0) + B * N * 4.0
-                else:
-                    nbytes = B * N * (E + D) * 4.0 + B * N * 4.0    # memory + processed memory (or stashed tanh) + weights row
-                per_step_us = 1e3 * phases[name]["ms"] / T if fused else phases[name]["avg_us"]
-                ach = nbytes / (per_step_us * 1e-6) / 1e9
-                roofs[name] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                               "frac": ach / pk["hbm_gbs"], "traffic": None, "avg_us": phases[name]["avg_us"],
-                               "us_per_step": per_step_us, "launches": phases[name]["launches"],
-                               "algorithmic_bytes_per_step": nbytes, "peak_source": pk["source"]}
-                if name == "attention" and fused:
-                    roofs[name]["note"] = ("one persistent launch = attention LSTM + query + attention of all T steps; "
-                                           "latency-bound (2 grid barriers + 2 exchanges per step), operands L2 resident")
-        tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
-        if os.path.isfile(tpath):          # DRAM bytes per launch from the committed ncu --set full capture (cold cache)
+        roofs = slot_rooflines(phases, B, N, T, pk, args.precision)
+        tpath = os.path.join(ROOT, "profiles", "traffic_r2.json")
+        if os.path.isfile(tpath):          # DRAM bytes per launch from the committed ncu --set full capture
             with open(tpath) as fh:
                 traffic = json.load(fh)
             for k, r in roofs.items():
                 if k in traffic:
                     r["traffic"] = traffic[k]["dram_bytes_per_launch"]
-                    r["traffic_note"] = f'ncu {traffic[k]["kernel"]}, {traffic[k]["launch"]}, cold cache'
+                    r["traffic_note"] = f'ncu {traffic[k]["kernel"]}, {traffic[k]["launch"]}'
         if roofs:
             dominant = max(roofs, key=lambda k: phases[k]["ms"])
             line["roofline"] = dict(roofs[dominant], kernel=dominant)
@@ -389,8 +466,10 @@ def run_ours(args, rank, world, local_rank):
         # ---- inference, BASELINE configs[1] (fp32 as the config states; bf16 reported beside it)
         dec.eval()
         mem_i = memory[:INFER["B"]]
+        mem_ih = memory_h[:INFER["B"]].clone().pin_memory()
         infer = {"workload": f"BASELINE configs[1]: batch {INFER['B']}, {INFER['N']} tokens, {INFER['steps']} fixed "
                              "decoder steps (gate ignored)"}
+        step_weights = 18.19e6                       # parameters every decoder step touches
         for prec in ("fp32", "bf16"):
             dec.precision = prec
             for _ in range(2):
@@ -403,14 +482,40 @@ def run_ours(args, rank, world, local_rank):
             e1.record()
             torch.cuda.synchronize()
             ims = e0.elapsed_time(e1) / reps
+            # end to end: encoder memory from pinned host memory, mel frames back to the host
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                m_i, _, _ = dec.inference(mem_ih.to(dev, non_blocking=True), ignore_gate=True, max_decoder_steps=INFER["steps"])
+                mel_host = m_i.cpu()
+            e2e_ims = (time.perf_counter() - t0) * 1e3 / reps
+            wbytes = step_weights * (4.0 if prec == "fp32" else 2.0)
+            ach = wbytes / (ims * 1e-3 / INFER["steps"]) / 1e9
             infer[prec] = {"decoder_steps_per_s": INFER["steps"] / (ims * 1e-3),
-                           "mel_frames_per_s": INFER["B"] * INFER["steps"] / (ims * 1e-3), "us_per_step": 1e3 * ims / INFER["steps"]}
+                           "mel_frames_per_s": INFER["B"] * INFER["steps"] / (ims * 1e-3), "us_per_step": 1e3 * ims / INFER["steps"],
+                           "e2e": {"decoder_steps_per_s": INFER["steps"] / (e2e_ims * 1e-3), "h2d_bytes": mem_ih.numel() * 4,
+                                   "d2h_bytes": mel_host.numel() * 4},
+                           "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                                        "algorithmic_bytes_per_step": wbytes, "traffic": None,
+                                        "note": "weight streaming: every step reads all recurrent / projection weights once "
+                                                "(they do not fit on chip in one kernel); SURVEY.md 8(d)"}}
         dec.precision = args.precision
         infer["decoder_steps_per_s"] = infer["fp32"]["decoder_steps_per_s"]       # headline: the config's own precision
         line["infer"] = infer
         dec.train()
+        if world == 1 and not args.no_gpu_torch:
+            # free this arm's memory first: the eager reference keeps ~(86 KB + 1168 N) bytes per sample-step for autograd
+            del dec, opt
+            torch.cuda.empty_cache()
+            line["gpu_torch_baseline"] = torch_gpu_legs(dev)
+            t = line["gpu_torch_baseline"]
+            t["ours_over_torch"] = {"train_bf16": value / t["train_bf16_autocast"]["mel_frames_per_s"],
+                                    "train_vs_fp32_eager": value / t["train_fp32"]["mel_frames_per_s"]}
+            if "infer_fp32" in t:
+                t["ours_over_torch"]["infer_fp32"] = infer["fp32"]["decoder_steps_per_s"] / t["infer_fp32"]["decoder_steps_per_s"]
+                t["ours_over_torch"]["infer_bf16"] = infer["bf16"]["decoder_steps_per_s"] / t["infer_bf16_autocast"]["decoder_steps_per_s"]
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = {k: v for k, v in cpu_train_leg(2, 1).items() if k != "ms_per_step"}
+        line["library"] = {"path": os.path.relpath(_native.library_path(), ROOT), "fresh": bool(_native.library_is_fresh())}
         print(json.dumps(line), flush=True)
 
 
@@ -421,9 +526,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--reference-device", choices=["cpu", "cuda"], default="cpu",
-                    help="--impl reference only: 'cuda' times the same torch ops on the GPU (stock PyTorch eager path); "
-                         "the contract's reference arm is the CPU one")
+    ap.add_argument("--no-gpu-torch", action="store_true", help="skip the stock-PyTorch-on-GPU baseline legs")
     ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16",
                     help="arithmetic of the recurrent GEMMs (BASELINE configs[2] is bf16; fp32 = parity mode)")
     args = ap.parse_args()

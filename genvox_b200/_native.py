@@ -89,8 +89,15 @@ def library_path():
     return _build.LIB_PATH
 
 
+def library_is_fresh():
+    """True when the in-tree library was compiled from exactly the sources in the tree (fingerprint compiled into it)."""
+    return _build.is_fresh()
+
+
 def load():
-    """Load (building first if the in-tree .so is absent or stale and nvcc is available)."""
+    """Load (building first if the in-tree .so is absent or stale and nvcc is available).  A library that was NOT built
+    from the sources in the tree is refused - kernels of other sources under this Python layer and these struct layouts
+    would run silently - unless GVX_ALLOW_STALE_LIB=1 says that is intended."""
     global _lib
     if _lib is not None:
         return _lib
@@ -98,9 +105,12 @@ def load():
     if not _build.is_fresh():
         try:
             _build.build()
-        except Exception as exc:  # no nvcc on this box: a stale-but-present library is still usable
+        except Exception as exc:
             if not os.path.isfile(path):
                 raise RuntimeError(f"genvox_b200: CUDA library missing and could not be built: {exc}") from exc
+            if os.environ.get("GVX_ALLOW_STALE_LIB") != "1":
+                raise RuntimeError(f"genvox_b200: {path} was built from other sources and the rebuild failed ({exc}); "
+                                   "set GVX_ALLOW_STALE_LIB=1 to load it anyway") from exc
     lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)      # AttributeError here = header/library mismatch: fail loudly

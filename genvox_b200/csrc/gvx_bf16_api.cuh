@@ -456,8 +456,11 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
         }
     }
     if (pc) {   // decoder LSTM (:355-358) for all frames: time-batched input part, then the persistent recurrence
+        {
+            ProfScope ps(PS_DEC_IN_GEMM, st);
+            GVX_TRY(gemm_nt_bf16(st, T * B, 4 * d.H, d.A + d.E, XDRM, d.Kd, (const bf16 *)(packed + BL.WdRM), d.Kd, s + S.GD, 4 * d.H));
+        }
         ProfScope ps(PS_DEC_LSTM, st);
-        GVX_TRY(gemm_nt_bf16(st, T * B, 4 * d.H, d.A + d.E, XDRM, d.Kd, (const bf16 *)(packed + BL.WdRM), d.Kd, s + S.GD, 4 * d.H));
         GVX_CUDA(cudaMemsetAsync(s + S.HIMG, 0, pc_himg_elems(d.H) * sizeof(bf16), st));
         PcFwdArgs f;
         memset(&f, 0, sizeof(f));

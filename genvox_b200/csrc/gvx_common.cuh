@@ -91,12 +91,12 @@ inline unsigned long long g_launches = 0;
 
 enum ProfSlot {
     PS_SETUP = 0, PS_PRENET, PS_ATT_LSTM, PS_QUERY, PS_ATTENTION, PS_DEC_LSTM, PS_PROJ, PS_OUTPUT,
-    PS_BWD_DEC_POINT, PS_BWD_DEC_GEMM, PS_BWD_ATTENTION, PS_BWD_ATT_POINT, PS_BWD_ATT_GEMM, PS_BWD_BATCHED, PS_NSLOT
+    PS_BWD_DEC_POINT, PS_BWD_DEC_GEMM, PS_BWD_ATTENTION, PS_BWD_ATT_POINT, PS_BWD_ATT_GEMM, PS_BWD_BATCHED, PS_DEC_IN_GEMM, PS_NSLOT
 };
 inline const char *prof_slot_name(int s) {
     static const char *names[PS_NSLOT] = {"setup", "prenet", "att_lstm", "query", "attention", "dec_lstm", "proj", "output",
                                           "bwd_dec_pointwise", "bwd_dec_gemm", "bwd_attention", "bwd_att_pointwise_query",
-                                          "bwd_att_gemm", "bwd_time_batched"};
+                                          "bwd_att_gemm", "bwd_time_batched", "dec_lstm_input_gemm"};
     return (s >= 0 && s < PS_NSLOT) ? names[s] : nullptr;
 }
 struct ProfRec { int slot; cudaEvent_t a, b; };

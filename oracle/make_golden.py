@@ -76,7 +76,12 @@ def run_reference_decode_loop(dims, W, mem, lens, seed, steps, dtype):
     return m.numpy(), g.numpy(), a.numpy()
 
 
-def case_forward(tag, dims, B, N, T, wseed, iseed, dseed, training=True, with_grads=True, wscale=1.0):
+def keep_frames_of(T, head=12, stride=13, tail=12):
+    """Frames a long fixture keeps (the file stays small): the first `head`, every `stride`-th, the last `tail`."""
+    return sorted(set(range(min(head, T))) | set(range(0, T, stride)) | set(range(max(0, T - tail), T)))
+
+
+def case_forward(tag, dims, B, N, T, wseed, iseed, dseed, training=True, with_grads=True, wscale=1.0, subsample=False):
     W = synth.make_decoder_weights(wseed, dims, wscale)
     mem, mel, lens = synth.make_inputs(iseed, B, N, T, dims)
     r_mel = (synth.uniform01(iseed, 20, B * dims.n_mels * T) - 0.5).astype(np.float32).reshape(B, dims.n_mels, T)
@@ -85,15 +90,57 @@ def case_forward(tag, dims, B, N, T, wseed, iseed, dseed, training=True, with_gr
     for dtype, sfx in ((torch.float32, "f32"), (torch.float64, "f64")):
         m, g, a, grads = run_reference_forward(dims, W, mem, mel, lens, dseed, training, dtype,
                                                r_mel if with_grads else None, r_gate)
+        if subsample:       # long sequences: selected frames only (tests slice their outputs with meta["frames"])
+            fr = keep_frames_of(T)
+            m, g, a = m[:, :, fr], g[:, fr], a[:, fr]
         out[f"mel_{sfx}"], out[f"gate_{sfx}"], out[f"align_{sfx}"] = m, g, a
         if grads is not None:
             for k, v in grads.items():
-                for kk, vv in grad_digest(k, v).items():
+                for kk, vv in grad_digest(k, v, 20000 if subsample else 70000).items():
                     out[f"grad_{sfx}|{kk}"] = vv
     meta = dict(kind="forward", dims=dims.kwargs(), B=B, N=N, T=T, weight_seed=wseed, input_seed=iseed,
                 dropout_seed=dseed, training=training, weight_scale=wscale, lengths=lens.tolist(),
                 with_grads=with_grads, r_mel_stream=20, r_gate_stream=21,
                 source="reference Decoder.forward (tacotron2.py:365-388) + autograd (:520)")
+    if subsample:
+        meta["frames"] = keep_frames_of(T)
+    save(tag, meta, out)
+
+
+def case_decode_stops(tag, dims, B, N, steps, wseed, iseed, dseed, wscale=1.0, margin=2e-3):
+    """Batched decode whose rows stop at DIFFERENT steps.  The reference's public loop is B = 1 only (:405 raises for
+    B > 1), so its decode() is driven for B rows (as in case_decode_loop) and the reference stop rule of :405 - first
+    frame with sigmoid(gate) > threshold, that frame included - is applied per row to the reference's own gate logits.
+    The threshold is chosen so that the rows' stop steps differ, at least one row never fires (-> max steps, :407), and
+    every logit is at least `margin` away from the threshold (the stop steps then do not hinge on fp32 rounding)."""
+    W = synth.make_decoder_weights(wseed, dims, wscale)
+    mem, _, lens = synth.make_inputs(iseed, B, N, 0, dims)
+    out, gates = {}, {}
+    for dtype, sfx in ((torch.float32, "f32"), (torch.float64, "f64")):
+        m, g, a = run_reference_decode_loop(dims, W, mem, lens, dseed, steps, dtype)
+        out[f"mel_{sfx}"], out[f"gate_{sfx}"], out[f"align_{sfx}"] = m, g, a
+        gates[sfx] = g.astype(np.float64)
+
+    def stops(g, logit_thr):
+        fired = g > logit_thr
+        return [int(np.argmax(fired[b])) + 1 if fired[b].any() else steps for b in range(B)]
+
+    best = None
+    vals = np.unique(gates["f64"].reshape(-1))
+    for cand in 0.5 * (vals[1:] + vals[:-1]):        # every threshold between two neighbouring logits
+        if np.abs(gates["f64"] - cand).min() < margin or np.abs(gates["f32"] - cand).min() < margin:
+            continue
+        st = stops(gates["f64"], cand)
+        score = (len(set(st)), st.count(steps) >= 1, -abs(st.count(steps) - 1))
+        if st == stops(gates["f32"], cand) and min(st) >= 2 and (best is None or score > best[0]):
+            best = (score, float(cand), st)
+    assert best is not None and best[0][0] >= 3 and best[0][1], best
+    logit_thr, n_frames = best[1], best[2]
+    meta = dict(kind="decode_stops", dims=dims.kwargs(), B=B, N=N, steps=steps, weight_seed=wseed, input_seed=iseed,
+                dropout_seed=dseed, masked=True, weight_scale=wscale, lengths=lens.tolist(),
+                gate_threshold=float(1.0 / (1.0 + np.exp(-logit_thr))), gate_logit_threshold=logit_thr, n_frames=n_frames,
+                source="reference initialize_decoder_states/prenet/decode driven for B rows (tacotron2.py:303,:140,:333); "
+                       "per-row stop rule of :405 / :407 applied to the reference's gate logits")
     save(tag, meta, out)
 
 
@@ -146,6 +193,11 @@ def save(tag, meta, arrays):
 def main():
     torch.set_num_threads(8)
     D, S = synth.DecoderDims(), synth.SMALL_DIMS
+    if "--new" in sys.argv:      # only the fixtures added in round 2 (the others regenerate bit-identically)
+        if "--stops-only" not in sys.argv:
+            case_forward("fwd_default_long", D, B=4, N=60, T=400, wseed=7, iseed=19, dseed=131, subsample=True)
+        case_decode_stops("stops_default_masked", D, B=6, N=33, steps=24, wseed=8, iseed=21, dseed=132, wscale=2.0)
+        return 0
     case_forward("fwd_small_train", S, B=3, N=11, T=7, wseed=7, iseed=11, dseed=123, wscale=3.0)
     case_forward("fwd_small_eval", S, B=2, N=9, T=5, wseed=8, iseed=12, dseed=124, training=False, wscale=3.0)
     case_forward("fwd_default_train", D, B=4, N=37, T=10, wseed=7, iseed=11, dseed=123)
@@ -155,6 +207,8 @@ def main():
     case_decode_loop("loop_small_masked", S, B=4, N=13, steps=15, wseed=8, iseed=16, dseed=128, masked=True, wscale=3.0)
     case_public_inference("infer_default_b1_gate", D, N=29, wseed=7, iseed=17, dseed=129)
     case_public_inference("infer_small_b1_gate", S, N=10, wseed=8, iseed=18, dseed=130, wscale=3.0)
+    case_forward("fwd_default_long", D, B=4, N=60, T=400, wseed=7, iseed=19, dseed=131, subsample=True)
+    case_decode_stops("stops_default_masked", D, B=6, N=33, steps=24, wseed=8, iseed=21, dseed=132, wscale=2.0)
 
 
 if __name__ == "__main__":

@@ -1,8 +1,9 @@
-"""TEST INFRASTRUCTURE (build container only) — import the UNMODIFIED reference.
+"""TEST / MEASUREMENT INFRASTRUCTURE — import the UNMODIFIED reference.
 
-/root/reference does not exist on the GPU box; nothing in the `-m gpu` tests, smoke() or
-bench.py imports this module.  It is used by oracle/make_golden.py and by the CPU tests
-that are skipped when the reference tree is absent.
+In the build container the reference is imported from /root/reference (oracle/make_golden.py, the CPU tests that are
+skipped when it is absent).  /root/reference does not exist on the GPU box: there the byte-identical copy staged by
+oracle/build_ref.py under oracle/_ref (git-ignored, travels with the snapshot) is used - by bench.py's reference arm and
+baselines only; the `-m gpu` tests and smoke() never need it.
 
 The reference's import chain pulls four third-party modules that are not installed and
 that the decoder never touches: yt_dlp, matplotlib, inflect, g2p_en.
@@ -17,7 +18,10 @@ import torch
 
 from . import philox
 
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 REFERENCE_ROOT = os.environ.get("GENVOX_REFERENCE_ROOT", "/root/reference")
+if not os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "tts", "tacotron2.py")) and os.path.isdir(_STAGED):
+    REFERENCE_ROOT = _STAGED
 
 
 def reference_available() -> bool:

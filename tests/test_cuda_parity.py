@@ -166,11 +166,13 @@ def test_forward_and_bptt_match_reference_golden(cuda_device, tag):
     dec.set_dropout_seed(meta["dropout_seed"])
     m, g, a = dec(memory, torch.from_numpy(mel).to(cuda_device), torch.from_numpy(lens).to(cuda_device))
     assert m.shape == (B, dims.n_mels, T) and g.shape == (B, T) and a.shape == (B, T, N)
-    errs = {k: rel_err(v.detach().cpu(), z[f"{k}_f64"]) for k, v in (("mel", m), ("gate", g), ("align", a))}
+    fr = meta.get("frames")         # long fixtures keep selected frames only (oracle/make_golden.py: keep_frames_of)
+    ms, gs, as_ = (m, g, a) if fr is None else (m[:, :, fr], g[:, fr], a[:, fr])
+    errs = {k: rel_err(v.detach().cpu(), z[f"{k}_f64"]) for k, v in (("mel", ms), ("gate", gs), ("align", as_))}
     print(tag, "forward rel err vs fp64 reference:", errs)
     for k, e in errs.items():
         assert e < _tol(z, k + "_{p}", FWD_TOL), (k, e)
-    ok, frac = argmax_agrees(a.detach().cpu().numpy(), z["align_f64"])
+    ok, frac = argmax_agrees(as_.detach().cpu().numpy(), z["align_f64"])
     assert ok, "alignment argmax differs from the reference where its margin is clear"
     for b, L in enumerate(lens):                        # padded tokens: exactly zero weight (tacotron2.py:125)
         if L < N:
@@ -219,6 +221,33 @@ def test_batched_inference_matches_reference_decode_loop(cuda_device, tag):
         assert e < _tol(z, k + "_{p}", FWD_TOL), (k, e)
     ok, _ = argmax_agrees(a.cpu().numpy(), z["align_f64"])
     assert ok
+
+
+@pytest.mark.parametrize("tag", golden_tags("decode_stops"))
+def test_batched_inference_rows_stop_at_different_steps(cuda_device, tag):
+    """Per-row stop rule (tacotron2.py:405 / :407) on a batch whose rows fire at different steps: `last_n_frames` exact,
+    every row's frames up to its own stop step equal to the reference's."""
+    meta, z = load_golden(tag)
+    dims = synth.DecoderDims(**{**meta["dims"], "gate_threshold": meta["gate_threshold"], "max_decoder_steps": meta["steps"]})
+    W = synth.make_decoder_weights(meta["weight_seed"], dims, meta["weight_scale"])
+    mem, _, lens = synth.make_inputs(meta["input_seed"], meta["B"], meta["N"], 0, dims)
+    nf = meta["n_frames"]
+    assert len(set(nf)) >= 3 and max(nf) == meta["steps"]
+    for precision in ("fp32", "bf16"):
+        dec = make_decoder(dims, W, cuda_device, False)
+        dec.precision = precision
+        dec.set_dropout_seed(meta["dropout_seed"])
+        m, g, a = dec.inference(torch.from_numpy(mem).to(cuda_device), memory_lengths=torch.from_numpy(lens).to(cuda_device))
+        if precision == "fp32":
+            assert dec.last_n_frames.tolist() == nf                                  # stop steps exact
+        assert m.shape[2] == max(dec.last_n_frames.tolist())
+        tol = FWD_TOL if precision == "fp32" else 3e-2
+        for b, n in enumerate(nf if precision == "fp32" else dec.last_n_frames.tolist()):
+            n = min(n, nf[b])
+            for k, v in (("mel", m[b, :, :n]), ("gate", g[b, :n]), ("align", a[b, :n])):
+                ref = z[f"{k}_f64"][b][..., :n] if k != "align" else z["align_f64"][b, :n]
+                e = float(np.abs(v.cpu().numpy() - ref).max() / max(np.abs(z[f"{k}_f64"]).max(), 1e-30))
+                assert e < max(tol, _tol(z, k + "_{p}", tol)), (precision, b, k, e)
 
 
 @pytest.mark.parametrize("tag", golden_tags("public_inference"))
