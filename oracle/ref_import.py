@@ -69,8 +69,17 @@ def build_reference_decoder(dims, weights, dtype=torch.float32):
     return dec.to(dtype)
 
 
+def build_reference_model(n_tokens=64, seed=0):
+    """The reference's full Tacotron2 (tacotron2.py:416-448) with its default configs (configs/models.py, configs/__init__.py)."""
+    ref = import_reference()
+    import configs  # type: ignore
+    from configs.models import Tacotron2Config  # type: ignore
+    torch.manual_seed(seed)
+    return ref.Tacotron2(Tacotron2Config(), configs.AudioConfig(), configs.TextConfig(n_tokens=n_tokens))
+
+
 @contextlib.contextmanager
-def philox_dropout_patch(seed: int, mode: str, row_offset: int = 0):
+def philox_dropout_patch(seed: int, mode: str, row_offset: int = 0, skip: int = 0, count_inactive: bool = True):
     """Replace torch.nn.functional.dropout, while a reference Decoder method runs, by a mask
     provider that replays the shared Philox stream (oracle/philox.py).
 
@@ -78,6 +87,9 @@ def philox_dropout_patch(seed: int, mode: str, row_offset: int = 0):
                       = prenet0[all frames], prenet1[all frames], (att_t, dec_t) for t = 0..T-1
     mode "inference": call order inside Decoder.inference (:398, :341, :358)
                       = (prenet0_t, prenet1_t, att_t, dec_t) for t = 0, 1, ...
+    Around a whole Tacotron2 (whose encoder / postnet call F.dropout too): `skip` = number of leading calls that belong to the
+    encoder and pass through unchanged; `count_inactive=False` ignores calls with training=False (an eval-mode encoder in
+    front of a train-mode decoder) instead of counting them.
     """
     import torch.nn.functional as F
     orig = F.dropout
@@ -92,6 +104,11 @@ def philox_dropout_patch(seed: int, mode: str, row_offset: int = 0):
         return (philox.SITE_PRENET0, philox.SITE_PRENET1, philox.SITE_ATT, philox.SITE_DEC)[n % 4], n // 4
 
     def patched(x, p=0.5, training=True, inplace=False):
+        if not training and not count_inactive:
+            return x
+        if calls.get("skipped", 0) < skip:
+            calls["skipped"] = calls.get("skipped", 0) + 1
+            return orig(x, p, training, inplace)
         site, t = site_and_t(calls["n"])
         calls["n"] += 1
         if not training or p == 0.0:
