@@ -519,6 +519,69 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
 
 
+def run_infer_sharded(args, rank, world, local_rank):
+    """BASELINE configs[3]: 4096 synthetic utterances sharded over the GPUs of the box (contiguous shards, NO collective on the
+    data path), decoded in batches of 64 by `Decoder.inference`; gate-stopped with at most 1000 steps as the config says, and
+    - because a random-init gate fires (or never fires) on the first steps - the gate-ignored variant beside it."""
+    import torch
+    import torch.distributed as dist
+    import genvox_b200
+    from genvox_b200.training import shard_rows
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    U, Bt, steps = int(os.environ.get("GVX_BENCH_UTTERANCES", "4096")), 64, INFER["steps"]
+    lo, hi = shard_rows(U, rank, world)
+    torch.manual_seed(0)
+    dec = genvox_b200.Decoder(**decoder_dims()).to(dev).eval()
+    dec.precision = args.precision
+    g = torch.Generator().manual_seed(7)
+    lengths_all = torch.sort(torch.randint(75, 151, (U,), generator=g), descending=True).values      # token counts, longest first
+    batches = []
+    for b0 in range(lo, hi, Bt):
+        ln = lengths_all[b0:min(b0 + Bt, hi)]
+        gb = torch.Generator().manual_seed(1000 + b0)
+        mem = 0.5 * torch.randn(len(ln), int(ln.max()), 512, generator=gb)
+        for r, n in enumerate(ln.tolist()):
+            mem[r, n:] = 0
+        batches.append((mem.to(dev), ln.to(dev)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    res = {}
+    for variant, ignore in (("gate_stopped", False), ("gate_ignored", True)):
+        for mem, ln in batches[:1]:
+            dec.inference(mem, memory_lengths=ln, ignore_gate=ignore, max_decoder_steps=steps)          # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        frames = 0
+        nsteps = 0
+        for mem, ln in batches:
+            m, _, _ = dec.inference(mem, memory_lengths=ln, ignore_gate=ignore, max_decoder_steps=steps)
+            frames += int(dec.last_n_frames.sum().item())
+            nsteps += m.shape[2]
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        genvox_b200.check_device_errors()
+        t = torch.tensor([dt, float(frames), float(nsteps)], dtype=torch.float64, device=dev)
+        if world > 1:
+            tm = t.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            dt = float(tm[0].item())
+        res[variant] = {"utterances_per_s": U / dt, "mel_frames_per_s": float(t[1].item()) / dt,
+                        "decoder_steps_per_s_per_gpu": float(t[2].item()) / world / dt, "seconds": dt}
+    if rank == 0:
+        print(json.dumps({"metric": "Tacotron2 sharded batched inference", "value": res["gate_ignored"]["utterances_per_s"],
+                          "unit": "utterances/s", "n_gpus": world, "higher_is_better": True, "scaling": "strong",
+                          "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+                          "config": {"workload": f"BASELINE configs[3]: {U} synthetic utterances (75-150 tokens) sharded over {world} "
+                                                 f"GPU(s), batches of {Bt}, max {steps} decoder steps; no data-path collective"},
+                          "variants": res}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -527,6 +590,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gpu-torch", action="store_true", help="skip the stock-PyTorch-on-GPU baseline legs")
+    ap.add_argument("--mode", choices=["train", "infer_sharded"], default="train",
+                    help="train: BASELINE configs[2] (the contract's line); infer_sharded: configs[3], utterances sharded over the GPUs")
     ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16",
                     help="arithmetic of the recurrent GEMMs (BASELINE configs[2] is bf16; fp32 = parity mode)")
     args = ap.parse_args()
@@ -554,7 +619,10 @@ def main():
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.mode == "infer_sharded":
+            run_infer_sharded(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

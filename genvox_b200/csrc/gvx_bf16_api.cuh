@@ -12,6 +12,7 @@
 #include "gvx_misc.cuh"
 #include "gvx_fused_fwd.cuh"
 #include "gvx_fused_bwd.cuh"
+#include "gvx_nt_gemm.cuh"
 #include "gvx_infer_prenet.cuh"
 #include "gvx_persist.cuh"
 
@@ -49,7 +50,7 @@ inline int tc_pick_ks(int mtiles, int nkb) {
 
 // ---- bf16 part of the packed weights, appended after the fp32 PackedL block (offsets in floats) ----
 struct PackedBfL {
-    size_t WaI, WdI, WaTI, WdTI, WqI, WqTI, WpgI, WpgRM, WdRM, WdhhI, WdhhTI, WaRecI, WaPRM, WqB, WaRecTI, total;
+    size_t WaI, WdI, WaTI, WdTI, WqI, WqTI, WpgI, WpgRM, WdRM, WdhhI, WdhhTI, WaRecI, WaPRM, WqB, WaRecTI, WdTRM, WaTRM, total;
     PackedBfL(const Dims &d, size_t base) {
         const BfGeom g(d);
         Carver c;
@@ -72,6 +73,9 @@ struct PackedBfL {
         WqB = c.take(((size_t)d.D * d.A + 1) / 2);
         // persistent BPTT of the attention chain (gvx_fused_bwd.cuh): resident [ctx | h_att] columns of W_att^T
         WaRecTI = c.take(fb_wimg_elems() / 2);
+        // transposed unit-major weights as row-major bf16 ([Kd][4H], [Ka][4A]): B operands of the all-frames d X contractions
+        WdTRM = c.take(((size_t)4 * d.H * d.Kd + 1) / 2);
+        WaTRM = c.take(((size_t)4 * d.A * d.Ka + 1) / 2);
         total = c.o;
     }
 };
@@ -106,7 +110,9 @@ int pack_weights_bf16(const Dims &d, const gvx_weights *w, float *packed, cudaSt
         GVX_LAUNCHED(2);
     }
     k_to_bf16<<<grid_for((size_t)d.D * d.A), 256, 0, st>>>(w->query_w, d.A, (size_t)d.D, d.A, (bf16 *)(packed + BL.WqB), d.A);
-    GVX_LAUNCHED(1);
+    k_to_bf16<<<grid_for((size_t)4 * d.H * d.Kd), 256, 0, st>>>(packed + PL.WdT, 4 * d.H, (size_t)d.Kd, 4 * d.H, (bf16 *)(packed + BL.WdTRM), 4 * d.H);
+    k_to_bf16<<<grid_for((size_t)4 * d.A * d.Ka), 256, 0, st>>>(packed + PL.WaT, 4 * d.A, (size_t)d.Ka, 4 * d.A, (bf16 *)(packed + BL.WaTRM), 4 * d.A);
+    GVX_LAUNCHED(3);
     if (d.A == FA_A && d.E == FA_E) {
         k_fa_pack_w<<<grid_for(fa_wimg_elems()), 256, 0, st>>>(packed + PL.Wa, d.Ka, d.P, (bf16 *)(packed + BL.WaRecI));
         k_to_bf16<<<grid_for((size_t)4 * d.A * d.P), 256, 0, st>>>(packed + PL.Wa, d.Ka, (size_t)4 * d.A, d.P, (bf16 *)(packed + BL.WaPRM), d.P);
@@ -157,7 +163,9 @@ struct StashBfL {
 
 struct BwdBfL {
     size_t DOUT, DOUTB, DHC, GDI, GAI, DQI, DGDRM, DGARM, DQRM, PDXD, PDXA, PS4, DCD, DCA, DCTX, DE, DCONV, DZ2, DZ1, DPM, DW, DCUM,
-        DWA, DWD, DBIAS, PART1, PART2, ONES, TMP, COLP, ERR, GIMG, DXDALL, BAR, GIMGA, DCTXX, DQX, BARA, total;
+        DWA, DWD, DBIAS, PART1, PART2, ONES, TMP, COLP, ERR, GIMG, DXDALL, BAR, GIMGA, DCTXX, DQX, BARA, GDT, XDT, GAT, XAT, HCT, DQT, DOT, GWS, total;
+    int TBp;                           // frames rounded up to a multiple of 8: row stride of the transposed operands
+    size_t gws_floats;
     size_t pdxd_stride, pdxa_stride;   // floats per ping-pong half
     int NPAD, KSdT, KSaT, KSs4, post_blocks, colchunks;
     BwdBfL(const Dims &d, int B, int N, int T) {
@@ -196,6 +204,13 @@ struct BwdBfL {
         DCTXX = c.take(2 * fb_dctxx_words());      // 64-bit (value, tag) words
         DQX = c.take(2 * fb_dqx_words());
         BARA = c.take(32 * 4);
+        // frame-major operands transposed for the weight-gradient contractions (K = frames must be the contiguous axis)
+        TBp = (T * B + 7) & ~7;
+        GDT = c.take((size_t)4 * d.H * TBp / 2); XDT = c.take((size_t)d.Kd * TBp / 2);
+        GAT = c.take((size_t)4 * d.A * TBp / 2); XAT = c.take((size_t)d.Ka * TBp / 2);
+        HCT = c.take((size_t)d.Kp * TBp / 2); DQT = c.take((size_t)d.D * TBp / 2); DOT = c.take((size_t)d.OL * TBp / 2);
+        gws_floats = (size_t)4 << 20;
+        GWS = c.take(gws_floats);              // split-K partial tiles of the small weight gradients
         total = c.o;
     }
 };
@@ -317,6 +332,22 @@ inline int gemm_nn_bf16(cudaStream_t st, int M, int N, int K, const bf16 *A, int
     return 0;
 }
 
+// The all-frames contractions run on the own tcgen05 GEMM (gvx_nt_gemm.cuh).  GVX_OWN_GEMM=0 sends them to cuBLAS instead
+// (comparison runs only).
+inline bool own_gemm() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("GVX_OWN_GEMM");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+// C[M,N] = A[M,K] . W[N,K]^T
+inline int gemm_nt(cudaStream_t st, int M, int N, int K, const bf16 *A, int lda, const bf16 *Wm, int ldw, float *Cm, int ldc, int *err) {
+    if (own_gemm() && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0) return nt_gemm_bf16(st, M, N, K, A, lda, Wm, ldw, Cm, ldc, err);
+    return gemm_nt_bf16(st, M, N, K, A, lda, Wm, ldw, Cm, ldc);
+}
+
 __global__ void k_add_bias_rows(float *x, size_t rows, int cols, int ld, const float *__restrict__ bias) {
     const size_t total = rows * cols;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -385,7 +416,7 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     if (fa) {
         {   // prenet part of the attention-LSTM gate pre-activations for all frames (tacotron2.py:338-340)
             ProfScope ps(PS_ATT_LSTM, st);
-            GVX_TRY(gemm_nt_bf16(st, T * B, 4 * d.A, d.P, XARM, d.Ka, (const bf16 *)(packed + BL.WaPRM), d.P, s + S.GA, 4 * d.A));
+            GVX_TRY(gemm_nt(st, T * B, 4 * d.A, d.P, XARM, d.Ka, (const bf16 *)(packed + BL.WaPRM), d.P, s + S.GA, 4 * d.A, err));
         }
         ProfScope ps(PS_ATTENTION, st);
         FaArgs f;
@@ -458,7 +489,7 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     if (pc) {   // decoder LSTM (:355-358) for all frames: time-batched input part, then the persistent recurrence
         {
             ProfScope ps(PS_DEC_IN_GEMM, st);
-            GVX_TRY(gemm_nt_bf16(st, T * B, 4 * d.H, d.A + d.E, XDRM, d.Kd, (const bf16 *)(packed + BL.WdRM), d.Kd, s + S.GD, 4 * d.H));
+            GVX_TRY(gemm_nt(st, T * B, 4 * d.H, d.A + d.E, XDRM, d.Kd, (const bf16 *)(packed + BL.WdRM), d.Kd, s + S.GD, 4 * d.H, err));
         }
         ProfScope ps(PS_DEC_LSTM, st);
         GVX_CUDA(cudaMemsetAsync(s + S.HIMG, 0, pc_himg_elems(d.H) * sizeof(bf16), st));
@@ -477,7 +508,7 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     }
     ProfScope ps_out(PS_OUTPUT, st);
     // mel / gate projections for all frames (:360-362): [T*B, H+E] bf16 . Wpg^T
-    GVX_TRY(gemm_nt_bf16(st, T * B, d.M + 1, d.Kp, HCRM, d.Kp, (const bf16 *)(packed + BL.WpgRM), d.Kp, s + S.OUT, d.OL));
+    GVX_TRY(gemm_nt(st, T * B, d.M + 1, d.Kp, HCRM, d.Kp, (const bf16 *)(packed + BL.WpgRM), d.Kp, s + S.OUT, d.OL, err));
     k_add_bias_rows<<<grid_for((size_t)T * B * (d.M + 1)), 256, 0, st>>>(s + S.OUT, (size_t)T * B, d.M + 1, d.OL, packed + PL.bpg);
     GVX_LAUNCHED(1);
     k_unpack_out<<<grid_for((size_t)B * (d.M + 1) * T), 256, 0, st>>>(s + S.OUT, B, d.M, d.OL, T, T, mel_out, gate_out);
@@ -598,7 +629,8 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
         }
         {   // d [h_att_t | ctx_t] from the decoder-LSTM input, all frames: d gates_dec . W_ih
             ProfScope ps(PS_BWD_DEC_GEMM, st);
-            GVX_TRY(gemm_nn_bf16(st, TB, AE, 4 * d.H, DGDRM, 4 * d.H, (const bf16 *)(packed + BL.WdRM), d.Kd, x + W.DXDALL, AE));
+            if (own_gemm()) GVX_TRY(nt_gemm_bf16(st, TB, AE, 4 * d.H, DGDRM, 4 * d.H, (const bf16 *)(packed + BL.WdTRM), 4 * d.H, x + W.DXDALL, AE, err));
+            else GVX_TRY(gemm_nn_bf16(st, TB, AE, 4 * d.H, DGDRM, 4 * d.H, (const bf16 *)(packed + BL.WdRM), d.Kd, x + W.DXDALL, AE));
         }
     }
 
@@ -708,7 +740,8 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     }
     ProfScope ps_batched(PS_BWD_BATCHED, st);
     if (fb) {   // prenet columns of d x_att for all frames: d gates_att . W_ih[:, prenet], then the relu / dropout mask (:143)
-        GVX_TRY(gemm_nn_bf16(st, TB, d.P, 4 * d.A, DGARM, 4 * d.A, (const bf16 *)(packed + BL.WaPRM), d.P, x + W.DZ1, d.P));
+        if (own_gemm()) GVX_TRY(nt_gemm_bf16(st, TB, d.P, 4 * d.A, DGARM, 4 * d.A, (const bf16 *)(packed + BL.WaTRM), 4 * d.A, x + W.DZ1, d.P, err));
+        else GVX_TRY(gemm_nn_bf16(st, TB, d.P, 4 * d.A, DGARM, 4 * d.A, (const bf16 *)(packed + BL.WaPRM), d.P, x + W.DZ1, d.P));
         k_prenet_bwd_mask<<<grid_for((size_t)TB * d.P), 256, 0, st>>>(x + W.DZ1, d.P, s + S.PRE2, TB, d.P, x + W.DZ2);
         GVX_LAUNCHED(1);
         GVX_CUDA(cudaGetLastError());
@@ -725,7 +758,27 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     }
     // projections: d Wpg = DOUT^T . [h_dec | ctx];  biases = column sums
     float *tmp = x + W.TMP;
-    GVX_TRY(gemm_tn_bf16(st, d.M + 1, d.Kp, TB, DOUTB, d.OL, HCRM, d.Kp, tmp, d.Kp));
+    // weight gradients: d W = G^T . X over all frames.  Own GEMM: both operands transposed first so that the frame axis is the
+    // contiguous K axis (k_transpose_bf16, HBM-bound), small outputs split over K (deterministic reduction)
+    const int TBp = W.TBp;
+    bf16 *GDT = (bf16 *)(x + W.GDT), *XDT = (bf16 *)(x + W.XDT), *GAT = (bf16 *)(x + W.GAT), *XAT = (bf16 *)(x + W.XAT),
+         *HCT = (bf16 *)(x + W.HCT), *DQT = (bf16 *)(x + W.DQT), *DOT = (bf16 *)(x + W.DOT);
+    const bool og = own_gemm();
+    if (og) {
+        if (TBp != TB) {      // K padding columns must be finite (zero) in both operands
+            GVX_CUDA(cudaMemsetAsync(GDT, 0, ((size_t)(W.GWS - W.GDT)) * sizeof(float), st));
+        }
+        GVX_TRY(transpose_bf16(st, DGDRM, TB, 4 * d.H, 4 * d.H, GDT, TBp));
+        GVX_TRY(transpose_bf16(st, XDRM, TB, d.Kd, d.Kd, XDT, TBp));
+        GVX_TRY(transpose_bf16(st, DGARM, TB, 4 * d.A, 4 * d.A, GAT, TBp));
+        GVX_TRY(transpose_bf16(st, XARM, TB, d.Ka, d.Ka, XAT, TBp));
+        GVX_TRY(transpose_bf16(st, HCRM, TB, d.Kp, d.Kp, HCT, TBp));
+        GVX_TRY(transpose_bf16(st, DQRM, TB, d.D, d.D, DQT, TBp));
+        GVX_TRY(transpose_bf16(st, DOUTB, TB, d.OL, d.OL, DOT, TBp));
+        GVX_TRY(nt_gemm_bf16(st, d.M + 1, d.Kp, TBp, DOT, TBp, HCT, TBp, tmp, d.Kp, err, x + W.GWS, W.gws_floats));
+    } else {
+        GVX_TRY(gemm_tn_bf16(st, d.M + 1, d.Kp, TB, DOUTB, d.OL, HCRM, d.Kp, tmp, d.Kp));
+    }
     GVX_CUDA(cudaMemcpyAsync(g->proj_w, tmp, (size_t)d.M * d.Kp * sizeof(float), cudaMemcpyDeviceToDevice, st));
     GVX_CUDA(cudaMemcpyAsync(g->gate_w, tmp + (size_t)d.M * d.Kp, (size_t)d.Kp * sizeof(float), cudaMemcpyDeviceToDevice, st));
     GVX_TRY(colsum(st, x + W.DOUT, TB, d.M + 1, d.OL, x + W.ONES, x + W.DBIAS));
@@ -741,13 +794,15 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
         GVX_CUDA(cudaGetLastError());
         return 0;
     };
-    GVX_TRY(gemm_tn_bf16(st, 4 * d.H, d.Kd, TB, DGDRM, 4 * d.H, XDRM, d.Kd, x + W.DWD, d.Kd));
+    if (og) GVX_TRY(nt_gemm_bf16(st, 4 * d.H, d.Kd, TBp, GDT, TBp, XDT, TBp, x + W.DWD, d.Kd, err, x + W.GWS, W.gws_floats));
+    else GVX_TRY(gemm_tn_bf16(st, 4 * d.H, d.Kd, TB, DGDRM, 4 * d.H, XDRM, d.Kd, x + W.DWD, d.Kd));
     k_unpack_lstm_grad<<<grid_for((size_t)4 * d.H * d.Kd), 256, 0, st>>>(x + W.DWD, d.H, d.A + d.E, g->dec_w_ih, g->dec_w_hh);
     GVX_LAUNCHED(1);
     GVX_TRY(colsum_bf(DGDRM, 4 * d.H, x + W.DBIAS));
     k_unpack_bias_grad<<<grid_for((size_t)4 * d.H), 256, 0, st>>>(x + W.DBIAS, d.H, g->dec_b_ih, g->dec_b_hh);
     GVX_LAUNCHED(1);
-    GVX_TRY(gemm_tn_bf16(st, 4 * d.A, d.Ka, TB, DGARM, 4 * d.A, XARM, d.Ka, x + W.DWA, d.Ka));
+    if (og) GVX_TRY(nt_gemm_bf16(st, 4 * d.A, d.Ka, TBp, GAT, TBp, XAT, TBp, x + W.DWA, d.Ka, err, x + W.GWS, W.gws_floats));
+    else GVX_TRY(gemm_tn_bf16(st, 4 * d.A, d.Ka, TB, DGARM, 4 * d.A, XARM, d.Ka, x + W.DWA, d.Ka));
     k_unpack_lstm_grad<<<grid_for((size_t)4 * d.A * d.Ka), 256, 0, st>>>(x + W.DWA, d.A, d.P + d.E, g->att_w_ih, g->att_w_hh);
     GVX_LAUNCHED(1);
     GVX_TRY(colsum_bf(DGARM, 4 * d.A, x + W.DBIAS));
@@ -755,7 +810,8 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     // query layer: d Wq [D, A] = DQ^T . h_att   (h_att_t = first A columns of the decoder-LSTM input rows)
-    GVX_TRY(gemm_tn_bf16(st, d.D, d.A, TB, DQRM, d.D, XDRM, d.Kd, g->query_w, d.A));
+    if (og) GVX_TRY(nt_gemm_bf16(st, d.D, d.A, TBp, DQT, TBp, XDT, TBp, g->query_w, d.A, err, x + W.GWS, W.gws_floats));
+    else GVX_TRY(gemm_tn_bf16(st, d.D, d.A, TB, DQRM, d.D, XDRM, d.Kd, g->query_w, d.A));
 
     BwdPostArgs pa;
     pa.TH = s + S.TH; pa.DE = x + W.DE; pa.CONVS = s + S.CONVS; pa.DCONV = x + W.DCONV; pa.ALIGN = s + S.ALIGN;
@@ -908,6 +964,68 @@ extern "C" int gvx_debug_option(const char *name, int value) {
 extern "C" int gvx_debug_timeline(void *device_buffer) {
     gvx::pc_dbg_buffer() = (long long *)device_buffer;
     return 0;
+}
+
+// ---- test hook: the tcgen05 NT GEMM (+ transpose) on its own: C[M,N] = A[M,K] . B[N,K]^T, or with mode 1 A given as [K,M] and
+// B as [K,N] (both transposed on the device first, the weight-gradient path).  fp32 in, rounded to bf16 on the device.
+extern "C" int gvx_test_nt_gemm(const float *A, const float *B, int M, int N, int K, int mode, float *C, void *stream) {
+    using namespace gvx;
+    GVX_CHECK(A && B && C && M > 0 && N > 0 && K > 0 && K % 8 == 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    bf16 *a = nullptr, *b = nullptr, *at = nullptr, *bt = nullptr;
+    int *err = nullptr;
+    GVX_CUDA(cudaMalloc(&a, (size_t)M * K * 2));
+    GVX_CUDA(cudaMalloc(&b, (size_t)N * K * 2));
+    GVX_CUDA(cudaMalloc(&err, 64));
+    GVX_CUDA(cudaMemsetAsync(err, 0, 64, st));
+    int rc = 0;
+    if (mode == 0) {
+        k_to_bf16<<<grid_for((size_t)M * K), 256, 0, st>>>(A, K, (size_t)M, K, a, K);
+        k_to_bf16<<<grid_for((size_t)N * K), 256, 0, st>>>(B, K, (size_t)N, K, b, K);
+        rc = nt_gemm_bf16(st, M, N, K, a, K, b, K, C, N, err);
+    } else {
+        GVX_CHECK(M % 8 == 0 && N % 8 == 0, "mode 1 needs M, N multiples of 8");
+        GVX_CUDA(cudaMalloc(&at, (size_t)M * K * 2));
+        GVX_CUDA(cudaMalloc(&bt, (size_t)N * K * 2));
+        k_to_bf16<<<grid_for((size_t)M * K), 256, 0, st>>>(A, M, (size_t)K, M, a, M);        // A given as [K, M]
+        k_to_bf16<<<grid_for((size_t)N * K), 256, 0, st>>>(B, N, (size_t)K, N, b, N);        // B given as [K, N]
+        rc = transpose_bf16(st, a, K, M, M, at, K);
+        if (!rc) rc = transpose_bf16(st, b, K, N, N, bt, K);
+        if (!rc) rc = nt_gemm_bf16(st, M, N, K, at, K, bt, K, C, N, err);
+    }
+    if (!rc) rc = check_tc_err(err, st, "nt_gemm");
+    else cudaStreamSynchronize(st);
+    cudaFree(a); cudaFree(b); cudaFree(at); cudaFree(bt); cudaFree(err);
+    return rc;
+}
+
+// ---- timing hook for profiles/nt_gemm_bench.py: average device time of `reps` launches on zero-filled operands
+extern "C" int gvx_bench_nt_gemm(int M, int N, int K, int reps, float *ms_out) {
+    using namespace gvx;
+    bf16 *a = nullptr, *b = nullptr;
+    float *c = nullptr;
+    int *err = nullptr;
+    GVX_CUDA(cudaMalloc(&a, (size_t)M * K * 2));
+    GVX_CUDA(cudaMalloc(&b, (size_t)N * K * 2));
+    GVX_CUDA(cudaMalloc(&c, (size_t)M * N * 4));
+    GVX_CUDA(cudaMalloc(&err, 64));
+    GVX_CUDA(cudaMemset(a, 0, (size_t)M * K * 2));
+    GVX_CUDA(cudaMemset(b, 0, (size_t)N * K * 2));
+    GVX_CUDA(cudaMemset(err, 0, 64));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int rc = nt_gemm_bf16(0, M, N, K, a, K, b, K, c, N, err);
+    cudaEventRecord(e0, 0);
+    for (int i = 0; i < reps && !rc; ++i) rc = nt_gemm_bf16(0, M, N, K, a, K, b, K, c, N, err);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out = ms / (reps > 0 ? reps : 1);
+    if (!rc) rc = check_tc_err(err, 0, "nt_gemm bench");
+    cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(err);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
 }
 
 // ---- test hook: the persistent LSTM chain on its own (forward, then optionally BPTT) -----------------------------

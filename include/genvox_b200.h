@@ -173,6 +173,14 @@ int gvx_dec_infer(const gvx_dims *d, const gvx_weights *w, const void *packed,
  * operands rounded to bf16, fp32 accumulation, the K range split over KS CTAs (test hook; allocates). */
 int gvx_test_tc_gemm(const float *W, const float *X, int B, int Mtot, int K, int KS, float *out, void *stream);
 
+/* Test hook: the tcgen05 GEMM of the time-batched contractions (csrc/gvx_nt_gemm.cuh) on its own.  Replaces nothing in the
+ * reference by itself: it is the engine behind every all-frames nn.Linear / nn.LSTMCell contraction and their autograd weight
+ * gradients (tacotron2.py:340,:357,:361-362,:520).  mode 0: C[M,N] = A[M,K] . B[N,K]^T; mode 1: A is [K,M], B is [K,N] (transposed on
+ * the device first: the weight-gradient path, K = frames).  fp32 device pointers, operands rounded to bf16, fp32 accumulate. */
+int gvx_test_nt_gemm(const float *A, const float *B, int M, int N, int K, int mode, float *C, void *stream);
+/* Timing hook (profiles/nt_gemm_bench.py): average device time in ms of `reps` launches of that GEMM on zero-filled operands. */
+int gvx_bench_nt_gemm(int M, int N, int K, int reps, float *ms_out);
+
 /* The persistent LSTM-chain kernels on their own (test hook; allocates): for t < T
  *   gates_t = pre_t + h_{t-1} . W_hh^T (h, W_hh rounded to bf16, fp32 accumulate), nn.LSTMCell pointwise part
  *   (tacotron2.py:357), carried-state dropout (:358, Philox site 3), h_{-1} = c_{-1} = 0.
