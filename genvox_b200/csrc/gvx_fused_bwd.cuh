@@ -152,8 +152,15 @@ __device__ __forceinline__ void st_async_f32x2(uint32_t caddr, float v0, float v
 // with the TMA ring's full / empty barriers slow the single-thread TMA and MMA loops down), the result is broadcast
 __device__ __forceinline__ bool fb_wait_warp(uint64_t *bar, uint32_t parity, volatile int *dead, int *err, int code) {
     int ok = 1;
-    if ((threadIdx.x & 31) == 0) ok = fa_wait_mbar(bar, parity, dead, err, code) ? 1 : 0;
-    return __shfl_sync(0xffffffffu, ok, 0) != 0;
+    if ((threadIdx.x & 31) == 0) ok = fa_wait_cluster(bar, parity, dead, err, code) ? 1 : 0;
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    // Every lane then performs its OWN acquire on the (already completed) phase: data written by st.async pushes / TMA is only
+    // guaranteed visible to threads that have observed the barrier themselves - a lane that merely learns of the completion
+    // through a shuffle read stale shared memory in the forward chain (seen as run-dependent wrong results).
+    if (ok) {
+        while (!mbar_try_wait_cluster(bar, parity)) {}
+    }
+    return ok != 0;
 }
 // lstm_bwd_point (gvx_gemm.cuh) with the SFU tanh the fused forward chain used for h = o * tanh(c)
 __device__ __forceinline__ float4 fb_lstm_bwd_point(float dh_dropped, float mult, float4 ga, float c_prev, float c_new, float dc_in,

@@ -62,7 +62,7 @@ struct FaShared {
 };
 
 struct FaSmem {      // byte offsets from the 1 KB aligned base
-    int ring, wsm, lp, convT, wldT, wlc, ctxp, wcat, e, p, v, qfull, qred, xch, sh, total;
+    int ring, wsm, lp, convT, wldT, wlc, ctxp, wcat, e, p, v, qfull, qred, xch, inbox, gt, sh, total;
     __host__ __device__ explicit FaSmem(int N) {
         const FaGeom g(N);
         int o = 0;
@@ -81,6 +81,8 @@ struct FaSmem {      // byte offsets from the 1 KB aligned base
         qfull = take(AF_D * 4);
         qred = take(8 * 4 * 16 * 4);
         xch = take(64);
+        inbox = take((2 + 16 + FA_E / 2) * 4);   // pushed by the peer CTA of the row: [0..1] max / sum, [2..17] 15 halo weights, [18..] its half of the context partial
+        gt = take(PC_ROWS * 36 * 4);             // [64 rows][36] gate pre-activations: the LSTM epilogue re-maps its threads through it
         sh = take((int)sizeof(FaShared));
         total = o + 1024;
     }
@@ -138,6 +140,15 @@ __device__ __forceinline__ float ld_cluster_f32(uint32_t caddr) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t caddr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
+}
+// push into the peer CTA's shared memory, the bytes counted on the peer's mbarrier (complete_tx): no release fence (a
+// release-arrive at cluster scope compiles to MEMBAR.ALL.GPU), no acquire.cluster wait (CCTL.IVALL) on the other side
+__device__ __forceinline__ void fa_st_async(uint32_t caddr, float v, uint32_t cmbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(caddr), "f"(v), "r"(cmbar) : "memory");
+}
+__device__ __forceinline__ void fa_st_async2(uint32_t caddr, float v0, float v1, uint32_t cmbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(caddr), "f"(v0), "f"(v1), "r"(cmbar)
+                 : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
@@ -231,7 +242,7 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
     float *part = lp;        // [7][512] partial contexts: lp is dead between the energies and the next location phase
     float *wcat = (float *)(smem + L.wcat), *es = (float *)(smem + L.e), *ps = (float *)(smem + L.p);
     float *vs = (float *)(smem + L.v), *qfull = (float *)(smem + L.qfull), *qred = (float *)(smem + L.qred);
-    float *xch = (float *)(smem + L.xch);
+    float *xch = (float *)(smem + L.xch), *inbox = (float *)(smem + L.inbox), *gt = (float *)(smem + L.gt);
     FaShared *sh = (FaShared *)(smem + L.sh);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, j = blockIdx.x;
@@ -336,8 +347,13 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
     } else {
         // ================================================================ workers
         const bool epi = (warp & 2) == 0;                  // warps 0,1,4,5,8,9,12,13: LSTM epilogue
-        // ---- LSTM epilogue state: one batch row, two hidden units per thread
-        const int eb = (warp & 1) * 32 + lane, cq = warp >> 2;
+        // ---- LSTM epilogue state: one batch row, two hidden units per thread.  TMEM hands the accumulator out with a row per lane
+        // (row tr = lane of quadrant warp & 1, column quarter tcq); the cell itself runs with thread = (row eb, unit pair cq),
+        // unit pair fastest, after one trip of the [64 x 32] tile through shared memory: with a row per lane every global
+        // access of the cell touched 32 different lines per instruction
+        const int tr = (warp & 1) * 32 + lane, tcq = warp >> 2;
+        const int eidx = ((warp >> 2) * 2 + (warp & 1)) * 32 + lane;       // 0 .. 255 over the 8 epilogue warps
+        const int eb = eidx >> 2, cq = eidx & 3;
         const bool evalid = epi && eb < B;
         const int u0 = 8 * j + 2 * cq;
         float cst[2] = {0.f, 0.f};
@@ -346,7 +362,7 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
 #pragma unroll
             for (int i = 0; i < 2; ++i) bi[i] = *reinterpret_cast<const float4 *>(a.bias + 4 * (u0 + i));
         }
-        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 1) * 32) << 16) + (uint32_t)(8 * cq);
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 1) * 32) << 16) + (uint32_t)(8 * tcq);
         const size_t himg_off = (size_t)(j >> 3) * PC_CHUNK_BYTES + eb * 128 + (((j & 7) ^ (eb & 7)) << 4) + 4 * cq;
 
         // ---- query projection: warps widx 0..7 hold W_q[16 rank .. +16][128 widx .. +128] as mma.sync B fragments
@@ -364,10 +380,9 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
         }
         const int qrow = min(4 * grp8 + g4, B - 1);         // batch row whose h_att feeds A-fragment row g4 (g4 < 4)
         const float4 v4 = *reinterpret_cast<const float4 *>(vs + lane * 4);
-        const uint32_t peer_xch = mapa_u32(smem_u32(xch), (uint32_t)peer);
-        const uint32_t peer_ps = mapa_u32(smem_u32(ps), (uint32_t)peer);
-        const uint32_t peer_ctxp = mapa_u32(smem_u32(ctxp), (uint32_t)peer);
+        const uint32_t peer_inbox = mapa_u32(smem_u32(inbox), (uint32_t)peer);
         const uint32_t peer_sbar = mapa_u32(smem_u32(&sh->sbar), (uint32_t)peer);
+        constexpr uint32_t kInboxBytes = (2 + AF_PAD + FA_E / 2) * 4;
         for (int t = 0; t < T; ++t) {
             // ============================================================ location features of step t (w_{t-1}, cum_{t-1})
             for (int task = wtid; task < AF_F * G.nblk; task += FA_NW) {
@@ -454,6 +469,16 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                     tc_fence_after();
                     tmem_ld8(taddr, acc);
                     tc_fence_before();
+                    float4 *gd = reinterpret_cast<float4 *>(gt + tr * 36 + 8 * tcq);
+                    gd[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    gd[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                {
+                    const float4 *gs4 = reinterpret_cast<const float4 *>(gt + eb * 36 + 8 * cq);
+                    const float4 x0 = gs4[0], x1 = gs4[1];
+                    acc[0] = x0.x; acc[1] = x0.y; acc[2] = x0.z; acc[3] = x0.w;
+                    acc[4] = x1.x; acc[5] = x1.y; acc[6] = x1.z; acc[7] = x1.w;
                 }
                 float4 ga[2];
                 uint32_t hp = 0u;
@@ -637,12 +662,34 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                           ((part[4 * FA_E + e] + part[5 * FA_E + e]) + part[6 * FA_E + e]);
             fa_bar_workers();
             if (tid == 0) pc_stamp(a.dbg, j, t, 15);
-            if (tid == 0) mbar_arrive_cluster(peer_sbar);    // release: this CTA's max / sum / exp / partial context are complete
-            fa_wait_cluster(&sh->sbar, (uint32_t)t & 1u, &sh->dead, a.err, 39);
+            // ---- exchange with the peer CTA of the row: each side PUSHES what the other needs (local max / sum, the 15 halo
+            // exponentials next to the peer's token range, the peer's half of the context partial) and waits for its own inbox
+            if (tid == 0) mbar_expect_tx(&sh->sbar, kInboxBytes);
+            if (wtid < 2) fa_st_async(peer_inbox + 4 * wtid, xch[wtid], peer_sbar);
+            else if (wtid >= 32 && wtid < 32 + AF_PAD) {
+                // the peer reads MY tokens next to its range: half 0 sends its last 15 tokens, half 1 its first 15
+                const int h = wtid - 32, ml = half == 0 ? G.NH - AF_PAD + h : h;
+                fa_st_async(peer_inbox + 4 * (2 + h), (ml >= 0 && ml < n_own) ? ps[ml] : 0.f, peer_sbar);
+            } else if (wtid >= 64 && wtid < 64 + FA_E / 4) {
+                const int k2 = wtid - 64;                    // float2 index inside the peer's half of the columns (two scalar pushes:
+                                                             // the .v2 form of st.async delivered wrong data here)
+                const float2 v2 = *reinterpret_cast<const float2 *>(ctxp + peer * (FA_E / 2) + 2 * k2);
+                fa_st_async(peer_inbox + 4 * (2 + 16 + 2 * k2), v2.x, peer_sbar);
+                fa_st_async(peer_inbox + 4 * (2 + 16 + 2 * k2 + 1), v2.y, peer_sbar);
+            }
+            {   // lane 0 of every warp spins; then EVERY lane acquires the completed phase itself: st.async data is only guaranteed
+                // visible to threads that observed the barrier (lanes that learned of it through a shuffle read stale values)
+                int okx = 1;
+                if (lane == 0) okx = fa_wait_cluster(&sh->sbar, (uint32_t)t & 1u, &sh->dead, a.err, 39) ? 1 : 0;
+                okx = __shfl_sync(0xffffffffu, okx, 0);
+                if (okx) {
+                    while (!mbar_try_wait_cluster(&sh->sbar, (uint32_t)t & 1u)) {}
+                }
+            }
             if (tid == 0) { pc_stamp(a.dbg, j, t, 6); fa_mark(a.prog, 0, j, 8 * t + 4); }
             {   // combine the two halves of the row (always "half 0 + half 1": both CTAs get identical values)
                 const float m_s = xch[0], s_s = xch[1];
-                const float m_p = ld_cluster_f32(peer_xch), s_p = ld_cluster_f32(peer_xch + 4);
+                const float m_p = inbox[0], s_p = inbox[1];
                 const float M = fmaxf(m_s, m_p);
                 const float a_s = m_s == -INFINITY ? 0.f : expf(m_s - M), a_p = m_p == -INFINITY ? 0.f : expf(m_p - M);
                 const float S = half == 0 ? s_s * a_s + s_p * a_p : s_p * a_p + s_s * a_s;
@@ -663,7 +710,7 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                     const int ng = half == 0 ? G.NH + h : pl;                        // global token
                     const int wi = half == 0 ? AF_PAD + G.NH + h : h;                // wcat index
                     if (ng >= 0 && ng < N) {
-                        const float w = ld_cluster_f32(peer_ps + 4 * pl) * a_p / S;
+                        const float w = inbox[2 + h] * a_p / S;
                         wcat[wi] = w;
                         wcat[G.NPS + wi] += w;
                     }
@@ -672,7 +719,7 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                     const int e0 = half * (FA_E / 2) + 8 * (wtid - 128);
                     float oth[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) oth[k] = ld_cluster_f32(peer_ctxp + 4 * (e0 + k));
+                    for (int k = 0; k < 8; ++k) oth[k] = inbox[2 + 16 + 8 * (wtid - 128) + k];
                     uint32_t pk[4];
                     float cxs[8];
 #pragma unroll

@@ -214,50 +214,54 @@ __global__ void __launch_bounds__(PCF64_THREADS, 1) k_lstm_chain_fwd(const PcFwd
         }
         __syncwarp();
     } else {
-        // ------------------------------------------------ epilogue: one thread (lower half-warp) = one batch row, 2 hidden units
-        const int b = (warp & 3) * 16 + (lane & 15), cq = warp >> 2;
-        const bool valid = lane < 16 && b < a.B;
-        const int u0 = 8 * j + 2 * cq;
-        float c[2];
-        float4 bi[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            c[i] = valid ? a.c_stash[(size_t)b * H + u0 + i] : 0.f;
-            bi[i] = a.bias ? *reinterpret_cast<const float4 *>(a.bias + 4 * (u0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        // ------------------------------------------------ epilogue.  TMEM hands the accumulator out with one batch row per lane
+        // (M = 64: rows 16 q .. 16 q + 15 in the lower half-warps of quadrant q), but with a row per lane every global access of
+        // the cell (pre-activations, gate / cell stashes, outputs) touches 32 different lines per instruction.  The [64 x 32] tile
+        // goes through shared memory once and the cell runs with thread = (row, unit), unit fastest: 8 consecutive lanes then
+        // read / write one contiguous run of a row.
+        float *gt = (float *)(((uintptr_t)(sh + 1) + 15) & ~(uintptr_t)15);     // [64 rows][36]: pre-activations of the 8 units x 4 gates
+        const int e = threadIdx.x;                         // 0 .. 511
+        const int b = e >> 3, uk = e & 7, u = 8 * j + uk;
+        const bool valid = b < a.B;
+        const int qrow = (warp & 3) * 16 + (lane & 15), cq = warp >> 2;       // TMEM side: row / column quarter of this thread
+        float c = valid ? a.c_stash[(size_t)b * H + u] : 0.f;
+        const float4 bi = a.bias ? *reinterpret_cast<const float4 *>(a.bias + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(8 * cq);
-        // 4-byte slot of this thread inside the 16-byte chunk (units 8j..8j+7 of row b) of the swizzled h image
-        const size_t himg_off = (size_t)(j >> 3) * PC_CHUNK_BYTES + b * 128 + (((j & 7) ^ (b & 7)) << 4) + 4 * cq;
+        // 2-byte slot of (row b, unit u) inside the 16-byte chunk (units 8j..8j+7 of row b) of the swizzled h image
+        const size_t himg_off = (size_t)(j >> 3) * PC_CHUNK_BYTES + b * 128 + (((j & 7) ^ (b & 7)) << 4) + 2 * uk;
         bool ok = true;
         for (int t = 0; t < T; ++t) {
-            float4 pr[2];
-            if (valid) {
-                const float4 *pp = reinterpret_cast<const float4 *>(a.pre + ((size_t)t * a.B + b) * 4 * H + 4 * u0);
-                pr[0] = __ldcs(pp);
-                pr[1] = __ldcs(pp + 1);
-            }
+            float4 pr = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) pr = __ldcs(reinterpret_cast<const float4 *>(a.pre + ((size_t)t * a.B + b) * 4 * H + 4 * u));
             if (ok) ok = __all_sync(0xffffffffu, pc_mbar_wait(&sh->tmem_full, (uint32_t)t & 1u, &sh->dead, a.err, 15)) != 0;
             if (threadIdx.x == 0) pc_stamp(a.dbg, j, t, 3);
-            float acc[8];
             if (ok) {
+                float acc[8];
                 tc_fence_after();
                 tmem_ld8(taddr, acc);
                 tc_fence_before();
-            }
-            float4 ga[2];
-            uint32_t hp = 0u;
-            if (ok && valid) {
-                float hv[2];
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const float gi = sigmoidf_(acc[4 * i] + pr[i].x + bi[i].x), gf = sigmoidf_(acc[4 * i + 1] + pr[i].y + bi[i].y);
-                    const float gg = tanhf(acc[4 * i + 2] + pr[i].z + bi[i].z), go = sigmoidf_(acc[4 * i + 3] + pr[i].w + bi[i].w);
-                    const float cn = gf * c[i] + gi * gg;
-                    c[i] = cn;
-                    hv[i] = go * tanhf(cn) * drop_mult(a.drop, a.site, (uint32_t)t, (uint32_t)(b + a.row_offset), (uint32_t)(u0 + i));
-                    ga[i] = make_float4(gi, gf, gg, go);
+                if (lane < 16) {
+                    float4 *dst = reinterpret_cast<float4 *>(gt + qrow * 36 + 8 * cq);
+                    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
                 }
-                hp = pack_bf2(hv[0], hv[1]);
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            float4 ga = make_float4(0.f, 0.f, 0.f, 0.f);
+            float hv = 0.f;
+            if (ok && valid) {
+                const float4 g4 = *reinterpret_cast<const float4 *>(gt + b * 36 + 4 * uk);
+                const float gi = sigmoidf_(g4.x + pr.x + bi.x), gf = sigmoidf_(g4.y + pr.y + bi.y);
+                const float gg = tanhf(g4.z + pr.z + bi.z), go = sigmoidf_(g4.w + pr.w + bi.w);
+                c = gf * c + gi * gg;
+                hv = go * tanhf(c) * drop_mult(a.drop, a.site, (uint32_t)t, (uint32_t)(b + a.row_offset), (uint32_t)u);
+                ga = make_float4(gi, gf, gg, go);
+            }
+            // two units per 4-byte store: the even lane of a unit pair writes both halves
+            const float hv_hi = __shfl_down_sync(0xffffffffu, hv, 1);
+            const uint32_t hp = pack_bf2(hv, hv_hi);
+            const bool writer = ok && valid && (uk & 1) == 0;
+            if (writer) {
                 // the next step's operand first: everything else is only read after the kernel and is written past the barrier
                 *reinterpret_cast<uint32_t *>((uint8_t *)a.himg + (size_t)((t + 1) & 1) * img_bytes + himg_off) = hp;
                 fence_proxy_async_global();
@@ -267,17 +271,15 @@ __global__ void __launch_bounds__(PCF64_THREADS, 1) k_lstm_chain_fwd(const PcFwd
             // release at gpu scope is cumulative over the stores ordered before it by the CTA barrier
             if (threadIdx.x == 0) { gbar_arrive(a.bar); pc_stamp(a.dbg, j, t, 6); }
             if (ok && valid) {
-                if (a.gates_stash) {
-                    float4 *gs = reinterpret_cast<float4 *>(a.gates_stash + ((size_t)t * a.B + b) * 4 * H + 4 * u0);
-                    gs[0] = ga[0];
-                    gs[1] = ga[1];
-                }
-                *reinterpret_cast<float2 *>(a.c_stash + ((size_t)(t + 1) * a.B + b) * H + u0) = make_float2(c[0], c[1]);
+                if (a.gates_stash) *reinterpret_cast<float4 *>(a.gates_stash + ((size_t)t * a.B + b) * 4 * H + 4 * u) = ga;
+                a.c_stash[((size_t)(t + 1) * a.B + b) * H + u] = c;
+                if (writer) {
 #pragma unroll
-                for (int o = 0; o < 2; ++o) {
-                    const PcOut &d = a.out[o];
-                    if (d.p && t + d.toff < T)
-                        *reinterpret_cast<uint32_t *>(d.p + (size_t)(t + d.toff) * d.tstride + (size_t)b * d.ld + d.koff + u0) = hp;
+                    for (int o = 0; o < 2; ++o) {
+                        const PcOut &d = a.out[o];
+                        if (d.p && t + d.toff < T)
+                            *reinterpret_cast<uint32_t *>(d.p + (size_t)(t + d.toff) * d.tstride + (size_t)b * d.ld + d.koff + u) = hp;
+                    }
                 }
             }
         }
@@ -306,16 +308,45 @@ struct PcBwdArgs {
     long long *dbg;
 };
 
-// Same organisation as the forward chain: 512 threads, warp 2 = TMA, warp 3 = MMA (lean single-thread loops, no
-// per-chunk empty barriers), warps with (warp & 2) == 0 = epilogue (TMEM lane quadrant = warp & 1, column quarter =
-// warp >> 2: the thread finishes the cell backward of two hidden units of one batch row = one 16-byte image chunk).
-// Every thread of the cluster takes part in the one cluster barrier per step (the K-quarter partial exchange).
+// 512 threads, one loop: thread = (batch row, hidden unit 8j + uk), unit fastest, keeps d c of its (row, unit) in a register
+// and does the cell backward with coalesced accesses to the stashes / the d-gates image.  Per step
+//   warp 0 (one elected lane): image barrier, then the 16 TMA bulk copies of this CTA's K quarter (whole quarter in the ring:
+//                              no empty barriers); warp 1 (one elected lane): UMMA 64 x 32 x 16 over the 16 slabs;
+//   all warps: tcgen05.ld of the [64 x 32] partial tile, PUSHED column-wise into the shared memory of the rank that owns the
+//              column's unit (st.async + mbarrier complete_tx: no cluster barrier, no fence - a cluster.sync per step costs a
+//              MEMBAR.ALL.GPU in every thread); each rank sums the four partials of its 8 units in rank order.
+constexpr int PCB_PLD = 68;        // row stride of a pushed partial column ([src rank][8 units][68]: reads by (row, unit) conflict-free)
+
+struct PcbShared {
+    uint64_t full[PC_MAXRING], tmem_full, wbar, xb;
+    uint32_t tmem_slot;
+    volatile int dead;
+};
+
+__device__ __forceinline__ void pcb_st_async(uint32_t caddr, float v, uint32_t cmbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(caddr), "f"(v), "r"(cmbar) : "memory");
+}
+__device__ __forceinline__ uint32_t pcb_try_wait_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ uint32_t pcb_mapa(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PCF_THREADS, 1) k_lstm_chain_bwd(const PcBwdArgs a) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ uint8_t smem_raw[];
-    // 1 KB alignment computed as an OFFSET into the shared array: the compiler keeps the shared address space (LDS/STS,
-    // not generic LD/ST) for everything derived from it
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int H = a.H, T = a.T;
     const int nchunk = (H + 63) / 64;
@@ -323,16 +354,19 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PCF_THREADS, 1) k_ls
     const uint32_t wbytes = (uint32_t)nchunk * 4096;
     uint8_t *ring = smem;
     uint8_t *wsm = ring + (size_t)nchunk * PC_CHUNK_BYTES;
-    float *part = (float *)(wsm + wbytes);                 // [32 units][64 rows] fp32 partial of this K quarter
-    PcShared *sh = (PcShared *)(part + PC_N * PC_ROWS);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, j = blockIdx.x;
+    float *pin = (float *)(wsm + wbytes);                  // [4 src ranks][8 units][PCB_PLD] partial d h of the own units
+    PcbShared *sh = (PcbShared *)(pin + 4 * 8 * PCB_PLD);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, j = blockIdx.x;
     const int s_rank = (int)cluster.block_rank();          // == j & 3
     const unsigned ncta = gridDim.x;
+    const int ub = tid >> 3, uk = tid & 7, u = 8 * j + uk;
+    const bool valid = ub < a.B;
 
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < PC_MAXRING; ++s) { mbar_init(sh->full + s, 1); mbar_init(sh->empty + s, 1); }
+    if (tid == 0) {
+        for (int s = 0; s < PC_MAXRING; ++s) mbar_init(sh->full + s, 1);
         mbar_init(&sh->tmem_full, 1);
         mbar_init(&sh->wbar, 1);
+        mbar_init(&sh->xb, 1);
         sh->dead = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -345,131 +379,118 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PCF_THREADS, 1) k_ls
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sh->tmem_slot;
-    cluster.sync();
-
-    if (warp == 2) {
-        // ------------------------------------------------ TMA producer
-        const bool leader = elect_one();
-        bool ok = true;
-        if (leader) {
-            mbar_expect_tx(&sh->wbar, wbytes);
-            const uint8_t *wsrc = (const uint8_t *)a.Wimg + (size_t)j * wbytes;
-            for (uint32_t off = 0; off < wbytes; off += 16384) {
-                const uint32_t n = wbytes - off < 16384 ? wbytes - off : 16384;
-                tma_bulk_g2s(wsm + off, wsrc + off, n, &sh->wbar);
-            }
+    if (tid == 0) {
+        mbar_expect_tx(&sh->wbar, wbytes);
+        const uint8_t *wsrc = (const uint8_t *)a.Wimg + (size_t)j * wbytes;
+        for (uint32_t off = 0; off < wbytes; off += 16384) {
+            const uint32_t n = wbytes - off < 16384 ? wbytes - off : 16384;
+            tma_bulk_g2s(wsm + off, wsrc + off, n, &sh->wbar);
         }
-        for (int i = 0; i < T; ++i) {
-            if (leader && ok) {
-                if (i > 0) ok = gbar_wait(a.bar, ncta * (unsigned)i, &sh->dead, a.err, 21);
-                pc_stamp(a.dbg, j, i, 0);
-                if (ok) {
-                    fence_proxy_async_global();
-                    const uint8_t *src = (const uint8_t *)a.gimg + (size_t)(i & 1) * 4 * q_bytes + (size_t)s_rank * q_bytes;
-                    for (int c = 0; c < nchunk; ++c) {
-                        mbar_expect_tx(sh->full + c, PC_CHUNK_BYTES);
-                        tma_bulk_g2s(ring + (size_t)c * PC_CHUNK_BYTES, src + (size_t)c * PC_CHUNK_BYTES, PC_CHUNK_BYTES, sh->full + c);
+    }
+    cluster.sync();                                        // every CTA's mbarriers exist before any remote push
+    const bool okw = pc_mbar_wait(&sh->wbar, 0, &sh->dead, a.err, 23);
+
+    // gate rows 4u .. 4u+3 of the 4H range = 8 bytes of the swizzled image of K quarter (4u / H)
+    const int kg = 4 * u, quarter = kg / H, kk = kg - quarter * H;
+    const size_t gimg_off = (size_t)quarter * q_bytes + (size_t)(kk >> 6) * PC_CHUNK_BYTES + ub * 128 + ((((kk & 63) >> 3) ^ (ub & 7)) << 4) + (kk & 7) * 2;
+    const uint32_t my_pin = smem_u32(pin), my_xb = smem_u32(&sh->xb);
+    const int tq = warp & 3, tcq = warp >> 2;              // TMEM side: lane quadrant (rows 16 tq ..) and column quarter (owner rank) of this warp
+    const uint32_t taddr = tmem_base + ((uint32_t)(tq * 32) << 16) + (uint32_t)(8 * tcq);
+    const uint32_t dst_pin = pcb_mapa(my_pin, (uint32_t)tcq) + 4u * (uint32_t)(s_rank * 8 * PCB_PLD + 16 * tq + (lane & 15));
+    const uint32_t dst_xb = pcb_mapa(my_xb, (uint32_t)tcq);
+    float dc = 0.f;
+    float c_new = valid ? a.c_stash[((size_t)T * a.B + ub) * H + u] : 0.f;
+    for (int i = 0; i < T; ++i) {
+        const int t = T - 1 - i;
+        float4 ga = make_float4(0.f, 0.f, 0.f, 0.f);
+        float c_prev = 0.f, dhe = 0.f;
+        if (valid) {
+            ga = __ldcs(reinterpret_cast<const float4 *>(a.gates_stash + ((size_t)t * a.B + ub) * 4 * H + 4 * u));
+            c_prev = __ldcs(a.c_stash + ((size_t)t * a.B + ub) * H + u);
+            dhe = __ldcs(a.dh_ext + (size_t)t * a.dh_tstride + (size_t)ub * a.dh_ld + u);
+        }
+        const float mult = valid ? drop_mult(a.drop, a.site, (uint32_t)t, (uint32_t)(ub + a.row_offset), (uint32_t)u) : 1.f;
+        float rec = 0.f;
+        if (i > 0) {       // d h_t from the recurrence: W_hh^T . d gates_{t+1} (at t = T-1 there is none)
+            const uint32_t par = (uint32_t)(i - 1) & 1u;
+            if (tid == 0) mbar_expect_tx(&sh->xb, 4u * 8u * PC_ROWS * 4u);
+            if (warp == 0) {
+                if (elect_one()) {
+                    if (okw && gbar_wait(a.bar, ncta * (unsigned)i, &sh->dead, a.err, 21)) {
+                        pc_stamp(a.dbg, j, i, 0);
+                        fence_proxy_async_global();
+                        const uint8_t *src = (const uint8_t *)a.gimg + (size_t)(i & 1) * 4 * q_bytes + (size_t)s_rank * q_bytes;
+                        for (int c = 0; c < nchunk; ++c) {
+                            mbar_expect_tx(sh->full + c, PC_CHUNK_BYTES);
+                            tma_bulk_g2s(ring + (size_t)c * PC_CHUNK_BYTES, src + (size_t)c * PC_CHUNK_BYTES, PC_CHUNK_BYTES, sh->full + c);
+                        }
                     }
                 }
-            }
-            __syncwarp();
-            cluster.sync();
-        }
-    } else if (warp == 3) {
-        // ------------------------------------------------ MMA issuer
-        const bool leader = elect_one();
-        constexpr uint32_t idesc = umma_idesc_bf16(128, PC_N);
-        bool ok = true;
-        if (leader) ok = pc_mbar_wait(&sh->wbar, 0, &sh->dead, a.err, 23);
-        const uint64_t a0 = umma_desc_sw128(smem_u32(ring)), b0 = umma_desc_sw128(smem_u32(wsm));
-        for (int i = 0; i < T; ++i) {
-            if (leader && ok) {
-                const uint32_t ph = (uint32_t)i & 1u;
-                for (int c = 0; c < nchunk; ++c) {
-                    if (!pc_mbar_wait(sh->full + c, ph, &sh->dead, a.err, 24)) { ok = false; break; }
-                    tc_fence_after();
-                    const uint64_t ad = a0 + (uint64_t)(c * (PC_CHUNK_BYTES >> 4)), bd = b0 + (uint64_t)(c * (4096 >> 4));
-                    umma_bf16(tmem_base, ad, bd, idesc, c > 0 ? 1u : 0u);
-                    umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
-                    umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
-                    umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
+                __syncwarp();
+            } else if (warp == 1) {
+                if (elect_one()) {
+                    constexpr uint32_t idesc = umma_idesc_bf16(64, PC_N);
+                    const uint64_t a0 = umma_desc_sw128(smem_u32(ring)), b0 = umma_desc_sw128(smem_u32(wsm));
+                    bool ok = okw;
+                    for (int c = 0; c < nchunk && ok; ++c) {
+                        if (!pc_mbar_wait(sh->full + c, par, &sh->dead, a.err, 24)) { ok = false; break; }
+                        tc_fence_after();
+                        const uint64_t ad = a0 + (uint64_t)(c * (PC_CHUNK_BYTES >> 4)), bd = b0 + (uint64_t)(c * (4096 >> 4));
+                        umma_bf16(tmem_base, ad, bd, idesc, c > 0 ? 1u : 0u);
+                        umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
+                        umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
+                        umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
+                    }
+                    if (ok) {
+                        umma_commit(&sh->tmem_full);
+                        pc_stamp(a.dbg, j, i, 2);
+                        pc_mbar_wait(&sh->tmem_full, par, &sh->dead, a.err, 25);      // the only thread that waits for the accumulator
+                    }
                 }
-                if (ok) umma_commit(&sh->tmem_full);
-                pc_stamp(a.dbg, j, i, 2);
+                __syncwarp();
             }
-            __syncwarp();
-            cluster.sync();
-        }
-    } else if ((warp & 2) == 0) {
-        // ------------------------------------------------ epilogue
-        const int b = (warp & 1) * 32 + lane, cq = warp >> 2;
-        const bool valid = b < a.B;
-        const int u0 = 8 * j + 2 * cq;                     // 8j == 32 * (j / 4) + 8 * s_rank
-        const float *p0 = cluster.map_shared_rank(part, 0), *p1 = cluster.map_shared_rank(part, 1);
-        const float *p2 = cluster.map_shared_rank(part, 2), *p3 = cluster.map_shared_rank(part, 3);
-        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 1) * 32) << 16) + (uint32_t)(8 * cq);
-        // gate rows 4*u0 .. 4*u0+7 = 8-element k chunk 4j+cq of the 4H range = one 16-byte chunk of the swizzled image
-        const int kc = 4 * j + cq, quarter = kc / (H / 8), cc = kc - quarter * (H / 8);
-        const size_t gimg_off = (size_t)quarter * q_bytes + (size_t)(cc >> 3) * PC_CHUNK_BYTES + b * 128 + (((cc & 7) ^ (b & 7)) << 4);
-        float dc[2] = {0.f, 0.f}, c_new[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) c_new[k] = valid ? a.c_stash[((size_t)T * a.B + b) * H + u0 + k] : 0.f;
-        bool ok = true;
-        for (int i = 0; i < T; ++i) {
-            const int t = T - 1 - i;
-            float4 ga[2];
-            float c_prev[2], dhe[2];
-            if (valid) {
-                const float4 *gp = reinterpret_cast<const float4 *>(a.gates_stash + ((size_t)t * a.B + b) * 4 * H + 4 * u0);
-                ga[0] = __ldcs(gp);
-                ga[1] = __ldcs(gp + 1);
-                const float2 c2 = __ldcs(reinterpret_cast<const float2 *>(a.c_stash + ((size_t)t * a.B + b) * H + u0));
-                c_prev[0] = c2.x; c_prev[1] = c2.y;
-                const float2 d2 = __ldcs(reinterpret_cast<const float2 *>(a.dh_ext + (size_t)t * a.dh_tstride + (size_t)b * a.dh_ld + u0));
-                dhe[0] = d2.x; dhe[1] = d2.y;
-            }
-            if (ok) ok = __all_sync(0xffffffffu, pc_mbar_wait(&sh->tmem_full, (uint32_t)i & 1u, &sh->dead, a.err, 25)) != 0;
-            if (threadIdx.x == 0) pc_stamp(a.dbg, j, i, 3);
-            if (ok) {
-                tc_fence_after();
+            __syncthreads();
+            if (tid == 0) pc_stamp(a.dbg, j, i, 3);
+            if (!sh->dead) {
                 float acc[8];
+                tc_fence_after();
                 tmem_ld8(taddr, acc);
                 tc_fence_before();
+                if (lane < 16) {
 #pragma unroll
-                for (int n = 0; n < 8; ++n) part[(8 * cq + n) * PC_ROWS + b] = acc[n];
-            }
-            __syncwarp();
-            cluster.sync();                                // the four K-quarter partials of this cluster are in shared memory
-            if (threadIdx.x == 0) pc_stamp(a.dbg, j, i, 4);
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (ok && valid) {
-                uint32_t dgp[4];
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int o = (8 * s_rank + 2 * cq + k) * PC_ROWS + b;
-                    const float dh = dhe[k] + (((p0[o] + p1[o]) + p2[o]) + p3[o]);
-                    const float mult = drop_mult(a.drop, a.site, (uint32_t)t, (uint32_t)(b + a.row_offset), (uint32_t)(u0 + k));
-                    float dcp;
-                    const float4 d4 = lstm_bwd_point(dh, mult, ga[k], c_prev[k], c_new[k], dc[k], dcp);
-                    dc[k] = dcp;
-                    c_new[k] = c_prev[k];
-                    dgp[2 * k] = pack_bf2(d4.x, d4.y);
-                    dgp[2 * k + 1] = pack_bf2(d4.z, d4.w);
+                    for (int n = 0; n < 8; ++n) pcb_st_async(dst_pin + 4u * (uint32_t)(n * PCB_PLD), acc[n], dst_xb);
                 }
-                v = make_uint4(dgp[0], dgp[1], dgp[2], dgp[3]);
-                *reinterpret_cast<uint4 *>((uint8_t *)a.gimg + (size_t)((i + 1) & 1) * 4 * q_bytes + gimg_off) = v;
-                fence_proxy_async_global();
             }
-            if (threadIdx.x == 0) pc_stamp(a.dbg, j, i, 5);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (threadIdx.x == 0) { gbar_arrive(a.bar); pc_stamp(a.dbg, j, i, 6); }
-            if (ok && valid) *reinterpret_cast<uint4 *>(a.dg_rm + ((size_t)t * a.B + b) * 4 * H + 4 * u0) = v;
+            {   // lane 0 spins; then EVERY lane acquires the completed phase itself (pushed data is only guaranteed visible to
+                // threads that have observed the barrier)
+                int okx = 1;
+                if (lane == 0) okx = pc_mbar_wait(&sh->xb, par, &sh->dead, a.err, 26) ? 1 : 0;
+                okx = __shfl_sync(0xffffffffu, okx, 0);
+                if (okx) {
+                    while (!pcb_try_wait_cluster(&sh->xb, par)) {}
+                }
+            }
+            const int o = uk * PCB_PLD + ub;
+            rec = ((pin[o] + pin[8 * PCB_PLD + o]) + pin[16 * PCB_PLD + o]) + pin[24 * PCB_PLD + o];
+            if (tid == 0) pc_stamp(a.dbg, j, i, 4);
         }
-    } else {
-        for (int i = 0; i < T; ++i) cluster.sync();
+        uint2 dgp = make_uint2(0u, 0u);
+        if (valid && !sh->dead) {
+            float dcp;
+            const float4 d4 = lstm_bwd_point(dhe + rec, mult, ga, c_prev, c_new, dc, dcp);
+            dc = dcp;
+            c_new = c_prev;
+            dgp = make_uint2(pack_bf2(d4.x, d4.y), pack_bf2(d4.z, d4.w));
+            *reinterpret_cast<uint2 *>((uint8_t *)a.gimg + (size_t)((i + 1) & 1) * 4 * q_bytes + gimg_off) = dgp;
+            fence_proxy_async_global();
+        }
+        if (tid == 0) pc_stamp(a.dbg, j, i, 5);
+        __syncthreads();
+        if (tid == 0) { gbar_arrive(a.bar); pc_stamp(a.dbg, j, i, 6); }
+        if (valid) *reinterpret_cast<uint2 *>(a.dg_rm + ((size_t)t * a.B + ub) * 4 * H + 4 * u) = dgp;
     }
     __syncthreads();
-    cluster.sync();                                        // peers may still be reading this CTA's partial
+    cluster.sync();                                        // peers may still be pushing into this CTA's shared memory
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(32) : "memory");
     }
@@ -512,7 +533,8 @@ inline size_t pc_smem_bytes(int H, bool bwd) {
     const int nchunk = (H + 63) / 64;
     const int R = nchunk;
     // + 8 KB: the M = 128 MMA reads 64 rows past the last ring slot (ignored accumulator lanes) - keep that inside the allocation
-    return (size_t)R * PC_CHUNK_BYTES + (size_t)nchunk * 4096 + (bwd ? PC_N * PC_ROWS * 4 : 0) + sizeof(PcShared) + 8192 + 1024;
+    // (forward: + the [64][36] fp32 tile the epilogue re-maps its threads through)
+    return (size_t)R * PC_CHUNK_BYTES + (size_t)nchunk * 4096 + (bwd ? 4 * 8 * 68 * 4 + 256 : PC_ROWS * 36 * 4) + sizeof(PcShared) + 8192 + 1024;
 }
 
 // how many clusters of `cluster` CTAs (block size / dynamic shared memory given) the device keeps resident at once
