@@ -658,7 +658,7 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
         f.th = (const bf16 *)(s + S.TH); f.memb = (const bf16 *)(s + S.MEMB);
         f.wlc = w->loc_conv_w; f.wldT = packed + PL.wldT; f.v = w->v_w; f.lengths = mem_lengths;
         f.dg_rm = DGARM; f.dq_rm = DQRM;
-        f.de_out = x + W.DE; f.dconv_out = x + W.DCONV; f.dctx_out = x + W.DCTX;
+        f.de_out = x + W.DE; f.dconv_out = reinterpret_cast<uint16_t *>(x + W.DCONV); f.dctx_out = x + W.DCTX;
         f.dctxx = (unsigned long long *)(x + W.DCTXX); f.dqx = (unsigned long long *)(x + W.DQX);
         f.bar = (unsigned *)(x + W.BARA); f.err = err;
         f.drop = make_drop(seed, d.p_att, training);

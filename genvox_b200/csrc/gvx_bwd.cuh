@@ -24,6 +24,7 @@
 #include "gvx_gemm.cuh"
 #include "gvx_layout.cuh"
 #include "gvx_misc.cuh"
+#include "gvx_post_tc.cuh"
 
 namespace gvx {
 int check_dims(const gvx_dims *d);
@@ -348,9 +349,15 @@ inline int bwd_post_common(const Dims &d, const gvx_weights *w, const float *mem
         const int nblk = p.post_blocks;
         const int threads = (d.D + 31) & ~31;
         GVX_CHECK(threads <= 512, "att_dim too large");
-        if (p.bf16_mode && d.D == 128 && d.F == 32) {
-            if (p.th_bf16) k_attn_post_dense_mma<true><<<nblk, 128, 0, st>>>(p.TH, p.DE, p.CONVS, w->v_w, T, B, N, p.DPM, p.PART1);
-            else k_attn_post_dense_mma<false><<<nblk, 128, 0, st>>>(p.TH, p.DE, p.CONVS, w->v_w, T, B, N, p.DPM, p.PART1);
+        const bool stream = p.th_bf16 && p.bf16_mode && d.D == 128 && d.F == 32 && d.KS == 31;
+        int nblk1 = nblk, nblk2 = nblk;
+        if (stream) {
+            // fused persistent chains: bf16 tanh stash (chunk-swizzled) and bf16 d conv rows -> the streaming kernels of gvx_post_tc.cuh
+            const int items = B * ((N + PT_TOK - 1) / PT_TOK);
+            nblk1 = items < nblk ? items : nblk;
+            k_post_dense_stream<<<nblk1, 128, 0, st>>>(reinterpret_cast<const uint16_t *>(p.TH), p.DE, p.CONVS, w->v_w, T, B, N, p.DPM, p.PART1);
+        } else if (p.bf16_mode && d.D == 128 && d.F == 32) {
+            k_attn_post_dense_mma<false><<<nblk, 128, 0, st>>>(p.TH, p.DE, p.CONVS, w->v_w, T, B, N, p.DPM, p.PART1);
         } else if (d.F <= 32) {
             k_attn_post_dense<32><<<nblk, threads, 0, st>>>(p.TH, p.DE, p.CONVS, w->v_w, T, B, N, d.D, d.F, p.DPM, p.PART1);
         } else {
@@ -359,24 +366,37 @@ inline int bwd_post_common(const Dims &d, const gvx_weights *w, const float *mem
         GVX_LAUNCHED(1);
         GVX_CUDA(cudaGetLastError());
         const int stride = d.D * d.F + d.D;
-        k_reduce_partials<<<(d.D * d.F + 31) / 32, dim3(32, 8), 0, st>>>(p.PART1, nblk, stride, 0, d.D * d.F, g->loc_dense_w);
+        k_reduce_partials<<<(d.D * d.F + 31) / 32, dim3(32, 8), 0, st>>>(p.PART1, nblk1, stride, 0, d.D * d.F, g->loc_dense_w);
         GVX_LAUNCHED(1);
-        k_reduce_partials<<<(d.D + 31) / 32, dim3(32, 8), 0, st>>>(p.PART1, nblk, stride, d.D * d.F, d.D, g->v_w);
+        k_reduce_partials<<<(d.D + 31) / 32, dim3(32, 8), 0, st>>>(p.PART1, nblk1, stride, d.D * d.F, d.D, g->v_w);
         GVX_LAUNCHED(1);
-        const int KB = (d.KS + 7) / 8, NCS = (N + 7) & ~7, NPS = NCS + 8 * KB + 8;
-        const int cthreads = (d.F * 2 * KB + 31) & ~31;
-        GVX_CHECK(cthreads <= 1024, "location conv too large for the conv-gradient kernel");
-        const size_t smem = ((size_t)2 * NPS + (size_t)d.F * NCS) * sizeof(float);
-        GVX_CHECK(smem <= 200 * 1024, "token count too large for the conv-gradient kernel");
-        static size_t configured = 0;
-        if (smem > configured) {
-            GVX_CUDA(cudaFuncSetAttribute(k_attn_post_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
+        if (stream) {
+            const PtConvGeom cg(N);
+            const size_t smem = (size_t)PT_CSTAGES * cg.stage_bytes;
+            GVX_CHECK(smem <= 200 * 1024, "token count too large for the conv-gradient kernel");
+            static size_t configured = 0;
+            if (smem > configured) {
+                GVX_CUDA(cudaFuncSetAttribute(k_post_conv_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured = smem;
+            }
+            nblk2 = T * B < nblk / 2 ? T * B : nblk / 2;
+            k_post_conv_stream<<<nblk2, 128, smem, st>>>(reinterpret_cast<const uint16_t *>(p.DCONV), p.ALIGN, p.CUMS, T, B, N, p.PART2);
+        } else {
+            const int KB = (d.KS + 7) / 8, NCS = (N + 7) & ~7, NPS = NCS + 8 * KB + 8;
+            const int cthreads = (d.F * 2 * KB + 31) & ~31;
+            GVX_CHECK(cthreads <= 1024, "location conv too large for the conv-gradient kernel");
+            const size_t smem = ((size_t)2 * NPS + (size_t)d.F * NCS) * sizeof(float);
+            GVX_CHECK(smem <= 200 * 1024, "token count too large for the conv-gradient kernel");
+            static size_t configured = 0;
+            if (smem > configured) {
+                GVX_CUDA(cudaFuncSetAttribute(k_attn_post_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured = smem;
+            }
+            k_attn_post_conv<<<nblk, cthreads < 64 ? 64 : cthreads, smem, st>>>(p.DCONV, p.ALIGN, p.CUMS, T, B, N, d.F, d.KS, p.PART2);
         }
-        k_attn_post_conv<<<nblk, cthreads < 64 ? 64 : cthreads, smem, st>>>(p.DCONV, p.ALIGN, p.CUMS, T, B, N, d.F, d.KS, p.PART2);
         GVX_LAUNCHED(1);
         GVX_CUDA(cudaGetLastError());
-        k_reduce_partials<<<(d.F * 2 * d.KS + 31) / 32, dim3(32, 8), 0, st>>>(p.PART2, nblk, d.F * 2 * d.KS, 0, d.F * 2 * d.KS,
+        k_reduce_partials<<<(d.F * 2 * d.KS + 31) / 32, dim3(32, 8), 0, st>>>(p.PART2, nblk2, d.F * 2 * d.KS, 0, d.F * 2 * d.KS,
                                                                            g->loc_conv_w);
         GVX_LAUNCHED(1);
         GVX_CUDA(cudaGetLastError());

@@ -121,7 +121,7 @@ struct FbArgs {
     __nv_bfloat16 *dg_rm;            // [T][B][4A]
     __nv_bfloat16 *dq_rm;            // [T][B][D]
     float *de_out;                   // [T][B][N]
-    float *dconv_out;                // [T][B][N][F]
+    uint16_t *dconv_out;             // [T][B][N][F] bf16: the A operand of k_post_conv_stream (gvx_post_tc.cuh)
     float *dctx_out;                 // [T][B][E]
     unsigned long long *dctxx;       // [2][64][E]   (value, tag) exchange of the recurrent d ctx part, zero at launch
     unsigned long long *dqx;         // [2][64][4 parts][D/2] (bf16x2, tag) exchange of the per-part d q, zero at launch
@@ -478,7 +478,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
                     if (n < G.NH) {
                         dconvT[f0 * G.NDS + AF_PAD + n] = x0;
                         dconvT[(f0 + 1) * G.NDS + AF_PAD + n] = x1;
-                        if (n < n_own) *reinterpret_cast<float2 *>(a.dconv_out + (((size_t)t * B + row) * N + n_lo + n) * AF_F + f0) = make_float2(x0, x1);
+                        if (n < n_own) *reinterpret_cast<uint32_t *>(a.dconv_out + (((size_t)t * B + row) * N + n_lo + n) * AF_F + f0) = pack_bf2(x0, x1);
                         // 15-token halos pushed straight into the neighbours' windows
                         if (has_left && n < AF_PAD) {
                             st_async_f32(nbl_dconv + 4 * (f0 * G.NDS + AF_PAD + G.NH + n), x0, nbl_xb2);
