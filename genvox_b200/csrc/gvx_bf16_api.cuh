@@ -421,6 +421,7 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
         ProfScope ps(PS_ATTENTION, st);
         FaArgs f;
         memset(&f, 0, sizeof(f));
+        f.loc_mma = fa_loc_mma();
         f.Wimg = (const bf16 *)(packed + BL.WaRecI);
         f.pre = s + S.GA; f.bias = packed + PL.ba;
         f.ximg = (uint8_t *)(s + S.XIMG);
@@ -957,6 +958,7 @@ int check_tc_err_public(int *err_dev, cudaStream_t st, const char *what) { retur
 extern "C" int gvx_debug_option(const char *name, int value) {
     if (!strcmp(name, "fused")) gvx::fa_mode() = value;
     else if (!strcmp(name, "persistent")) gvx::pc_mode() = value;
+    else if (!strcmp(name, "locmma")) gvx::fa_loc_mma() = value < 0 ? 1 : value;
     else { snprintf(gvx::g_err, sizeof(gvx::g_err), "gvx_debug_option: unknown option %s", name); return 1; }
     return 0;
 }

@@ -45,6 +45,8 @@ constexpr int FA_MAXN = 160;
 constexpr int FA_IMG_BYTES = FA_NSLAB * PC_CHUNK_BYTES;     // one operand image: [24][64 rows][128 B]
 constexpr int FA_CLUSTER = 2;                 // the two CTAs (token halves) of one batch row
 constexpr int FA_GROUP = 8;                   // CTAs sharing 4 batch rows: they split the query projection 8 ways
+constexpr int FA_LPS = 136;                   // row stride (floats) of the location + processed-memory tile: the 64-bit fragment stores of the
+                                              // tensor-core location phase are conflict-free (136 = 8 mod 32), rows stay 16-byte aligned
 
 struct FaGeom {
     int NH, nblk, NPS;
@@ -69,8 +71,8 @@ struct FaSmem {      // byte offsets from the 1 KB aligned base
         auto take = [&](int bytes) { int r = o; o += (bytes + 127) & ~127; return r; };
         ring = take(FA_RING * PC_CHUNK_BYTES);
         wsm = take(FA_NSLAB * 4096);           // also absorbs the 64-row over-read of the last ring slot
-        lp = take(g.NH * AF_D * 4 > 7 * FA_E * 4 ? g.NH * AF_D * 4 : 7 * FA_E * 4);     // also the [7][512] partial contexts
-        convT = take(AF_F * g.NH * 4);
+        lp = take(g.NH * FA_LPS * 4 > 7 * FA_E * 4 ? g.NH * FA_LPS * 4 : 7 * FA_E * 4);     // also the [7][512] partial contexts
+        convT = take(AF_F * g.NH * 4 > 8192 ? AF_F * g.NH * 4 : 8192);     // also the 8 KB of conv B fragments (tensor-core location phase)
         wldT = take(AF_F * AF_D * 4);
         wlc = take(AF_F * 2 * AF_KS * 4);
         ctxp = take(FA_E * 4);
@@ -123,6 +125,7 @@ struct FaArgs {
     int row_offset, B, N, T;
     long long *dbg;
     int *prog;                   // optional [3][128] progress markers (post-mortem of a stuck launch)
+    int loc_mma;                 // 1: location conv + dense on mma.sync (hi + lo bf16 operands), 0: FFMA (debug option "locmma")
 };
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
@@ -208,6 +211,12 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+// (not volatile: a pure function of its operands - the compiler may interleave independent accumulator chains)
+__device__ __forceinline__ void mma_bf16_pure(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ float sigmoid_fast(float x) {
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
@@ -276,8 +285,29 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_slot)), "n"(32) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < AF_F * 2 * AF_KS; i += FA_THREADS) wlc[i] = a.wlc[i];
-    for (int i = tid; i < AF_F * AF_D / 4; i += FA_THREADS) reinterpret_cast<float4 *>(wldT)[i] = reinterpret_cast<const float4 *>(a.wldT)[i];
+    // tensor-core location phase: both weight matrices live in shared memory as ready-made mma.sync B fragments, one uint4
+    // {b0 hi, b1 hi, b0 lo, b1 lo} per (k-step, n-tile, lane); they take the place of the fp32 copies (and of convT)
+    uint4 *wlcB = reinterpret_cast<uint4 *>(smem + L.convT), *wldB = reinterpret_cast<uint4 *>(smem + L.wldT);
+    if (a.loc_mma) {
+        for (int e = tid; e < 16 * 32; e += FA_THREADS) {          // conv: k = (channel, tap) in 4 steps of 16, n = filter
+            const int ln = e & 31, nt = (e >> 5) & 3, ks = e >> 7, gg = ln >> 2, tg = ln & 3;
+            const int c = ks >> 1, f = 8 * nt + gg, tap0 = 16 * (ks & 1) + 2 * tg;
+            const float *wr = a.wlc + (f * 2 + c) * AF_KS;
+            const float x0 = wr[tap0], x1 = wr[tap0 + 1], x8 = tap0 + 8 < AF_KS ? wr[tap0 + 8] : 0.f, x9 = tap0 + 9 < AF_KS ? wr[tap0 + 9] : 0.f;
+            const uint32_t h0 = pack_bf2(x0, x1), h1 = pack_bf2(x8, x9);
+            wlcB[e] = make_uint4(h0, h1, pack_bf2(x0 - bf_lo(h0), x1 - bf_hi(h0)), pack_bf2(x8 - bf_lo(h1), x9 - bf_hi(h1)));
+        }
+        for (int e = tid; e < 32 * 32; e += FA_THREADS) {          // dense: k = filter in 2 steps of 16, n = attention dim
+            const int ln = e & 31, nt2 = (e >> 5) & 15, ks2 = e >> 9, gg = ln >> 2, tg = ln & 3;
+            const float *wc0 = a.wldT + (16 * ks2 + 2 * tg) * AF_D + 8 * nt2 + gg;
+            const float x0 = wc0[0], x1 = wc0[AF_D], x8 = wc0[8 * AF_D], x9 = wc0[9 * AF_D];
+            const uint32_t h0 = pack_bf2(x0, x1), h1 = pack_bf2(x8, x9);
+            wldB[e] = make_uint4(h0, h1, pack_bf2(x0 - bf_lo(h0), x1 - bf_hi(h0)), pack_bf2(x8 - bf_lo(h1), x9 - bf_hi(h1)));
+        }
+    } else {
+        for (int i = tid; i < AF_F * 2 * AF_KS; i += FA_THREADS) wlc[i] = a.wlc[i];
+        for (int i = tid; i < AF_F * AF_D / 4; i += FA_THREADS) reinterpret_cast<float4 *>(wldT)[i] = reinterpret_cast<const float4 *>(a.wldT)[i];
+    }
     if (tid < AF_D) vs[tid] = a.v[tid];
     for (int i = tid; i < 2 * G.NPS; i += FA_THREADS) wcat[i] = 0.f;       // w_{-1} = cum_{-1} = 0 (tacotron2.py:303-315)
     tc_fence_before();
@@ -340,6 +370,7 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                 }
                 if (ok) umma_commit(&sh->tmem_full);
                 pc_stamp(a.dbg, j, t, 1);
+                if (a.dbg && ok) { fa_wait_mbar(&sh->tmem_full, (uint32_t)t & 1u, &sh->dead, a.err, 36); pc_stamp(a.dbg, j, t, 18); }
                 fa_mark(a.prog, 2, j, t + 1);
             }
         }
@@ -383,72 +414,178 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
         const uint32_t peer_inbox = mapa_u32(smem_u32(inbox), (uint32_t)peer);
         const uint32_t peer_sbar = mapa_u32(smem_u32(&sh->sbar), (uint32_t)peer);
         constexpr uint32_t kInboxBytes = (2 + AF_PAD + FA_E / 2) * 4;
+        // processed memory of the own tokens -> lp (16-byte cp.async, no registers): requested as soon as lp is dead (after the
+        // partial contexts of the previous step are summed), it lands long before the location phase adds the dense output to it
+        const float *pm_own = a.pm + ((size_t)rowc * N + n_lo) * AF_D;
+        auto pm_prefetch = [&]() {
+            for (int i = wtid; i < n_own * (AF_D / 4); i += FA_NW) cp_async16(lp + (i >> 5) * FA_LPS + (i & 31) * 4, pm_own + (size_t)i * 4, true);
+            cp_async_commit();
+        };
+        if (a.loc_mma) pm_prefetch();
         for (int t = 0; t < T; ++t) {
             // ============================================================ location features of step t (w_{t-1}, cum_{t-1})
-            for (int task = wtid; task < AF_F * G.nblk; task += FA_NW) {
-                const int f = task / G.nblk, n0 = (task - f * G.nblk) * 8;
-                float acc[8];
+            if (a.loc_mma) {
+                // conv (Toeplitz window of the two zero-padded rows . W_loc_conv) and dense (. W_loc_dense) chained on mma.sync: the
+                // conv accumulator fragments of a 16-token tile ARE the A fragments of the dense contraction.  Every fp32 operand is
+                // split hi + lo (bf16 each) and the lo x lo term dropped: ~2^-17 relative, i.e. fp32-grade like the FFMA path.
+                cp_async_wait<0>();
+                fa_bar_workers();                       // everybody's processed-memory chunks are in lp
+                if (tid == 0) pc_stamp(a.dbg, j, t, 19);
+                const int nmt = (G.NH + 15) >> 4;
+                float *cs = (rvalid && a.conv_stash) ? a.conv_stash + (((size_t)t * B + row) * N + n_lo) * AF_F : nullptr;
+                // only the 6 worker warps WITHOUT an LSTM-epilogue role take tasks: the epilogue warps go straight to the
+                // accumulator wait (the ctx part of the gate GEMM completes long before these tiles do), and the tiles are not
+                // needed before the energies, i.e. after the cell, the grid barrier and the query projection
+                const int lslot = (warp >> 2) * 2 + (warp & 1) - 2;           // warps 6,7,10,11,14,15 -> 0..5
+                for (int task = epi ? 2 * nmt : lslot; task < 2 * nmt; task += 6) {
+                    const int mt = task >> 1, nh = task & 1;
+                    float c1[4][4];
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) acc[jj] = 0.f;
+                    for (int nt = 0; nt < 4; ++nt) c1[nt][0] = c1[nt][1] = c1[nt][2] = c1[nt][3] = 0.f;
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    float x[40];
-                    const float4 *xr = reinterpret_cast<const float4 *>(wcat + c * G.NPS + n0);
+                    for (int c = 0; c < 2; ++c) {
+                        const float *base = wcat + c * G.NPS + 16 * mt + g4 + 2 * tig;
+                        uint32_t ph[5], pl[5];
 #pragma unroll
-                    for (int i = 0; i < 10; ++i) {
-                        const float4 t4 = xr[i];
-                        x[4 * i] = t4.x; x[4 * i + 1] = t4.y; x[4 * i + 2] = t4.z; x[4 * i + 3] = t4.w;
-                    }
-                    const float *wr = wlc + (f * 2 + c) * AF_KS;
+                        for (int i = 0; i < 5; ++i) {
+                            const float x0 = base[8 * i], x1 = base[8 * i + 1];
+                            ph[i] = pack_bf2(x0, x1);
+                            pl[i] = pack_bf2(x0 - bf_lo(ph[i]), x1 - bf_hi(ph[i]));
+                        }
 #pragma unroll
-                    for (int k = 0; k < AF_KS; ++k) {
-                        const float wk = wr[k];
+                        for (int s2 = 0; s2 < 2; ++s2) {
+                            uint4 b[4];
 #pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) acc[jj] = fmaf(wk, x[jj + k], acc[jj]);
-                    }
-                }
-                float4 *dst = reinterpret_cast<float4 *>(convT + f * G.NH + n0);
-                dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-            }
-            fa_bar_workers();
-            if (rvalid && a.conv_stash) {
-                float *cs = a.conv_stash + (((size_t)t * B + row) * N + n_lo) * AF_F;
-                for (int i = wtid; i < n_own * AF_F; i += FA_NW) cs[i] = convT[(i & 31) * G.NH + (i >> 5)];
-            }
-            {   // location dense + processed memory -> lp[n][d]; a warp takes 4 tokens, a lane 4 attention dims.  The processed
-                // memory rows (L2 resident, read-only) are requested first and land while the FFMA loop runs.
-                const float *pm_b = a.pm + ((size_t)rowc * N + n_lo) * AF_D;
-                const int ngrp = (n_own + 3) / 4;
-                for (int grp = widx; grp < ngrp; grp += 14) {
-                    const int n0 = grp * 4;
-                    float4 pmv[4];
+                            for (int nt = 0; nt < 4; ++nt) b[nt] = wlcB[((2 * c + s2) * 4 + nt) * 32 + lane];
+                            // term by term over the 4 independent accumulators: no back-to-back dependent MMAs
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj)
-                        pmv[jj] = n0 + jj < n_own ? __ldg(reinterpret_cast<const float4 *>(pm_b + (size_t)(n0 + jj) * AF_D + lane * 4))
-                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-                    float loc[4][4];
+                            for (int nt = 0; nt < 4; ++nt) mma_bf16_pure(c1[nt], ph[2 * s2], ph[2 * s2 + 1], ph[2 * s2 + 1], ph[2 * s2 + 2], b[nt].x, b[nt].y);
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj)
+                            for (int nt = 0; nt < 4; ++nt) mma_bf16_pure(c1[nt], pl[2 * s2], pl[2 * s2 + 1], pl[2 * s2 + 1], pl[2 * s2 + 2], b[nt].x, b[nt].y);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) loc[jj][i] = 0.f;
-#pragma unroll 8
-                    for (int f = 0; f < AF_F; ++f) {
-                        const float4 wd = *reinterpret_cast<const float4 *>(wldT + f * AF_D + lane * 4);
-                        const float4 c4 = *reinterpret_cast<const float4 *>(convT + f * G.NH + n0);
-                        const float cj[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            loc[jj][0] = fmaf(cj[jj], wd.x, loc[jj][0]);
-                            loc[jj][1] = fmaf(cj[jj], wd.y, loc[jj][1]);
-                            loc[jj][2] = fmaf(cj[jj], wd.z, loc[jj][2]);
-                            loc[jj][3] = fmaf(cj[jj], wd.w, loc[jj][3]);
+                            for (int nt = 0; nt < 4; ++nt) mma_bf16_pure(c1[nt], ph[2 * s2], ph[2 * s2 + 1], ph[2 * s2 + 1], ph[2 * s2 + 2], b[nt].z, b[nt].w);
                         }
                     }
+                    const int r0 = 16 * mt + g4, r1 = r0 + 8;
+                    if (cs && nh == 0) {
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj)
-                        *reinterpret_cast<float4 *>(lp + (size_t)(n0 + jj) * AF_D + lane * 4) =
-                            make_float4(loc[jj][0] + pmv[jj].x, loc[jj][1] + pmv[jj].y, loc[jj][2] + pmv[jj].z, loc[jj][3] + pmv[jj].w);
+                        for (int nt = 0; nt < 4; ++nt) {
+                            if (r0 < n_own) *reinterpret_cast<float2 *>(cs + (size_t)r0 * AF_F + 8 * nt + 2 * tig) = make_float2(c1[nt][0], c1[nt][1]);
+                            if (r1 < n_own) *reinterpret_cast<float2 *>(cs + (size_t)r1 * AF_F + 8 * nt + 2 * tig) = make_float2(c1[nt][2], c1[nt][3]);
+                        }
+                    }
+                    uint32_t ah[2][4], al[2][4];
+#pragma unroll
+                    for (int k2 = 0; k2 < 2; ++k2)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float x0 = c1[2 * k2 + (q >> 1)][2 * (q & 1)], x1 = c1[2 * k2 + (q >> 1)][2 * (q & 1) + 1];
+                            ah[k2][q] = pack_bf2(x0, x1);
+                            al[k2][q] = pack_bf2(x0 - bf_lo(ah[k2][q]), x1 - bf_hi(ah[k2][q]));
+                        }
+#pragma unroll
+                    for (int qq = 0; qq < 2; ++qq) {
+                        float c2[4][4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) c2[q][0] = c2[q][1] = c2[q][2] = c2[q][3] = 0.f;
+#pragma unroll
+                        for (int k2 = 0; k2 < 2; ++k2) {
+                            uint4 b[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) b[q] = wldB[(k2 * 16 + 8 * nh + 4 * qq + q) * 32 + lane];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) mma_bf16_pure(c2[q], ah[k2][0], ah[k2][1], ah[k2][2], ah[k2][3], b[q].x, b[q].y);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) mma_bf16_pure(c2[q], al[k2][0], al[k2][1], al[k2][2], al[k2][3], b[q].x, b[q].y);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) mma_bf16_pure(c2[q], ah[k2][0], ah[k2][1], ah[k2][2], ah[k2][3], b[q].z, b[q].w);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int nt2 = 8 * nh + 4 * qq + q;
+                            if (r0 < G.NH) {
+                                float2 *p0 = reinterpret_cast<float2 *>(lp + (size_t)r0 * FA_LPS + 8 * nt2 + 2 * tig);
+                                float2 v0 = *p0;
+                                v0.x += c2[q][0]; v0.y += c2[q][1];
+                                *p0 = v0;
+                            }
+                            if (r1 < G.NH) {
+                                float2 *p1 = reinterpret_cast<float2 *>(lp + (size_t)r1 * FA_LPS + 8 * nt2 + 2 * tig);
+                                float2 v1 = *p1;
+                                v1.x += c2[q][2]; v1.y += c2[q][3];
+                                *p1 = v1;
+                            }
+                        }
+                    }
+                }
+                if (warp == 6 && lane == 0) pc_stamp(a.dbg, j, t, 20);
+            } else {
+                for (int task = wtid; task < AF_F * G.nblk; task += FA_NW) {
+                    const int f = task / G.nblk, n0 = (task - f * G.nblk) * 8;
+                    float acc[8];
+    #pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) acc[jj] = 0.f;
+    #pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        float x[40];
+                        const float4 *xr = reinterpret_cast<const float4 *>(wcat + c * G.NPS + n0);
+    #pragma unroll
+                        for (int i = 0; i < 10; ++i) {
+                            const float4 t4 = xr[i];
+                            x[4 * i] = t4.x; x[4 * i + 1] = t4.y; x[4 * i + 2] = t4.z; x[4 * i + 3] = t4.w;
+                        }
+                        const float *wr = wlc + (f * 2 + c) * AF_KS;
+    #pragma unroll
+                        for (int k = 0; k < AF_KS; ++k) {
+                            const float wk = wr[k];
+    #pragma unroll
+                            for (int jj = 0; jj < 8; ++jj) acc[jj] = fmaf(wk, x[jj + k], acc[jj]);
+                        }
+                    }
+                    float4 *dst = reinterpret_cast<float4 *>(convT + f * G.NH + n0);
+                    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                }
+                fa_bar_workers();
+                if (tid == 0) pc_stamp(a.dbg, j, t, 19);
+                if (rvalid && a.conv_stash) {
+                    float *cs = a.conv_stash + (((size_t)t * B + row) * N + n_lo) * AF_F;
+                    for (int i = wtid; i < n_own * AF_F; i += FA_NW) cs[i] = convT[(i & 31) * G.NH + (i >> 5)];
+                }
+                {   // location dense + processed memory -> lp[n][d]; a warp takes 4 tokens, a lane 4 attention dims.  The processed
+                    // memory rows (L2 resident, read-only) are requested first and land while the FFMA loop runs.
+                    const float *pm_b = a.pm + ((size_t)rowc * N + n_lo) * AF_D;
+                    const int ngrp = (n_own + 3) / 4;
+                    for (int grp = widx; grp < ngrp; grp += 14) {
+                        const int n0 = grp * 4;
+                        float4 pmv[4];
+    #pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            pmv[jj] = n0 + jj < n_own ? __ldg(reinterpret_cast<const float4 *>(pm_b + (size_t)(n0 + jj) * AF_D + lane * 4))
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                        float loc[4][4];
+    #pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+    #pragma unroll
+                            for (int i = 0; i < 4; ++i) loc[jj][i] = 0.f;
+    #pragma unroll 8
+                        for (int f = 0; f < AF_F; ++f) {
+                            const float4 wd = *reinterpret_cast<const float4 *>(wldT + f * AF_D + lane * 4);
+                            const float4 c4 = *reinterpret_cast<const float4 *>(convT + f * G.NH + n0);
+                            const float cj[4] = {c4.x, c4.y, c4.z, c4.w};
+    #pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                loc[jj][0] = fmaf(cj[jj], wd.x, loc[jj][0]);
+                                loc[jj][1] = fmaf(cj[jj], wd.y, loc[jj][1]);
+                                loc[jj][2] = fmaf(cj[jj], wd.z, loc[jj][2]);
+                                loc[jj][3] = fmaf(cj[jj], wd.w, loc[jj][3]);
+                            }
+                        }
+    #pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            *reinterpret_cast<float4 *>(lp + (size_t)(n0 + jj) * FA_LPS + lane * 4) =
+                                make_float4(loc[jj][0] + pmv[jj].x, loc[jj][1] + pmv[jj].y, loc[jj][2] + pmv[jj].z, loc[jj][3] + pmv[jj].w);
+                    }
                 }
             }
             if (tid == 0) pc_stamp(a.dbg, j, t, 12);
@@ -573,7 +710,7 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                     for (int jj = 0; jj < 4; ++jj) {
                         pe[jj] = 0.f;
                         if (n0 + jj < n_own) {
-                            const float4 l4 = *reinterpret_cast<const float4 *>(lp + (size_t)(n0 + jj) * AF_D + lane * 4);
+                            const float4 l4 = *reinterpret_cast<const float4 *>(lp + (size_t)(n0 + jj) * FA_LPS + lane * 4);
                             float4 th;
                             th.x = tanh_fast(q4.x + l4.x);
                             th.y = tanh_fast(q4.y + l4.y);
@@ -662,6 +799,7 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                           ((part[4 * FA_E + e] + part[5 * FA_E + e]) + part[6 * FA_E + e]);
             fa_bar_workers();
             if (tid == 0) pc_stamp(a.dbg, j, t, 15);
+            if (a.loc_mma && t + 1 < T) pm_prefetch();       // lp (= the partial contexts) is dead from here on
             // ---- exchange with the peer CTA of the row: each side PUSHES what the other needs (local max / sum, the 15 halo
             // exponentials next to the peer's token range, the peer's half of the context partial) and waits for its own inbox
             if (tid == 0) mbar_expect_tx(&sh->sbar, kInboxBytes);
@@ -804,6 +942,10 @@ inline bool fa_supported(const Dims &d, int B, int N) {
         cached_smem = smem;
     }
     return cached;
+}
+inline int &fa_loc_mma() {     // location phase of k_att_chain_fwd on mma.sync (1, default) or FFMA (0): debug option "locmma"
+    static int on = 1;
+    return on;
 }
 inline int &fa_mode() {        // -1 = not yet read from the environment, 0 = off, 1 = on
     static int on = -1;
