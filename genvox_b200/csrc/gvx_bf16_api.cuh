@@ -958,6 +958,7 @@ int check_tc_err_public(int *err_dev, cudaStream_t st, const char *what) { retur
 extern "C" int gvx_debug_option(const char *name, int value) {
     if (!strcmp(name, "fused")) gvx::fa_mode() = value;
     else if (!strcmp(name, "persistent")) gvx::pc_mode() = value;
+    else if (!strcmp(name, "multicast")) gvx::pc_multicast() = value < 0 ? 4 : (value == 0 ? 1 : (value == 1 ? 4 : value));
     else if (!strcmp(name, "locmma")) gvx::fa_loc_mma() = value < 0 ? 1 : value;
     else { snprintf(gvx::g_err, sizeof(gvx::g_err), "gvx_debug_option: unknown option %s", name); return 1; }
     return 0;

@@ -700,46 +700,57 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
             }
             fa_bar_workers();
             if (tid == 0) { pc_stamp(a.dbg, j, t, 5); fa_mark(a.prog, 0, j, 8 * t + 3); }
-            {   // energies of the own tokens
+            {   // energies of the own tokens: warp w takes tokens w, w + 14, ... (at most 6 of the <= 80), a lane 4 attention dims; the
+                // per-token partial dots of a lane are reduced together by a transposing butterfly (9 shuffles for 8 slots)
                 const float4 q4 = *reinterpret_cast<const float4 *>(qfull + lane * 4);
-                const int ngrp = (n_own + 3) / 4;
-                for (int grp = widx; grp < ngrp; grp += 14) {
-                    const int n0 = grp * 4;
-                    float pe[4];
+                static_assert((((FA_MAXN + 1) / 2 + 7) & ~7) <= 6 * 14, "6 tokens per worker warp do not cover the own tokens");
+                float pe[8];
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        pe[jj] = 0.f;
-                        if (n0 + jj < n_own) {
-                            const float4 l4 = *reinterpret_cast<const float4 *>(lp + (size_t)(n0 + jj) * FA_LPS + lane * 4);
-                            float4 th;
-                            th.x = tanh_fast(q4.x + l4.x);
-                            th.y = tanh_fast(q4.y + l4.y);
-                            th.z = tanh_fast(q4.z + l4.z);
-                            th.w = tanh_fast(q4.w + l4.w);
-                            if (rvalid && a.th_stash) {
-                                const size_t trow = ((size_t)t * B + row) * N + n_lo + n0 + jj;
-                                if (a.th_bf16) {
-                                    const int nn = n_lo + n0 + jj;
-                                    __stcs(reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(a.th_stash) + trow * (AF_D * 2) +
-                                                                     (((lane >> 1) ^ (nn & 7)) << 4) + (lane & 1) * 8),
-                                           make_uint2(pack_bf2(th.x, th.y), pack_bf2(th.z, th.w)));
-                                } else {
-                                    __stcs(reinterpret_cast<float4 *>(a.th_stash + trow * AF_D + lane * 4), th);
-                                }
+                for (int i = 0; i < 8; ++i) pe[i] = 0.f;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    const int n = widx + 14 * i;
+                    if (n < n_own) {
+                        const float4 l4 = *reinterpret_cast<const float4 *>(lp + (size_t)n * FA_LPS + lane * 4);
+                        float4 th;
+                        th.x = tanh_fast(q4.x + l4.x);
+                        th.y = tanh_fast(q4.y + l4.y);
+                        th.z = tanh_fast(q4.z + l4.z);
+                        th.w = tanh_fast(q4.w + l4.w);
+                        if (rvalid && a.th_stash) {
+                            const size_t trow = ((size_t)t * B + row) * N + n_lo + n;
+                            if (a.th_bf16) {
+                                const int nn = n_lo + n;
+                                __stcs(reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(a.th_stash) + trow * (AF_D * 2) +
+                                                                 (((lane >> 1) ^ (nn & 7)) << 4) + (lane & 1) * 8),
+                                       make_uint2(pack_bf2(th.x, th.y), pack_bf2(th.z, th.w)));
+                            } else {
+                                __stcs(reinterpret_cast<float4 *>(a.th_stash + trow * AF_D + lane * 4), th);
                             }
-                            pe[jj] = fmaf(v4.x, th.x, fmaf(v4.y, th.y, fmaf(v4.z, th.z, v4.w * th.w)));
                         }
+                        pe[i] = fmaf(v4.x, th.x, fmaf(v4.y, th.y, fmaf(v4.z, th.z, v4.w * th.w)));
+                    }
+                }
+                {
+                    const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float send = h16 ? pe[k] : pe[k + 4], keep = h16 ? pe[k + 4] : pe[k];
+                        pe[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
                     }
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) pe[jj] += __shfl_xor_sync(0xffffffffu, pe[jj], o);
+                    for (int k = 0; k < 2; ++k) {
+                        const float send = h8 ? pe[k] : pe[k + 2], keep = h8 ? pe[k + 2] : pe[k];
+                        pe[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
                     }
-                    if (lane < 4) {
-                        const int nl = n0 + lane;
-                        const float pv = lane == 0 ? pe[0] : (lane == 1 ? pe[1] : (lane == 2 ? pe[2] : pe[3]));
-                        if (nl < n_own) es[nl] = (n_lo + nl) < len ? pv : -INFINITY;
-                    }
+                    const float send = h4 ? pe[0] : pe[1], keep = h4 ? pe[1] : pe[0];
+                    float tot = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+                    tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+                    // this lane group (lane >> 2) now holds slot (bit 2) + 2 (bit 3) + 4 (bit 4)
+                    const int slot = ((lane >> 2) & 1) + 2 * ((lane >> 3) & 1) + 4 * ((lane >> 4) & 1);
+                    const int nl = widx + 14 * slot;
+                    if ((lane & 3) == 0 && slot < 6 && nl < n_own) es[nl] = (n_lo + nl) < len ? tot : -INFINITY;
                 }
             }
             fa_bar_workers();
@@ -768,6 +779,13 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                 float acc[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+                // the 14 tokens of a thread are the same for the whole warp (one token group per 64 threads): lane i computes the
+                // exponential of token i once, the FMA loop takes it by shuffle
+                float pmine = 0.f;
+                {
+                    const int n = tg + 7 * (lane < 2 * HB ? lane : 0);
+                    if (lane < 2 * HB && n < own_len) pmine = expf(es[n] - mloc);
+                }
 #pragma unroll
                 for (int hb = 0; hb < 2; ++hb) {
                     uint4 mv[HB];
@@ -779,8 +797,8 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
 #pragma unroll
                     for (int i = 0; i < HB; ++i) {
                         const int n = tg + 7 * (HB * hb + i);
+                        const float pexp = __shfl_sync(0xffffffffu, pmine, HB * hb + i);
                         if (n < own_len) {
-                            const float pexp = expf(es[n] - mloc);
                             acc[0] = fmaf(pexp, bf_lo(mv[i].x), acc[0]); acc[1] = fmaf(pexp, bf_hi(mv[i].x), acc[1]);
                             acc[2] = fmaf(pexp, bf_lo(mv[i].y), acc[2]); acc[3] = fmaf(pexp, bf_hi(mv[i].y), acc[3]);
                             acc[4] = fmaf(pexp, bf_lo(mv[i].z), acc[4]); acc[5] = fmaf(pexp, bf_hi(mv[i].z), acc[5]);

@@ -148,6 +148,12 @@ __global__ void __launch_bounds__(PCF64_THREADS, 1) k_lstm_chain_fwd(const PcFwd
     PcShared *sh = (PcShared *)(wsm + wbytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, j = blockIdx.x;
     const unsigned ncta = gridDim.x;
+    // launched in clusters of CS CTAs (1, 2 or 4): every CTA needs the SAME operand image each step, so rank r pulls only the
+    // slabs c = r (mod CS) out of L2 and multicasts them into the ring of every CTA of the cluster - the stream is bound by the
+    // aggregate L2 -> SM bandwidth (128 x 128 KB per step), which this divides by CS
+    uint32_t crank, csize;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < PC_MAXRING; ++s) { mbar_init(sh->full + s, 1); mbar_init(sh->empty + s, 1); }
@@ -165,6 +171,10 @@ __global__ void __launch_bounds__(PCF64_THREADS, 1) k_lstm_chain_fwd(const PcFwd
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sh->tmem_slot;
+    if (csize > 1) {        // every CTA's mbarriers exist before a peer's multicast can signal them
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
 
     if (warp == 16) {
         // ------------------------------------------------ TMA producer
@@ -181,9 +191,18 @@ __global__ void __launch_bounds__(PCF64_THREADS, 1) k_lstm_chain_fwd(const PcFwd
                 fence_proxy_async_global();       // other CTAs' generic-proxy stores of h -> this thread's async-proxy reads
                 pc_stamp(a.dbg, j, t, 7);
                 const uint8_t *src = (const uint8_t *)a.himg + (size_t)(t & 1) * img_bytes;
-                for (int c = 0; c < nchunk; ++c) {
-                    mbar_expect_tx(sh->full + c, PC_CHUNK_BYTES);
-                    tma_bulk_g2s(ring + (size_t)c * PC_CHUNK_BYTES, src + (size_t)c * PC_CHUNK_BYTES, PC_CHUNK_BYTES, sh->full + c);
+                if (csize == 1) {
+                    for (int c = 0; c < nchunk; ++c) {
+                        mbar_expect_tx(sh->full + c, PC_CHUNK_BYTES);
+                        tma_bulk_g2s(ring + (size_t)c * PC_CHUNK_BYTES, src + (size_t)c * PC_CHUNK_BYTES, PC_CHUNK_BYTES, sh->full + c);
+                    }
+                } else {
+                    // (a peer's bytes may be counted on a barrier before this CTA has armed it: the phase cannot complete until the
+                    // arrive below; the ring slots are free - every CTA of the grid passed its accumulator wait before the barrier)
+                    for (int c = (int)crank; c < nchunk; c += (int)csize)
+                        tma_bulk_g2s_mc(ring + (size_t)c * PC_CHUNK_BYTES, src + (size_t)c * PC_CHUNK_BYTES, PC_CHUNK_BYTES, sh->full + c,
+                                        (uint16_t)((1u << csize) - 1u));
+                    for (int c = 0; c < nchunk; ++c) mbar_expect_tx(sh->full + c, PC_CHUNK_BYTES);
                 }
                 pc_stamp(a.dbg, j, t, 1);
             }
@@ -597,12 +616,21 @@ inline long long *&pc_dbg_buffer() {
     return p;
 }
 
+inline int &pc_multicast() {   // cluster size wanted for the forward chain's multicast operand stream (debug option "multicast": 0 -> 1)
+    static int cs = 4;
+    return cs;
+}
+inline int pc_fwd_cluster(int H) {
+    const int grid = H / 8, want = pc_multicast();
+    return want >= 4 && grid % 4 == 0 ? 4 : (want >= 2 && grid % 2 == 0 ? 2 : 1);
+}
 inline bool pc_coresident(int H) {
     static int cached_H = -1;
     static bool cached = false;
     if (cached_H != H) {
         const int grid = H / 8;
-        const int fwd = max_resident_clusters(k_lstm_chain_fwd, PCF64_THREADS, pc_smem_bytes(H, false), 1, grid);
+        const int cs = grid % 4 == 0 ? 4 : (grid % 2 == 0 ? 2 : 1);          // the largest cluster pc_fwd_cluster may ask for
+        const int fwd = cs * max_resident_clusters(k_lstm_chain_fwd, PCF64_THREADS, pc_smem_bytes(H, false), cs, grid);
         const int bwd = max_resident_clusters(k_lstm_chain_bwd, PCF_THREADS, pc_smem_bytes(H, true), 4, grid);
         cached = fwd >= grid && 4 * bwd >= grid;
         cached_H = H;
@@ -620,7 +648,22 @@ inline int launch_lstm_chain_fwd(const PcFwdArgs &a_in, cudaStream_t st) {
         configured = smem;
     }
     GVX_CUDA(cudaMemsetAsync(a.bar, 0, sizeof(unsigned), st));
-    k_lstm_chain_fwd<<<a.H / 8, PCF64_THREADS, smem, st>>>(a);
+    {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(a.H / 8);
+        cfg.blockDim = dim3(PCF64_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = pc_fwd_cluster(a.H);
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        GVX_CUDA(cudaLaunchKernelEx(&cfg, k_lstm_chain_fwd, a));
+    }
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     return 0;
