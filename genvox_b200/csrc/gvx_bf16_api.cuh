@@ -126,7 +126,7 @@ int pack_weights_bf16(const Dims &d, const gvx_weights *w, float *packed, cudaSt
 // ---- bf16 training stash -----------------------------------------------------------------------------
 struct StashBfL {
     size_t FR, PRE1, PRE2, PM, CA, GA, CD, GD, ALIGN, CUMS, TH, CONVS, OUT, WPREV, CUM, XAI, XDI, XARM, XDRM, HCRM, PA, PD, PQ, ERR,
-        SEED, HIMG, BAR, XIMG, MEMB, BAR2, QBUF, CTX32, total;
+        SEED, HIMG, BAR, XIMG, MEMB, BAR2, QBUF, HQ, CTX32, total;
     size_t xai_stride, xdi_stride;     // bf16 elements per frame image
     int NPAD, KSa, KSd, KSq;
     StashBfL(const Dims &d, int B, int N, int T) {
@@ -156,6 +156,7 @@ struct StashBfL {
         MEMB = c.take(((size_t)B * N * d.E + 1) / 2);     // bf16 copy of the encoder memory (context operand)
         BAR2 = c.take(32 * 18);                    // 2 grid barriers + 16 row-group counters, one 128-byte line each
         QBUF = c.take((size_t)2 * 2 * 64 * d.D);   // 64-bit (value, tag) words
+        HQ = c.take(2 * fa_hq_words());            // 64-bit (h_att pair, tag) words: the query projection's input exchange
         CTX32 = c.take(TB * d.E);                  // fp32 attention context per frame (softmax backward of the persistent BPTT)
         total = c.o;
     }
@@ -432,7 +433,7 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
         f.pm = s + S.PM; f.memb = (const bf16 *)(s + S.MEMB);
         f.wlc = w->loc_conv_w; f.wldT = packed + PL.wldT; f.v = w->v_w; f.lengths = mem_lengths;
         f.align_out = s + S.ALIGN; f.cum_stash = s + S.CUMS; f.th_stash = s + S.TH; f.th_bf16 = 1; f.conv_stash = s + S.CONVS; f.ctx32_stash = s + S.CTX32;
-        f.bar = (unsigned *)(s + S.BAR2); f.qbuf = (unsigned long long *)(s + S.QBUF); f.err = err;
+        f.bar = (unsigned *)(s + S.BAR2); f.qbuf = (unsigned long long *)(s + S.QBUF); f.hq = (unsigned long long *)(s + S.HQ); f.err = err;
         f.drop = make_drop(seed, d.p_att, training);
         f.row_offset = row_offset; f.B = B; f.N = N; f.T = T;
         GVX_TRY(launch_att_chain_fwd(f, st));

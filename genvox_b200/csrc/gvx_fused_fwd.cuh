@@ -120,6 +120,8 @@ struct FaArgs {
                                  // slices of row group g delivered
     unsigned long long *qbuf;    // [2][64][D] ping-pong query exchange between the 8 CTAs of a row group: (value, step tag)
                                  // pairs in one 64-bit word, zero at launch
+    unsigned long long *hq;      // [2][64 rows][A/2] ping-pong h_att exchange for the query projection: (bf16 pair, step tag) words,
+                                 // zero at launch - the query warps poll the data itself instead of waiting for the grid barrier
     int *err;
     DropCfg drop;
     int row_offset, B, N, T;
@@ -593,10 +595,13 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
             // ============================================================ attention LSTM cell of step t
             if (epi) {
                 float4 pr[2];
+                float dm[2] = {1.f, 1.f};             // dropout multipliers of the two units: Philox, nothing to do with the accumulator
                 if (evalid) {
                     const float4 *pp = reinterpret_cast<const float4 *>(a.pre + ((size_t)t * B + eb) * 4 * FA_A + 4 * u0);
                     pr[0] = __ldcs(pp);
                     pr[1] = __ldcs(pp + 1);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) dm[i] = drop_mult(a.drop, SITE_ATT, (uint32_t)t, (uint32_t)(eb + a.row_offset), (uint32_t)(u0 + i));
                 }
                 // (the wait returns at once when the CTA is already draining; `ok` stays warp-uniform)
                 const bool ok = __all_sync(0xffffffffu, fa_wait_mbar(&sh->tmem_full, (uint32_t)t & 1u, &sh->dead, a.err, 36)) != 0;
@@ -628,11 +633,12 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                         const float gg = tanh_fast(acc[4 * i + 2] + pr[i].z + bi[i].z), go = sigmoid_fast(acc[4 * i + 3] + pr[i].w + bi[i].w);
                         const float cn = gf * cst[i] + gi * gg;
                         cst[i] = cn;
-                        hv[i] = go * tanh_fast(cn) * drop_mult(a.drop, SITE_ATT, (uint32_t)t, (uint32_t)(eb + a.row_offset), (uint32_t)(u0 + i));
+                        hv[i] = go * tanh_fast(cn) * dm[i];
                         ga[i] = make_float4(gi, gf, gg, go);
                     }
                     hp = pack_bf2(hv[0], hv[1]);
-                    // what the chain itself consumes first: the next step's operand image and the rows the query reads
+                    // what the chain itself consumes first: the tagged word the query projection polls, the next step's operand image
+                    st_relaxed_u64(a.hq + ((size_t)(t & 1) * PC_ROWS + eb) * (FA_A / 2) + (u0 >> 1), ((unsigned long long)(unsigned)(t + 1) << 32) | hp);
                     *reinterpret_cast<uint32_t *>(a.ximg + (size_t)((t + 1) & 1) * FA_IMG_BYTES + himg_off) = hp;
                     *reinterpret_cast<uint32_t *>(a.xdrm + ((size_t)t * B + eb) * a.Kd + u0) = hp;
                     fence_proxy_async_global();
@@ -649,18 +655,29 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
             }
 
             // ============================================================ attention of step t
-            if (tid == 0) fa_wait_gbar(bar1, ncta * (unsigned)(t + 1), &sh->dead, a.err, 37);
-            fa_bar_workers();                               // h_att_t of every unit is visible
-            if (tid == 0) { pc_stamp(a.dbg, j, t, 4); fa_mark(a.prog, 0, j, 8 * t + 2); }
             if (widx < 8) {   // query slice: q[4 rows][16 dims] partial over k in [128 widx, +128)
                 float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-                const __nv_bfloat16 *hrow = a.xdrm + ((size_t)t * B + qrow) * a.Kd + 128 * widx + 2 * tig;
+                // h_att_t comes straight from the cells that produce it: 16 (bf16 pair, tag) words per lane, polled until every tag
+                // says step t - no grid barrier, no release fence on the producer, no second round trip for the data
+                const unsigned long long *hsrc = a.hq + ((size_t)(t & 1) * PC_ROWS + qrow) * (FA_A / 2) + 64 * widx + tig;
                 uint32_t ha[8][2];
 #pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    ha[s][0] = g4 < 4 ? __ldcg(reinterpret_cast<const unsigned int *>(hrow + 16 * s)) : 0u;
-                    ha[s][1] = g4 < 4 ? __ldcg(reinterpret_cast<const unsigned int *>(hrow + 16 * s + 8)) : 0u;
+                for (int s = 0; s < 8; ++s) ha[s][0] = ha[s][1] = 0u;
+                if (g4 < 4) {
+                    fa_spin([&] {
+                        bool all = true;
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) {
+                            const unsigned long long w0 = ld_relaxed_u64(hsrc + 8 * s), w1 = ld_relaxed_u64(hsrc + 8 * s + 4);
+                            all = all && (unsigned)(w0 >> 32) == (unsigned)(t + 1) && (unsigned)(w1 >> 32) == (unsigned)(t + 1);
+                            ha[s][0] = (uint32_t)w0;
+                            ha[s][1] = (uint32_t)w1;
+                        }
+                        return all;
+                    }, &sh->dead, a.err, 37);
                 }
+                __syncwarp();
+                if (tid == 0) { pc_stamp(a.dbg, j, t, 4); fa_mark(a.prog, 0, j, 8 * t + 2); }
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
                     mma_bf16_16816(c0, ha[s][0], 0u, ha[s][1], 0u, wq[s][0][0], wq[s][0][1]);
@@ -939,6 +956,7 @@ __global__ void k_fa_pack_w(const float *__restrict__ Wa_packed, int Ka, int P, 
 }
 inline size_t fa_wimg_elems() { return (size_t)128 * FA_NSLAB * 2048; }
 inline size_t fa_ximg_bytes() { return (size_t)2 * FA_IMG_BYTES; }
+inline size_t fa_hq_words() { return (size_t)2 * PC_ROWS * (FA_A / 2); }
 
 inline bool fa_supported(const Dims &d, int B, int N) {
     static int sms = -1;
@@ -990,6 +1008,7 @@ inline int launch_att_chain_fwd(const FaArgs &a_in, cudaStream_t st) {
     }
     GVX_CUDA(cudaMemsetAsync(a.bar, 0, 32 * 18 * sizeof(unsigned), st));
     GVX_CUDA(cudaMemsetAsync(a.qbuf, 0, (size_t)2 * PC_ROWS * AF_D * sizeof(unsigned long long), st));
+    GVX_CUDA(cudaMemsetAsync(a.hq, 0, fa_hq_words() * sizeof(unsigned long long), st));
     k_att_chain_fwd<<<128, FA_THREADS, smem, st>>>(a);
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
