@@ -640,12 +640,14 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                     // what the chain itself consumes first: the tagged word the query projection polls, the next step's operand image
                     st_relaxed_u64(a.hq + ((size_t)(t & 1) * PC_ROWS + eb) * (FA_A / 2) + (u0 >> 1), ((unsigned long long)(unsigned)(t + 1) << 32) | hp);
                     *reinterpret_cast<uint32_t *>(a.ximg + (size_t)((t + 1) & 1) * FA_IMG_BYTES + himg_off) = hp;
-                    *reinterpret_cast<uint32_t *>(a.xdrm + ((size_t)t * B + eb) * a.Kd + u0) = hp;
                     fence_proxy_async_global();
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (tid == 0) { gbar_arrive(bar1); pc_stamp(a.dbg, j, t, 3); }
+                // the release (a fence that drains this SM's stores, then the counter) is only for the TMA thread of the NEXT step's
+                // h_att part: it is issued by a warp that has no query slice to compute, and before the stash-only stores
+                if (tid == 384) { gbar_arrive(bar1); pc_stamp(a.dbg, j, t, 3); }
                 if (ok && evalid) {
+                    *reinterpret_cast<uint32_t *>(a.xdrm + ((size_t)t * B + eb) * a.Kd + u0) = hp;
                     float4 *gs = reinterpret_cast<float4 *>(a.gates_stash + ((size_t)t * B + eb) * 4 * FA_A + 4 * u0);
                     gs[0] = ga[0];
                     gs[1] = ga[1];
@@ -860,6 +862,10 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                 }
             }
             if (tid == 0) { pc_stamp(a.dbg, j, t, 6); fa_mark(a.prog, 0, j, 8 * t + 4); }
+            float st_w = 0.f, st_c = 0.f, st_cx[8];          // results whose global stores are deferred past the grid-barrier arrive
+            uint4 st_v = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) st_cx[k] = 0.f;
             {   // combine the two halves of the row (always "half 0 + half 1": both CTAs get identical values)
                 const float m_s = xch[0], s_s = xch[1];
                 const float m_p = inbox[0], s_p = inbox[1];
@@ -867,13 +873,11 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                 const float a_s = m_s == -INFINITY ? 0.f : expf(m_s - M), a_p = m_p == -INFINITY ? 0.f : expf(m_p - M);
                 const float S = half == 0 ? s_s * a_s + s_p * a_p : s_p * a_p + s_s * a_s;
                 if (wtid < n_own) {
-                    const int n = wtid, ng = n_lo + n;
+                    const int n = wtid;
                     const float w = ps[n] * a_s / S;
                     const float c_old = wcat[G.NPS + AF_PAD + n];
-                    if (rvalid) {
-                        a.align_out[((size_t)row * T + t) * N + ng] = w;
-                        if (a.cum_stash) a.cum_stash[((size_t)row * T + t) * N + ng] = c_old;
-                    }
+                    st_w = w;
+                    st_c = c_old;
                     wcat[AF_PAD + n] = w;
                     wcat[G.NPS + AF_PAD + n] = c_old + w;
                 } else if (wtid >= 96 && wtid < 96 + AF_PAD) {
@@ -894,7 +898,6 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
 #pragma unroll
                     for (int k = 0; k < 8; ++k) oth[k] = inbox[2 + 16 + 8 * (wtid - 128) + k];
                     uint32_t pk[4];
-                    float cxs[8];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         float cx[2];
@@ -902,33 +905,44 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                         for (int q2 = 0; q2 < 2; ++q2) {
                             const float mine = ctxp[e0 + 2 * k + q2] * a_s, other = oth[2 * k + q2] * a_p;
                             cx[q2] = (half == 0 ? mine + other : other + mine) / S;
-                            cxs[2 * k + q2] = cx[q2];
+                            st_cx[2 * k + q2] = cx[q2];
                         }
                         pk[k] = pack_bf2(cx[0], cx[1]);
                     }
-                    const uint4 v = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    st_v = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     if (rvalid) {
+                        // the one store the chain itself waits for: ctx_t in the next step's operand image
                         const int kc = (FA_A + e0) >> 3;                             // 16-byte chunk of the K range
                         *reinterpret_cast<uint4 *>(a.ximg + (size_t)((t + 1) & 1) * FA_IMG_BYTES + (size_t)(kc >> 3) * PC_CHUNK_BYTES + row * 128 +
-                                                   (((kc & 7) ^ (row & 7)) << 4)) = v;
+                                                   (((kc & 7) ^ (row & 7)) << 4)) = st_v;
                         fence_proxy_async_global();
-                        *reinterpret_cast<uint4 *>(a.xdrm + ((size_t)t * B + row) * a.Kd + FA_A + e0) = v;
-                        *reinterpret_cast<uint4 *>(a.hcrm + ((size_t)t * B + row) * a.Kp + a.H + e0) = v;
-                        if (t + 1 < T) *reinterpret_cast<uint4 *>(a.xarm + ((size_t)(t + 1) * B + row) * a.Ka + a.P + e0) = v;
-                        if (a.ctx32_stash) {
-                            float4 *cd = reinterpret_cast<float4 *>(a.ctx32_stash + ((size_t)t * B + row) * FA_E + e0);
-                            cd[0] = make_float4(cxs[0], cxs[1], cxs[2], cxs[3]);
-                            cd[1] = make_float4(cxs[4], cxs[5], cxs[6], cxs[7]);
-                        }
                     }
                 }
             }
             fa_bar_workers();
-            if (tid == 0) {
+            if (tid == 384) {
                 gbar_arrive(bar2);
                 pc_stamp(a.dbg, j, t, 7);
                 fa_mark(a.prog, 0, j, 8 * t + 5);
                 if (j == 0 && a.dbg && t < 1024) a.dbg[t * 32 + 8] = fa_globaltimer();
+            }
+            // ---- everything only the stashes / later GEMMs read goes out after the release
+            if (rvalid) {
+                if (wtid < n_own) {
+                    const int ng = n_lo + wtid;
+                    a.align_out[((size_t)row * T + t) * N + ng] = st_w;
+                    if (a.cum_stash) a.cum_stash[((size_t)row * T + t) * N + ng] = st_c;
+                } else if (wtid >= 128 && wtid < 160) {
+                    const int e0 = half * (FA_E / 2) + 8 * (wtid - 128);
+                    *reinterpret_cast<uint4 *>(a.xdrm + ((size_t)t * B + row) * a.Kd + FA_A + e0) = st_v;
+                    *reinterpret_cast<uint4 *>(a.hcrm + ((size_t)t * B + row) * a.Kp + a.H + e0) = st_v;
+                    if (t + 1 < T) *reinterpret_cast<uint4 *>(a.xarm + ((size_t)(t + 1) * B + row) * a.Ka + a.P + e0) = st_v;
+                    if (a.ctx32_stash) {
+                        float4 *cd = reinterpret_cast<float4 *>(a.ctx32_stash + ((size_t)t * B + row) * FA_E + e0);
+                        cd[0] = make_float4(st_cx[0], st_cx[1], st_cx[2], st_cx[3]);
+                        cd[1] = make_float4(st_cx[4], st_cx[5], st_cx[6], st_cx[7]);
+                    }
+                }
             }
         }
     }
