@@ -422,7 +422,6 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
         ProfScope ps(PS_ATTENTION, st);
         FaArgs f;
         memset(&f, 0, sizeof(f));
-        f.loc_mma = fa_loc_mma();
         f.Wimg = (const bf16 *)(packed + BL.WaRecI);
         f.pre = s + S.GA; f.bias = packed + PL.ba;
         f.ximg = (uint8_t *)(s + S.XIMG);
@@ -960,7 +959,6 @@ extern "C" int gvx_debug_option(const char *name, int value) {
     if (!strcmp(name, "fused")) gvx::fa_mode() = value;
     else if (!strcmp(name, "persistent")) gvx::pc_mode() = value;
     else if (!strcmp(name, "multicast")) gvx::pc_multicast() = value < 0 ? 4 : (value == 0 ? 1 : (value == 1 ? 4 : value));
-    else if (!strcmp(name, "locmma")) gvx::fa_loc_mma() = value < 0 ? 1 : value;
     else { snprintf(gvx::g_err, sizeof(gvx::g_err), "gvx_debug_option: unknown option %s", name); return 1; }
     return 0;
 }

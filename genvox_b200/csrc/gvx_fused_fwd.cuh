@@ -40,7 +40,7 @@ constexpr int FA_NW = 448;                     // worker threads: every warp exc
 constexpr int FA_A = 1024, FA_E = 512;
 constexpr int FA_HSLAB = FA_A / 64;            // 16 K slabs of h_att
 constexpr int FA_NSLAB = (FA_A + FA_E) / 64;   // 24 K slabs of [h_att | ctx]
-constexpr int FA_RING = 4;
+constexpr int FA_RING = 5;                     // operand-image slots in flight (8 KB each): the stream is latency x depth bound
 constexpr int FA_MAXN = 160;
 constexpr int FA_IMG_BYTES = FA_NSLAB * PC_CHUNK_BYTES;     // one operand image: [24][64 rows][128 B]
 constexpr int FA_CLUSTER = 2;                 // the two CTAs (token halves) of one batch row
@@ -64,7 +64,7 @@ struct FaShared {
 };
 
 struct FaSmem {      // byte offsets from the 1 KB aligned base
-    int ring, wsm, lp, convT, wldT, wlc, ctxp, wcat, e, p, v, qfull, qred, xch, inbox, gt, sh, total;
+    int ring, wsm, lp, wlcB, wldB, ctxp, wcat, e, p, v, qfull, qred, xch, inbox, gt, sh, total;
     __host__ __device__ explicit FaSmem(int N) {
         const FaGeom g(N);
         int o = 0;
@@ -72,9 +72,8 @@ struct FaSmem {      // byte offsets from the 1 KB aligned base
         ring = take(FA_RING * PC_CHUNK_BYTES);
         wsm = take(FA_NSLAB * 4096);           // also absorbs the 64-row over-read of the last ring slot
         lp = take(g.NH * FA_LPS * 4 > 7 * FA_E * 4 ? g.NH * FA_LPS * 4 : 7 * FA_E * 4);     // also the [7][512] partial contexts
-        convT = take(AF_F * g.NH * 4 > 8192 ? AF_F * g.NH * 4 : 8192);     // also the 8 KB of conv B fragments (tensor-core location phase)
-        wldT = take(AF_F * AF_D * 4);
-        wlc = take(AF_F * 2 * AF_KS * 4);
+        wlcB = take(16 * 32 * 16);             // location conv weights as mma.sync B fragments (hi, lo): [4 k-steps][4 n-tiles][32 lanes] uint4
+        wldB = take(32 * 32 * 16);             // location dense weights likewise: [2 k-steps][16 n-tiles][32 lanes] uint4
         ctxp = take(FA_E * 4);
         wcat = take(2 * g.NPS * 4);
         e = take(g.NH * 4);
@@ -127,7 +126,6 @@ struct FaArgs {
     int row_offset, B, N, T;
     long long *dbg;
     int *prog;                   // optional [3][128] progress markers (post-mortem of a stuck launch)
-    int loc_mma;                 // 1: location conv + dense on mma.sync (hi + lo bf16 operands), 0: FFMA (debug option "locmma")
 };
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
@@ -248,8 +246,7 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
     const FaGeom G(N);
     const FaSmem L(N);
     uint8_t *ring = smem + L.ring, *wsm = smem + L.wsm;
-    float *lp = (float *)(smem + L.lp), *convT = (float *)(smem + L.convT), *wldT = (float *)(smem + L.wldT);
-    float *wlc = (float *)(smem + L.wlc), *ctxp = (float *)(smem + L.ctxp);
+    float *lp = (float *)(smem + L.lp), *ctxp = (float *)(smem + L.ctxp);
     float *part = lp;        // [7][512] partial contexts: lp is dead between the energies and the next location phase
     float *wcat = (float *)(smem + L.wcat), *es = (float *)(smem + L.e), *ps = (float *)(smem + L.p);
     float *vs = (float *)(smem + L.v), *qfull = (float *)(smem + L.qfull), *qred = (float *)(smem + L.qred);
@@ -288,9 +285,9 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // tensor-core location phase: both weight matrices live in shared memory as ready-made mma.sync B fragments, one uint4
-    // {b0 hi, b1 hi, b0 lo, b1 lo} per (k-step, n-tile, lane); they take the place of the fp32 copies (and of convT)
-    uint4 *wlcB = reinterpret_cast<uint4 *>(smem + L.convT), *wldB = reinterpret_cast<uint4 *>(smem + L.wldT);
-    if (a.loc_mma) {
+    // {b0 hi, b1 hi, b0 lo, b1 lo} per (k-step, n-tile, lane)
+    uint4 *wlcB = reinterpret_cast<uint4 *>(smem + L.wlcB), *wldB = reinterpret_cast<uint4 *>(smem + L.wldB);
+    {
         for (int e = tid; e < 16 * 32; e += FA_THREADS) {          // conv: k = (channel, tap) in 4 steps of 16, n = filter
             const int ln = e & 31, nt = (e >> 5) & 3, ks = e >> 7, gg = ln >> 2, tg = ln & 3;
             const int c = ks >> 1, f = 8 * nt + gg, tap0 = 16 * (ks & 1) + 2 * tg;
@@ -306,9 +303,6 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
             const uint32_t h0 = pack_bf2(x0, x1), h1 = pack_bf2(x8, x9);
             wldB[e] = make_uint4(h0, h1, pack_bf2(x0 - bf_lo(h0), x1 - bf_hi(h0)), pack_bf2(x8 - bf_lo(h1), x9 - bf_hi(h1)));
         }
-    } else {
-        for (int i = tid; i < AF_F * 2 * AF_KS; i += FA_THREADS) wlc[i] = a.wlc[i];
-        for (int i = tid; i < AF_F * AF_D / 4; i += FA_THREADS) reinterpret_cast<float4 *>(wldT)[i] = reinterpret_cast<const float4 *>(a.wldT)[i];
     }
     if (tid < AF_D) vs[tid] = a.v[tid];
     for (int i = tid; i < 2 * G.NPS; i += FA_THREADS) wcat[i] = 0.f;       // w_{-1} = cum_{-1} = 0 (tacotron2.py:303-315)
@@ -423,10 +417,10 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
             for (int i = wtid; i < n_own * (AF_D / 4); i += FA_NW) cp_async16(lp + (i >> 5) * FA_LPS + (i & 31) * 4, pm_own + (size_t)i * 4, true);
             cp_async_commit();
         };
-        if (a.loc_mma) pm_prefetch();
+        pm_prefetch();
         for (int t = 0; t < T; ++t) {
             // ============================================================ location features of step t (w_{t-1}, cum_{t-1})
-            if (a.loc_mma) {
+            {
                 // conv (Toeplitz window of the two zero-padded rows . W_loc_conv) and dense (. W_loc_dense) chained on mma.sync: the
                 // conv accumulator fragments of a 16-token tile ARE the A fragments of the dense contraction.  Every fp32 operand is
                 // split hi + lo (bf16 each) and the lo x lo term dropped: ~2^-17 relative, i.e. fp32-grade like the FFMA path.
@@ -521,74 +515,6 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                     }
                 }
                 if (warp == 6 && lane == 0) pc_stamp(a.dbg, j, t, 20);
-            } else {
-                for (int task = wtid; task < AF_F * G.nblk; task += FA_NW) {
-                    const int f = task / G.nblk, n0 = (task - f * G.nblk) * 8;
-                    float acc[8];
-    #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) acc[jj] = 0.f;
-    #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        float x[40];
-                        const float4 *xr = reinterpret_cast<const float4 *>(wcat + c * G.NPS + n0);
-    #pragma unroll
-                        for (int i = 0; i < 10; ++i) {
-                            const float4 t4 = xr[i];
-                            x[4 * i] = t4.x; x[4 * i + 1] = t4.y; x[4 * i + 2] = t4.z; x[4 * i + 3] = t4.w;
-                        }
-                        const float *wr = wlc + (f * 2 + c) * AF_KS;
-    #pragma unroll
-                        for (int k = 0; k < AF_KS; ++k) {
-                            const float wk = wr[k];
-    #pragma unroll
-                            for (int jj = 0; jj < 8; ++jj) acc[jj] = fmaf(wk, x[jj + k], acc[jj]);
-                        }
-                    }
-                    float4 *dst = reinterpret_cast<float4 *>(convT + f * G.NH + n0);
-                    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-                }
-                fa_bar_workers();
-                if (tid == 0) pc_stamp(a.dbg, j, t, 19);
-                if (rvalid && a.conv_stash) {
-                    float *cs = a.conv_stash + (((size_t)t * B + row) * N + n_lo) * AF_F;
-                    for (int i = wtid; i < n_own * AF_F; i += FA_NW) cs[i] = convT[(i & 31) * G.NH + (i >> 5)];
-                }
-                {   // location dense + processed memory -> lp[n][d]; a warp takes 4 tokens, a lane 4 attention dims.  The processed
-                    // memory rows (L2 resident, read-only) are requested first and land while the FFMA loop runs.
-                    const float *pm_b = a.pm + ((size_t)rowc * N + n_lo) * AF_D;
-                    const int ngrp = (n_own + 3) / 4;
-                    for (int grp = widx; grp < ngrp; grp += 14) {
-                        const int n0 = grp * 4;
-                        float4 pmv[4];
-    #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj)
-                            pmv[jj] = n0 + jj < n_own ? __ldg(reinterpret_cast<const float4 *>(pm_b + (size_t)(n0 + jj) * AF_D + lane * 4))
-                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-                        float loc[4][4];
-    #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj)
-    #pragma unroll
-                            for (int i = 0; i < 4; ++i) loc[jj][i] = 0.f;
-    #pragma unroll 8
-                        for (int f = 0; f < AF_F; ++f) {
-                            const float4 wd = *reinterpret_cast<const float4 *>(wldT + f * AF_D + lane * 4);
-                            const float4 c4 = *reinterpret_cast<const float4 *>(convT + f * G.NH + n0);
-                            const float cj[4] = {c4.x, c4.y, c4.z, c4.w};
-    #pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) {
-                                loc[jj][0] = fmaf(cj[jj], wd.x, loc[jj][0]);
-                                loc[jj][1] = fmaf(cj[jj], wd.y, loc[jj][1]);
-                                loc[jj][2] = fmaf(cj[jj], wd.z, loc[jj][2]);
-                                loc[jj][3] = fmaf(cj[jj], wd.w, loc[jj][3]);
-                            }
-                        }
-    #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj)
-                            *reinterpret_cast<float4 *>(lp + (size_t)(n0 + jj) * FA_LPS + lane * 4) =
-                                make_float4(loc[jj][0] + pmv[jj].x, loc[jj][1] + pmv[jj].y, loc[jj][2] + pmv[jj].z, loc[jj][3] + pmv[jj].w);
-                    }
-                }
             }
             if (tid == 0) pc_stamp(a.dbg, j, t, 12);
 
@@ -836,7 +762,7 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                           ((part[4 * FA_E + e] + part[5 * FA_E + e]) + part[6 * FA_E + e]);
             fa_bar_workers();
             if (tid == 0) pc_stamp(a.dbg, j, t, 15);
-            if (a.loc_mma && t + 1 < T) pm_prefetch();       // lp (= the partial contexts) is dead from here on
+            if (t + 1 < T) pm_prefetch();       // lp (= the partial contexts) is dead from here on
             // ---- exchange with the peer CTA of the row: each side PUSHES what the other needs (local max / sum, the 15 halo
             // exponentials next to the peer's token range, the peer's half of the context partial) and waits for its own inbox
             if (tid == 0) mbar_expect_tx(&sh->sbar, kInboxBytes);
@@ -992,10 +918,6 @@ inline bool fa_supported(const Dims &d, int B, int N) {
         cached_smem = smem;
     }
     return cached;
-}
-inline int &fa_loc_mma() {     // location phase of k_att_chain_fwd on mma.sync (1, default) or FFMA (0): debug option "locmma"
-    static int on = 1;
-    return on;
 }
 inline int &fa_mode() {        // -1 = not yet read from the environment, 0 = off, 1 = on
     static int on = -1;
