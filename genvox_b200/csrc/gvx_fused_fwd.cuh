@@ -361,6 +361,7 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                     umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
                     umma_commit(sh->empty + slot);
                     if (++slot == FA_RING) { slot = 0; ph ^= 1u; }
+                    if (c == FA_HSLAB) pc_stamp(a.dbg, j, t, 21);                      // first ctx slab of step t consumed
                     if (c == 0 && t > 0) pc_stamp(a.dbg, j, t - 1, 16);              // first h_att slab of step t has landed
                     if (c == FA_HSLAB - 1 && t > 0) pc_stamp(a.dbg, j, t - 1, 17);   // h_att part issued (during step t-1's attention)
                 }

@@ -63,7 +63,7 @@ if T > 4:
     for i, n in enumerate(names):
         print(f"   {n:18s} +{np.median(x[2:, i] - x[2:, 0]):8.0f} cyc")
     print(f"   loc_phase_done     +{np.median(x[2:, 12] - x[2:, 0]):8.0f} cyc   (started at the previous gbar2_arrive)")
-    for i, n in ((13, "energies_done"), (14, "ctx_partial_done"), (15, "ctxp_sum_done"), (16, "next_hatt_first_mma"), (17, "next_hatt_mma_issued"), (18, "mma_done(MMA thr)"), (19, "loc_conv_done"), (20, "loc_tiles_done(w6)")):
+    for i, n in ((13, "energies_done"), (14, "ctx_partial_done"), (15, "ctxp_sum_done"), (16, "next_hatt_first_mma"), (17, "next_hatt_mma_issued"), (18, "mma_done(MMA thr)"), (19, "loc_conv_done"), (20, "loc_tiles_done(w6)"), (21, "first_ctx_slab_mma")):
         print(f"   {n:18s} +{np.median(x[2:, i] - x[2:, 0]):8.0f} cyc")
     print("   next ctx_part_go   +%8.0f cyc" % np.median(x[3:, 0] - x[2:-1, 0]))
 
