@@ -148,12 +148,6 @@ __global__ void __launch_bounds__(PCF64_THREADS, 1) k_lstm_chain_fwd(const PcFwd
     PcShared *sh = (PcShared *)(wsm + wbytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, j = blockIdx.x;
     const unsigned ncta = gridDim.x;
-    // launched in clusters of CS CTAs (1, 2 or 4): every CTA needs the SAME operand image each step, so rank r pulls only the
-    // slabs c = r (mod CS) out of L2 and multicasts them into the ring of every CTA of the cluster - the stream is bound by the
-    // aggregate L2 -> SM bandwidth (128 x 128 KB per step), which this divides by CS
-    uint32_t crank, csize;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
-    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < PC_MAXRING; ++s) { mbar_init(sh->full + s, 1); mbar_init(sh->empty + s, 1); }
@@ -171,10 +165,6 @@ __global__ void __launch_bounds__(PCF64_THREADS, 1) k_lstm_chain_fwd(const PcFwd
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sh->tmem_slot;
-    if (csize > 1) {        // every CTA's mbarriers exist before a peer's multicast can signal them
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    }
 
     if (warp == 16) {
         // ------------------------------------------------ TMA producer
@@ -191,18 +181,9 @@ __global__ void __launch_bounds__(PCF64_THREADS, 1) k_lstm_chain_fwd(const PcFwd
                 fence_proxy_async_global();       // other CTAs' generic-proxy stores of h -> this thread's async-proxy reads
                 pc_stamp(a.dbg, j, t, 7);
                 const uint8_t *src = (const uint8_t *)a.himg + (size_t)(t & 1) * img_bytes;
-                if (csize == 1) {
-                    for (int c = 0; c < nchunk; ++c) {
-                        mbar_expect_tx(sh->full + c, PC_CHUNK_BYTES);
-                        tma_bulk_g2s(ring + (size_t)c * PC_CHUNK_BYTES, src + (size_t)c * PC_CHUNK_BYTES, PC_CHUNK_BYTES, sh->full + c);
-                    }
-                } else {
-                    // (a peer's bytes may be counted on a barrier before this CTA has armed it: the phase cannot complete until the
-                    // arrive below; the ring slots are free - every CTA of the grid passed its accumulator wait before the barrier)
-                    for (int c = (int)crank; c < nchunk; c += (int)csize)
-                        tma_bulk_g2s_mc(ring + (size_t)c * PC_CHUNK_BYTES, src + (size_t)c * PC_CHUNK_BYTES, PC_CHUNK_BYTES, sh->full + c,
-                                        (uint16_t)((1u << csize) - 1u));
-                    for (int c = 0; c < nchunk; ++c) mbar_expect_tx(sh->full + c, PC_CHUNK_BYTES);
+                for (int c = 0; c < nchunk; ++c) {
+                    mbar_expect_tx(sh->full + c, PC_CHUNK_BYTES);
+                    tma_bulk_g2s(ring + (size_t)c * PC_CHUNK_BYTES, src + (size_t)c * PC_CHUNK_BYTES, PC_CHUNK_BYTES, sh->full + c);
                 }
                 pc_stamp(a.dbg, j, t, 1);
             }
@@ -289,6 +270,188 @@ __global__ void __launch_bounds__(PCF64_THREADS, 1) k_lstm_chain_fwd(const PcFwd
             asm volatile("bar.sync 1, 512;" ::: "memory");
             // release at gpu scope is cumulative over the stores ordered before it by the CTA barrier
             if (threadIdx.x == 0) { gbar_arrive(a.bar); pc_stamp(a.dbg, j, t, 6); }
+            if (ok && valid) {
+                if (a.gates_stash) *reinterpret_cast<float4 *>(a.gates_stash + ((size_t)t * a.B + b) * 4 * H + 4 * u) = ga;
+                a.c_stash[((size_t)(t + 1) * a.B + b) * H + u] = c;
+                if (writer) {
+#pragma unroll
+                    for (int o = 0; o < 2; ++o) {
+                        const PcOut &d = a.out[o];
+                        if (d.p && t + d.toff < T)
+                            *reinterpret_cast<uint32_t *>(d.p + (size_t)(t + d.toff) * d.tstride + (size_t)b * d.ld + d.koff + u) = hp;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(32) : "memory");
+    }
+}
+
+// Forward chain, operands swapped (the default).  The two halves of the batch never meet in the recurrence, so CTA
+// (jc, rh) = (j >> 1, j & 1) owns SIXTEEN hidden units (64 gate rows: the UMMA M side, 128 KB of W_hh resident) for the 32 batch
+// rows of half rh (the N side): it needs only its half of the h image - 64 KB per step - and the step barrier only joins the 64
+// CTAs of a half.  Two measured facts shape the step (profiles/chain_timeline.py, GVX_EXP experiments):
+//   * what bounded the TMA-fed version (one bulk copy + one mbarrier wait + 4 MMAs per 64-column slab, ~280 cycles per slab
+//     whether the slab is 4, 8 or 16 KB, whatever the MMA shape, with 1 or 4 accumulators) was the single-thread issue loop
+//     itself: ~45 dependent instructions per slab.  The 512 epilogue threads are idle at that moment, so THEY fetch the half image
+//     with 16-byte cp.async (64 KB in ~1.4k cycles), and the issuer then fires all 64 MMAs from one unrolled block with
+//     immediate descriptor offsets;
+//   * the image is private to this kernel: [ping-pong][batch half][slab][32 rows][128 B], SWIZZLE_128B inside a slab.
+//   UMMA 64 x 32 x 16: A = weight slab [64 gate rows][64 k] (resident), B = image slab [32 batch rows][64 k];
+//   accumulator D[gate row m][batch row n]: m -> lane (m & 15) of TMEM quadrant m >> 4, n -> column.
+//   Epilogue warp w reads quadrant w & 3, columns 8 (w >> 2) .. +7, and the [64 x 32] tile is transposed through shared
+//   memory ([batch row][gate row], stride 68) so that the cell runs with thread = (batch row, unit), unit fastest.
+__global__ void __launch_bounds__(PCF64_THREADS, 1) k_lstm_chain_fwd_swap(const PcFwdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int H = a.H, T = a.T;
+    const int nchunk = (H + 63) / 64;
+    const int img_bytes = nchunk * PC_CHUNK_BYTES;         // one h image (both batch halves)
+    const uint32_t wbytes = (uint32_t)nchunk * 8192;       // [slab][64 gate rows][128 B]
+    constexpr uint32_t SLOT = 32 * 128;                    // one slab of a batch half: 32 rows x 128 B
+    uint8_t *wsm = smem;
+    uint8_t *ring = wsm + wbytes;
+    PcShared *sh = (PcShared *)(ring + (size_t)nchunk * SLOT);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, j = blockIdx.x;
+    const int jc = j >> 1, rh = j & 1;
+    const unsigned nhalf = gridDim.x >> 1;                 // CTAs that share a batch half = arrivals per barrier
+    unsigned *bar = a.bar + 32 * rh;                       // one counter per batch half, 128 B apart
+
+    if (threadIdx.x == 0) {
+        mbar_init(sh->full + 0, 1);                        // "the half image of this step is in shared memory"
+        mbar_init(&sh->tmem_full, 1);
+        mbar_init(&sh->wbar, 1);
+        sh->dead = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_slot)), "n"(32) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sh->tmem_slot;
+
+    if (warp == 16) {
+        // ------------------------------------------------ the resident weights, once
+        if (elect_one()) {
+            mbar_expect_tx(&sh->wbar, wbytes);
+            const uint8_t *wsrc = (const uint8_t *)a.Wimg + (size_t)jc * wbytes;
+            for (uint32_t off = 0; off < wbytes; off += 16384) {
+                const uint32_t n = wbytes - off < 16384 ? wbytes - off : 16384;
+                tma_bulk_g2s(wsm + off, wsrc + off, n, &sh->wbar);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 17) {
+        // ------------------------------------------------ MMA issuer
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(64, 32);
+            bool ok = pc_mbar_wait(&sh->wbar, 0, &sh->dead, a.err, 13);
+            const uint64_t a0 = umma_desc_sw128(smem_u32(wsm)), b0 = umma_desc_sw128(smem_u32(ring));
+            for (int t = 0; t < T && ok; ++t) {
+                if (!pc_mbar_wait(sh->full + 0, (uint32_t)t & 1u, &sh->dead, a.err, 14)) break;
+                pc_stamp(a.dbg, j, t, 8);
+                tc_fence_after();
+                // descriptors advance in 16-byte units: slab stride 8 KB (A) / 4 KB (B), 32 B per K = 16 step
+                if (nchunk == 16) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const uint64_t ad = a0 + (uint64_t)(c * (8192 >> 4)), bd = b0 + (uint64_t)(c * (SLOT >> 4));
+                        umma_bf16(tmem_base, ad, bd, idesc, c > 0 ? 1u : 0u);
+                        umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
+                        umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
+                        umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
+                    }
+                } else {
+                    for (int c = 0; c < nchunk; ++c) {
+                        const uint64_t ad = a0 + (uint64_t)(c * (8192 >> 4)), bd = b0 + (uint64_t)(c * (SLOT >> 4));
+                        umma_bf16(tmem_base, ad, bd, idesc, c > 0 ? 1u : 0u);
+                        umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
+                        umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
+                        umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
+                    }
+                }
+                umma_commit(&sh->tmem_full);
+                pc_stamp(a.dbg, j, t, 2);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------ image loaders + epilogue
+        constexpr int GS = 68;                             // tile stride: [32 batch rows][64 gate rows + 4]
+        float *gt = (float *)(((uintptr_t)(sh + 1) + 15) & ~(uintptr_t)15);
+        const int e = threadIdx.x;                         // 0 .. 511
+        const int bl = e >> 4, lu = e & 15, b = 32 * rh + bl, u = 16 * jc + lu;
+        const bool valid = b < a.B;
+        const int mrow = (warp & 3) * 16 + (lane & 15), cq = warp >> 2;       // TMEM side: gate row / column octet of this thread
+        float c = valid ? a.c_stash[(size_t)b * H + u] : 0.f;
+        const float4 bi = a.bias ? *reinterpret_cast<const float4 *>(a.bias + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(8 * cq);
+        // 2-byte slot of (row b, unit u) in the swizzled h image: slab u / 64, 16-byte chunk (u % 64) / 8
+        const size_t himg_off = ((size_t)rh * nchunk + (jc >> 2)) * SLOT + bl * 128 + (((2 * (jc & 3) + (lu >> 3)) ^ (bl & 7)) << 4) + 2 * (lu & 7);
+        const int nvec = nchunk * (int)SLOT / 16;
+        bool ok = true;
+        for (int t = 0; t < T; ++t) {
+            float4 pr = make_float4(0.f, 0.f, 0.f, 0.f);
+            float dm = 1.f;
+            if (valid) {
+                pr = __ldcs(reinterpret_cast<const float4 *>(a.pre + ((size_t)t * a.B + b) * 4 * H + 4 * u));
+                dm = drop_mult(a.drop, a.site, (uint32_t)t, (uint32_t)(b + a.row_offset), (uint32_t)u);     // before the wait: off the chain
+            }
+            // ---- h_{t-1} of this batch half -> shared memory
+            if (t > 0 && threadIdx.x == 0 && ok) gbar_wait(bar, nhalf * (unsigned)t, &sh->dead, a.err, 11);
+            if (threadIdx.x == 0) pc_stamp(a.dbg, j, t, 0);
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            {
+                const uint8_t *src = (const uint8_t *)a.himg + (size_t)(t & 1) * img_bytes + (size_t)rh * nchunk * SLOT;
+                for (int i = e; i < nvec; i += 512) cp_async16(ring + (size_t)i * 16, src + (size_t)i * 16, true);
+                cp_async_commit();
+                cp_async_wait<0>();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> the MMA's async-proxy reads
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (threadIdx.x == 0) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sh->full + 0)) : "memory");
+                pc_stamp(a.dbg, j, t, 1);
+            }
+            if (ok) ok = __all_sync(0xffffffffu, pc_mbar_wait(&sh->tmem_full, (uint32_t)t & 1u, &sh->dead, a.err, 15)) != 0;
+            if (threadIdx.x == 0) pc_stamp(a.dbg, j, t, 3);
+            if (ok) {
+                float acc[8];
+                tc_fence_after();
+                tmem_ld8(taddr, acc);
+                tc_fence_before();
+                if (lane < 16) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) gt[(8 * cq + i) * GS + mrow] = acc[i];
+                }
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            float4 ga = make_float4(0.f, 0.f, 0.f, 0.f);
+            float hv = 0.f;
+            if (ok && valid) {
+                const float4 g4 = *reinterpret_cast<const float4 *>(gt + bl * GS + 4 * lu);
+                const float gi = sigmoidf_(g4.x + pr.x + bi.x), gf = sigmoidf_(g4.y + pr.y + bi.y);
+                const float gg = tanhf(g4.z + pr.z + bi.z), go = sigmoidf_(g4.w + pr.w + bi.w);
+                c = gf * c + gi * gg;
+                hv = go * tanhf(c) * dm;
+                ga = make_float4(gi, gf, gg, go);
+            }
+            // two units per 4-byte store: the even lane of a unit pair writes both halves
+            const float hv_hi = __shfl_down_sync(0xffffffffu, hv, 1);
+            const uint32_t hp = pack_bf2(hv, hv_hi);
+            const bool writer = ok && valid && (lu & 1) == 0;
+            if (writer) *reinterpret_cast<uint32_t *>((uint8_t *)a.himg + (size_t)((t + 1) & 1) * img_bytes + himg_off) = hp;
+            if (threadIdx.x == 0) pc_stamp(a.dbg, j, t, 4);
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            // release at gpu scope is cumulative over the stores ordered before it by the CTA barrier
+            if (threadIdx.x == 0) { gbar_arrive(bar); pc_stamp(a.dbg, j, t, 6); }
             if (ok && valid) {
                 if (a.gates_stash) *reinterpret_cast<float4 *>(a.gates_stash + ((size_t)t * a.B + b) * 4 * H + 4 * u) = ga;
                 a.c_stash[((size_t)(t + 1) * a.B + b) * H + u] = c;
@@ -528,7 +691,16 @@ __global__ void k_pc_pack_w(const float *__restrict__ w_hh, int ld, int H, int m
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int j = (int)(i / per_cta);
         const int rem = (int)(i - (size_t)j * per_cta);
-        const int slab = rem >> 11, r = (rem >> 6) & 31, cpos = (rem >> 3) & 7, e = rem & 7;
+        int slab = rem >> 11, r = (rem >> 6) & 31, cpos = (rem >> 3) & 7, e = rem & 7;
+        if (mode == 2) {     // forward, operands swapped: block jc = 16 units, [slab][64 rows m = 4*lu+g][64]; two "CTAs" of this loop per block
+            const size_t per_blk = 2 * per_cta;
+            const int jc = (int)(i / per_blk), rm = (int)(i - (size_t)jc * per_blk);
+            slab = rm >> 12;
+            const int m = (rm >> 6) & 63;
+            const int kk = slab * 64 + ((cpos ^ (m & 7)) << 3) + e;
+            img[i] = __float2bfloat16(kk < H ? w_hh[(size_t)((m & 3) * H + 16 * jc + (m >> 2)) * ld + kk] : 0.f);
+            continue;
+        }
         const int k = slab * 64 + ((cpos ^ (r & 7)) << 3) + e;
         float v = 0.f;
         if (k < H) {
@@ -554,6 +726,10 @@ inline size_t pc_smem_bytes(int H, bool bwd) {
     // + 8 KB: the M = 128 MMA reads 64 rows past the last ring slot (ignored accumulator lanes) - keep that inside the allocation
     // (forward: + the [64][36] fp32 tile the epilogue re-maps its threads through)
     return (size_t)R * PC_CHUNK_BYTES + (size_t)nchunk * 4096 + (bwd ? 4 * 8 * 68 * 4 + 256 : PC_ROWS * 36 * 4) + sizeof(PcShared) + 8192 + 1024;
+}
+inline size_t pc_smem_bytes_swap(int H) {       // k_lstm_chain_fwd_swap: resident 64-row weight slabs + half-image ring + the [32][68] tile
+    const int nchunk = (H + 63) / 64;
+    return (size_t)nchunk * 8192 + (size_t)nchunk * 4096 + 32 * 68 * 4 + sizeof(PcShared) + 256 + 1024;
 }
 
 // how many clusters of `cluster` CTAs (block size / dynamic shared memory given) the device keeps resident at once
@@ -616,21 +792,17 @@ inline long long *&pc_dbg_buffer() {
     return p;
 }
 
-inline int &pc_multicast() {   // cluster size wanted for the forward chain's multicast operand stream (debug option "multicast": 0 -> 1)
-    static int cs = 4;
-    return cs;
-}
-inline int pc_fwd_cluster(int H) {
-    const int grid = H / 8, want = pc_multicast();
-    return want >= 4 && grid % 4 == 0 ? 4 : (want >= 2 && grid % 2 == 0 ? 2 : 1);
+inline int &pc_fwd_swap() {    // forward chain with the operands swapped (1, default) or batch rows on the M side (0): debug option "decswap"
+    static int on = 1;
+    return on;
 }
 inline bool pc_coresident(int H) {
     static int cached_H = -1;
     static bool cached = false;
     if (cached_H != H) {
         const int grid = H / 8;
-        const int cs = grid % 4 == 0 ? 4 : (grid % 2 == 0 ? 2 : 1);          // the largest cluster pc_fwd_cluster may ask for
-        const int fwd = cs * max_resident_clusters(k_lstm_chain_fwd, PCF64_THREADS, pc_smem_bytes(H, false), cs, grid);
+        const int fwd = min(max_resident_clusters(k_lstm_chain_fwd, PCF64_THREADS, pc_smem_bytes(H, false), 1, grid),
+                            max_resident_clusters(k_lstm_chain_fwd_swap, PCF64_THREADS, pc_smem_bytes_swap(H), 1, grid));
         const int bwd = max_resident_clusters(k_lstm_chain_bwd, PCF_THREADS, pc_smem_bytes(H, true), 4, grid);
         cached = fwd >= grid && 4 * bwd >= grid;
         cached_H = H;
@@ -641,29 +813,17 @@ inline bool pc_coresident(int H) {
 inline int launch_lstm_chain_fwd(const PcFwdArgs &a_in, cudaStream_t st) {
     PcFwdArgs a = a_in;
     a.dbg = pc_dbg_buffer();
-    const size_t smem = pc_smem_bytes(a.H, false);
-    static size_t configured = 0;
-    if (configured < smem) {
-        GVX_CUDA(cudaFuncSetAttribute(k_lstm_chain_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    const bool swap = pc_fwd_swap() != 0;          // (the weight image must have been packed for the same variant: k_pc_pack_w mode 2 / 0)
+    const size_t smem = swap ? pc_smem_bytes_swap(a.H) : pc_smem_bytes(a.H, false);
+    static size_t configured[2] = {0, 0};
+    if (configured[swap] < smem) {
+        if (swap) GVX_CUDA(cudaFuncSetAttribute(k_lstm_chain_fwd_swap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else GVX_CUDA(cudaFuncSetAttribute(k_lstm_chain_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[swap] = smem;
     }
-    GVX_CUDA(cudaMemsetAsync(a.bar, 0, sizeof(unsigned), st));
-    {
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(a.H / 8);
-        cfg.blockDim = dim3(PCF64_THREADS);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = pc_fwd_cluster(a.H);
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        GVX_CUDA(cudaLaunchKernelEx(&cfg, k_lstm_chain_fwd, a));
-    }
+    GVX_CUDA(cudaMemsetAsync(a.bar, 0, 64 * sizeof(unsigned), st));          // two counters, 128 B apart
+    if (swap) k_lstm_chain_fwd_swap<<<a.H / 8, PCF64_THREADS, smem, st>>>(a);
+    else k_lstm_chain_fwd<<<a.H / 8, PCF64_THREADS, smem, st>>>(a);
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     return 0;

@@ -73,13 +73,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gsrc, u
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// the same copy delivered to the same CTA-relative address (and counted on the same CTA-relative mbarrier) of every CTA in `mask`
-__device__ __forceinline__ void tma_bulk_g2s_mc(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint16_t mask) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
-                 : "memory");
-}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
