@@ -596,34 +596,46 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PCF_THREADS, 1) k_ls
         if (i > 0) {       // d h_t from the recurrence: W_hh^T . d gates_{t+1} (at t = T-1 there is none)
             const uint32_t par = (uint32_t)(i - 1) & 1u;
             if (tid == 0) mbar_expect_tx(&sh->xb, 4u * 8u * PC_ROWS * 4u);
-            if (warp == 0) {
-                if (elect_one()) {
-                    if (okw && gbar_wait(a.bar, ncta * (unsigned)i, &sh->dead, a.err, 21)) {
-                        pc_stamp(a.dbg, j, i, 0);
-                        fence_proxy_async_global();
-                        const uint8_t *src = (const uint8_t *)a.gimg + (size_t)(i & 1) * 4 * q_bytes + (size_t)s_rank * q_bytes;
-                        for (int c = 0; c < nchunk; ++c) {
-                            mbar_expect_tx(sh->full + c, PC_CHUNK_BYTES);
-                            tma_bulk_g2s(ring + (size_t)c * PC_CHUNK_BYTES, src + (size_t)c * PC_CHUNK_BYTES, PC_CHUNK_BYTES, sh->full + c);
-                        }
-                    }
-                }
-                __syncwarp();
-            } else if (warp == 1) {
+            // the K quarter of the d-gates image -> shared memory by ALL 512 threads (16-byte cp.async: 128 KB in ~2.5k cycles),
+            // then ONE unrolled block of 64 MMAs: the per-slab single-thread loop (mbarrier wait + descriptor arithmetic + 4 MMAs,
+            // ~280 cycles a slab) was what bounded this phase, not L2 and not the tensor pipe
+            if (tid == 0 && okw) {
+                gbar_wait(a.bar, ncta * (unsigned)i, &sh->dead, a.err, 21);
+                pc_stamp(a.dbg, j, i, 0);
+            }
+            __syncthreads();
+            {
+                const uint8_t *src = (const uint8_t *)a.gimg + (size_t)(i & 1) * 4 * q_bytes + (size_t)s_rank * q_bytes;
+                for (int v = tid; v < q_bytes / 16; v += PCF_THREADS) cp_async16(ring + (size_t)v * 16, src + (size_t)v * 16, true);
+                cp_async_commit();
+                cp_async_wait<0>();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            __syncthreads();
+            if (warp == 1) {
                 if (elect_one()) {
                     constexpr uint32_t idesc = umma_idesc_bf16(64, PC_N);
                     const uint64_t a0 = umma_desc_sw128(smem_u32(ring)), b0 = umma_desc_sw128(smem_u32(wsm));
-                    bool ok = okw;
-                    for (int c = 0; c < nchunk && ok; ++c) {
-                        if (!pc_mbar_wait(sh->full + c, par, &sh->dead, a.err, 24)) { ok = false; break; }
+                    if (okw && !sh->dead) {
                         tc_fence_after();
-                        const uint64_t ad = a0 + (uint64_t)(c * (PC_CHUNK_BYTES >> 4)), bd = b0 + (uint64_t)(c * (4096 >> 4));
-                        umma_bf16(tmem_base, ad, bd, idesc, c > 0 ? 1u : 0u);
-                        umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
-                        umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
-                        umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
-                    }
-                    if (ok) {
+                        if (nchunk == 16) {
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) {
+                                const uint64_t ad = a0 + (uint64_t)(c * (PC_CHUNK_BYTES >> 4)), bd = b0 + (uint64_t)(c * (4096 >> 4));
+                                umma_bf16(tmem_base, ad, bd, idesc, c > 0 ? 1u : 0u);
+                                umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
+                                umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
+                                umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
+                            }
+                        } else {
+                            for (int c = 0; c < nchunk; ++c) {
+                                const uint64_t ad = a0 + (uint64_t)(c * (PC_CHUNK_BYTES >> 4)), bd = b0 + (uint64_t)(c * (4096 >> 4));
+                                umma_bf16(tmem_base, ad, bd, idesc, c > 0 ? 1u : 0u);
+                                umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
+                                umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
+                                umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
+                            }
+                        }
                         umma_commit(&sh->tmem_full);
                         pc_stamp(a.dbg, j, i, 2);
                         pc_mbar_wait(&sh->tmem_full, par, &sh->dead, a.err, 25);      // the only thread that waits for the accumulator
