@@ -599,7 +599,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
                 // consumes in order (fixed accumulation order: bit-exact run to run).
                 const unsigned target = 2u * (unsigned)(i + 1);
                 const uint8_t *src = a.gimg + (size_t)par * 4 * FB_QBYTES + (size_t)r * FB_QBYTES;
-                uint32_t pending = okw ? 0xffffu : 0u;
+                uint32_t pending = okw ? 0xffffu : 0u, have = 0u;
                 bool first = true;
                 const long long t0 = clock64();
                 while (pending) {
@@ -630,17 +630,28 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
                             first = false;
                         }
 #pragma unroll 1
-                        for (int s = 0; s < 16; ++s) {
+                        for (int s = 0; s < 8; ++s) {
                             if (!(ready >> s & 1u)) continue;
-                            const int slot = s & 7;
-                            if (s >= 8 && !mbar_try_wait(sh->empty + slot, 0u)) continue;      // slab s - 8 not consumed yet
-                            mbar_expect_tx(sh->full + slot, PC_CHUNK_BYTES);
-                            tma_bulk_g2s(ring + (size_t)slot * PC_CHUNK_BYTES, src + (size_t)s * PC_CHUNK_BYTES, PC_CHUNK_BYTES, sh->full + slot);
-                            pending &= ~(1u << s);
+                            mbar_expect_tx(sh->full + s, PC_CHUNK_BYTES);
+                            tma_bulk_g2s(ring + (size_t)s * PC_CHUNK_BYTES, src + (size_t)s * PC_CHUNK_BYTES, PC_CHUNK_BYTES, sh->full + s);
                         }
+                        pending &= ~(ready & 0xffu);
+                        have |= ready;
                     }
+                    if ((pending & 0xffu) == 0u && (have & 0xff00u) == 0xff00u) break;       // first revolution issued, second one ready
                     if (sh->dead) break;
                     if (clock64() - t0 > FA_WAIT_CYCLES) { sh->dead = 1; atomicCAS(a.err, 0, 58); break; }
+                }
+                // second revolution of the ring: slab s takes slot s - 8 as soon as the MMA issuer has released it (a shared-memory
+                // mbarrier wait - re-polling the global counters here cost an L2 round trip per attempt)
+                if (!sh->dead && (have & 0xff00u) == 0xff00u) {
+#pragma unroll 1
+                    for (int s = 8; s < 16; ++s) {
+                        const int slot = s - 8;
+                        if (!fa_wait_mbar(sh->empty + slot, 0u, &sh->dead, a.err, 59)) break;
+                        mbar_expect_tx(sh->full + slot, PC_CHUNK_BYTES);
+                        tma_bulk_g2s(ring + (size_t)slot * PC_CHUNK_BYTES, src + (size_t)s * PC_CHUNK_BYTES, PC_CHUNK_BYTES, sh->full + slot);
+                    }
                 }
                 pc_stamp(a.dbg, j, i, 9);
             }
@@ -650,17 +661,23 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
                 constexpr uint32_t idesc = umma_idesc_bf16(64, FB_NCOL);
                 const uint64_t a0 = umma_desc_sw128(smem_u32(ring)), b0 = umma_desc_sw128(smem_u32(wsm));
                 bool ok = okw;
-                for (int s = 0; s < FB_KSLAB && ok; ++s) {
+                static_assert(FB_KSLAB == 16, "the issue loop below is unrolled for two revolutions of the 8-slot ring");
+                // fully unrolled: slot, phase parity and both descriptors are immediates - the rolled loop spent ~280 cycles per slab
+                // on its own bookkeeping (mbarrier wait helper, descriptor arithmetic through R2UR) and bounded the whole stream
+#pragma unroll
+                for (int s = 0; s < FB_KSLAB; ++s) {
                     const int ring_slot = s & 7;                 // slab s lives in slot s % 8: phase parity 0 for s < 8, 1 for s >= 8
-                    if (!fa_wait_mbar(sh->full + ring_slot, (uint32_t)(s >> 3), &sh->dead, a.err, 60)) { ok = false; break; }
+                    if (ok && !mbar_try_wait(sh->full + ring_slot, (uint32_t)(s >> 3))) ok = fa_wait_mbar(sh->full + ring_slot, (uint32_t)(s >> 3), &sh->dead, a.err, 60);
                     if (s == 0) pc_stamp(a.dbg, j, i, 10);
-                    tc_fence_after();
-                    const uint64_t ad = a0 + (uint64_t)(ring_slot * (PC_CHUNK_BYTES >> 4)), bd = b0 + (uint64_t)(s * (FB_WSLAB_BYTES >> 4));
-                    umma_bf16(tmem_base, ad, bd, idesc, s > 0 ? 1u : 0u);
-                    umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
-                    umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
-                    umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
-                    umma_commit(sh->empty + ring_slot);
+                    if (ok) {
+                        tc_fence_after();
+                        const uint64_t ad = a0 + (uint64_t)(ring_slot * (PC_CHUNK_BYTES >> 4)), bd = b0 + (uint64_t)(s * (FB_WSLAB_BYTES >> 4));
+                        umma_bf16(tmem_base, ad, bd, idesc, s > 0 ? 1u : 0u);
+                        umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
+                        umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
+                        umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
+                        umma_commit(sh->empty + ring_slot);
+                    }
                 }
                 if (ok) umma_commit(&sh->tmem_full);
                 pc_stamp(a.dbg, j, i, 11);
