@@ -321,7 +321,8 @@ __global__ void __launch_bounds__(PCF64_THREADS, 1) k_lstm_chain_fwd_swap(const 
     unsigned *bar = a.bar + 32 * rh;                       // one counter per batch half, 128 B apart
 
     if (threadIdx.x == 0) {
-        mbar_init(sh->full + 0, 1);                        // "the half image of this step is in shared memory"
+        mbar_init(sh->full + 0, 1);                        // "the first / second half of the K slabs of this step is in shared memory"
+        mbar_init(sh->full + 1, 1);
         mbar_init(&sh->tmem_full, 1);
         mbar_init(&sh->wbar, 1);
         sh->dead = 0;
@@ -355,20 +356,27 @@ __global__ void __launch_bounds__(PCF64_THREADS, 1) k_lstm_chain_fwd_swap(const 
             bool ok = pc_mbar_wait(&sh->wbar, 0, &sh->dead, a.err, 13);
             const uint64_t a0 = umma_desc_sw128(smem_u32(wsm)), b0 = umma_desc_sw128(smem_u32(ring));
             for (int t = 0; t < T && ok; ++t) {
-                if (!pc_mbar_wait(sh->full + 0, (uint32_t)t & 1u, &sh->dead, a.err, 14)) break;
-                pc_stamp(a.dbg, j, t, 8);
-                tc_fence_after();
                 // descriptors advance in 16-byte units: slab stride 8 KB (A) / 4 KB (B), 32 B per K = 16 step
                 if (nchunk == 16) {
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        const uint64_t ad = a0 + (uint64_t)(c * (8192 >> 4)), bd = b0 + (uint64_t)(c * (SLOT >> 4));
-                        umma_bf16(tmem_base, ad, bd, idesc, c > 0 ? 1u : 0u);
-                        umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
-                        umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
-                        umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
+                    for (int hf = 0; hf < 2; ++hf) {
+                        if (!pc_mbar_wait(sh->full + hf, (uint32_t)t & 1u, &sh->dead, a.err, 14)) { ok = false; break; }
+                        if (hf == 0) pc_stamp(a.dbg, j, t, 8);
+                        tc_fence_after();
+#pragma unroll
+                        for (int c = 8 * hf; c < 8 * hf + 8; ++c) {
+                            const uint64_t ad = a0 + (uint64_t)(c * (8192 >> 4)), bd = b0 + (uint64_t)(c * (SLOT >> 4));
+                            umma_bf16(tmem_base, ad, bd, idesc, c > 0 ? 1u : 0u);
+                            umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
+                            umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
+                            umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
+                        }
                     }
+                    if (!ok) break;
                 } else {
+                    if (!pc_mbar_wait(sh->full + 0, (uint32_t)t & 1u, &sh->dead, a.err, 14)) break;
+                    if (!pc_mbar_wait(sh->full + 1, (uint32_t)t & 1u, &sh->dead, a.err, 14)) break;
+                    tc_fence_after();
                     for (int c = 0; c < nchunk; ++c) {
                         const uint64_t ad = a0 + (uint64_t)(c * (8192 >> 4)), bd = b0 + (uint64_t)(c * (SLOT >> 4));
                         umma_bf16(tmem_base, ad, bd, idesc, c > 0 ? 1u : 0u);
@@ -410,14 +418,22 @@ __global__ void __launch_bounds__(PCF64_THREADS, 1) k_lstm_chain_fwd_swap(const 
             asm volatile("bar.sync 1, 512;" ::: "memory");
             {
                 const uint8_t *src = (const uint8_t *)a.himg + (size_t)(t & 1) * img_bytes + (size_t)rh * nchunk * SLOT;
-                for (int i = e; i < nvec; i += 512) cp_async16(ring + (size_t)i * 16, src + (size_t)i * 16, true);
+                // two commit groups (K slabs [0, n/2) and [n/2, n)): the issuer starts on the first half while the second is landing
+                const int nv0 = (nchunk / 2) * (int)SLOT / 16;
+                for (int i = e; i < nv0; i += 512) cp_async16(ring + (size_t)i * 16, src + (size_t)i * 16, true);
                 cp_async_commit();
-                cp_async_wait<0>();
+                for (int i = nv0 + e; i < nvec; i += 512) cp_async16(ring + (size_t)i * 16, src + (size_t)i * 16, true);
+                cp_async_commit();
+                cp_async_wait<1>();
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> the MMA's async-proxy reads
             }
             asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (threadIdx.x == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sh->full + 0)) : "memory");
+            cp_async_wait<0>();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, 512;" ::: "memory");
             if (threadIdx.x == 0) {
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sh->full + 0)) : "memory");
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sh->full + 1)) : "memory");
                 pc_stamp(a.dbg, j, t, 1);
             }
             if (ok) ok = __all_sync(0xffffffffu, pc_mbar_wait(&sh->tmem_full, (uint32_t)t & 1u, &sh->dead, a.err, 15)) != 0;
