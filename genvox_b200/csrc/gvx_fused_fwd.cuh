@@ -844,15 +844,18 @@ __global__ void __cluster_dims__(FA_CLUSTER, 1, 1) __launch_bounds__(FA_THREADS,
                                                    (((kc & 7) ^ (row & 7)) << 4)) = st_v;
                         fence_proxy_async_global();
                     }
+                    // the 32 threads of this warp are the only writers of ctx_t: the release for the grid barrier goes out from here
+                    // (ordered behind the warp's stores by the warp barrier), not after the CTA barrier below
+                    __syncwarp();
+                    if (lane == 0) {
+                        gbar_arrive(bar2);
+                        pc_stamp(a.dbg, j, t, 7);
+                        fa_mark(a.prog, 0, j, 8 * t + 5);
+                        if (j == 0 && a.dbg && t < 1024) a.dbg[t * 32 + 8] = fa_globaltimer();
+                    }
                 }
             }
             fa_bar_workers();
-            if (tid == 384) {
-                gbar_arrive(bar2);
-                pc_stamp(a.dbg, j, t, 7);
-                fa_mark(a.prog, 0, j, 8 * t + 5);
-                if (j == 0 && a.dbg && t < 1024) a.dbg[t * 32 + 8] = fa_globaltimer();
-            }
             // ---- everything only the stashes / later GEMMs read goes out after the release
             if (rvalid) {
                 if (wtid < n_own) {
