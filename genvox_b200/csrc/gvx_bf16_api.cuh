@@ -210,7 +210,7 @@ struct BwdBfL {
         GDT = c.take((size_t)4 * d.H * TBp / 2); XDT = c.take((size_t)d.Kd * TBp / 2);
         GAT = c.take((size_t)4 * d.A * TBp / 2); XAT = c.take((size_t)d.Ka * TBp / 2);
         HCT = c.take((size_t)d.Kp * TBp / 2); DQT = c.take((size_t)d.D * TBp / 2); DOT = c.take((size_t)d.OL * TBp / 2);
-        gws_floats = (size_t)4 << 20;
+        gws_floats = (size_t)32 << 20;         // 128 MB: up to 3 partial copies of the largest weight gradient
         GWS = c.take(gws_floats);              // split-K partial tiles of the small weight gradients
         total = c.o;
     }
@@ -976,15 +976,18 @@ extern "C" int gvx_test_nt_gemm(const float *A, const float *B, int M, int N, in
     cudaStream_t st = (cudaStream_t)stream;
     bf16 *a = nullptr, *b = nullptr, *at = nullptr, *bt = nullptr;
     int *err = nullptr;
+    float *ws = nullptr;
+    const size_t ws_floats = (size_t)32 << 20;           // the production workspace size: split-K is taken exactly as in training
     GVX_CUDA(cudaMalloc(&a, (size_t)M * K * 2));
     GVX_CUDA(cudaMalloc(&b, (size_t)N * K * 2));
     GVX_CUDA(cudaMalloc(&err, 64));
+    GVX_CUDA(cudaMalloc(&ws, ws_floats * 4));
     GVX_CUDA(cudaMemsetAsync(err, 0, 64, st));
     int rc = 0;
     if (mode == 0) {
         k_to_bf16<<<grid_for((size_t)M * K), 256, 0, st>>>(A, K, (size_t)M, K, a, K);
         k_to_bf16<<<grid_for((size_t)N * K), 256, 0, st>>>(B, K, (size_t)N, K, b, K);
-        rc = nt_gemm_bf16(st, M, N, K, a, K, b, K, C, N, err);
+        rc = nt_gemm_bf16(st, M, N, K, a, K, b, K, C, N, err, ws, ws_floats);
     } else {
         GVX_CHECK(M % 8 == 0 && N % 8 == 0, "mode 1 needs M, N multiples of 8");
         GVX_CUDA(cudaMalloc(&at, (size_t)M * K * 2));
@@ -993,11 +996,11 @@ extern "C" int gvx_test_nt_gemm(const float *A, const float *B, int M, int N, in
         k_to_bf16<<<grid_for((size_t)N * K), 256, 0, st>>>(B, N, (size_t)K, N, b, N);        // B given as [K, N]
         rc = transpose_bf16(st, a, K, M, M, at, K);
         if (!rc) rc = transpose_bf16(st, b, K, N, N, bt, K);
-        if (!rc) rc = nt_gemm_bf16(st, M, N, K, at, K, bt, K, C, N, err);
+        if (!rc) rc = nt_gemm_bf16(st, M, N, K, at, K, bt, K, C, N, err, ws, ws_floats);
     }
     if (!rc) rc = check_tc_err(err, st, "nt_gemm");
     else cudaStreamSynchronize(st);
-    cudaFree(a); cudaFree(b); cudaFree(at); cudaFree(bt); cudaFree(err);
+    cudaFree(a); cudaFree(b); cudaFree(at); cudaFree(bt); cudaFree(err); cudaFree(ws);
     return rc;
 }
 
@@ -1005,8 +1008,10 @@ extern "C" int gvx_test_nt_gemm(const float *A, const float *B, int M, int N, in
 extern "C" int gvx_bench_nt_gemm(int M, int N, int K, int reps, float *ms_out) {
     using namespace gvx;
     bf16 *a = nullptr, *b = nullptr;
-    float *c = nullptr;
+    float *c = nullptr, *ws = nullptr;
     int *err = nullptr;
+    const size_t ws_floats = (size_t)32 << 20;
+    GVX_CUDA(cudaMalloc(&ws, ws_floats * 4));
     GVX_CUDA(cudaMalloc(&a, (size_t)M * K * 2));
     GVX_CUDA(cudaMalloc(&b, (size_t)N * K * 2));
     GVX_CUDA(cudaMalloc(&c, (size_t)M * N * 4));
@@ -1016,16 +1021,16 @@ extern "C" int gvx_bench_nt_gemm(int M, int N, int K, int reps, float *ms_out) {
     GVX_CUDA(cudaMemset(err, 0, 64));
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    int rc = nt_gemm_bf16(0, M, N, K, a, K, b, K, c, N, err);
+    int rc = nt_gemm_bf16(0, M, N, K, a, K, b, K, c, N, err, ws, ws_floats);
     cudaEventRecord(e0, 0);
-    for (int i = 0; i < reps && !rc; ++i) rc = nt_gemm_bf16(0, M, N, K, a, K, b, K, c, N, err);
+    for (int i = 0; i < reps && !rc; ++i) rc = nt_gemm_bf16(0, M, N, K, a, K, b, K, c, N, err, ws, ws_floats);
     cudaEventRecord(e1, 0);
     cudaEventSynchronize(e1);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     *ms_out = ms / (reps > 0 ? reps : 1);
     if (!rc) rc = check_tc_err(err, 0, "nt_gemm bench");
-    cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(err);
+    cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(err); cudaFree(ws);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return rc;
 }

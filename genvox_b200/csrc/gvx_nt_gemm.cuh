@@ -10,13 +10,14 @@
 // transposed once (they are static), activations / gradients whose contraction runs over the frame axis are transposed by
 // k_transpose_bf16 first (HBM-bound, ~0.1 ms each).
 //
-// Kernel: persistent, one CTA per SM, 128 x 128 output tiles, K blocks of 64.
-//   warp 0  TMA producer  : cp.async.bulk.tensor.2d (tensor maps, SWIZZLE_128B) into a 6-stage ring, OOB rows / K tail zero-filled
-//   warp 1  MMA issuer    : tcgen05.mma kind::f16 128 x 128 x 16, fp32 accumulators in TMEM, two accumulator buffers
+// Kernel: persistent, one CTA per SM, 128 x 256 output tiles, K blocks of 64.
+//   warp 0  TMA producer  : cp.async.bulk.tensor.2d (tensor maps, SWIZZLE_128B) into a 4-stage ring, OOB rows / K tail zero-filled
+//   warp 1  MMA issuer    : tcgen05.mma kind::f16 128 x 256 x 16, fp32 accumulators in TMEM, two accumulator buffers
 //   warps 2..5 epilogue   : tcgen05.ld (each warp its 32-lane quadrant) -> fp32 rows of C; drains tile i while tile i+1 is contracted
 // Every output element is accumulated in a fixed order (one CTA in k order; for the few small weight gradients whose tiles would
 // leave most SMs idle the K blocks are split over CTAs and the partial tiles summed in split order) -> bit-exact run to run.
-// Measured on B200 (profiles/nt_gemm_bench.py): 1.34 PFLOP/s on the decoder-LSTM weight gradient (4096 x 2560, K = 51200).
+// Measured on B200 (profiles/nt_gemm_bench.py): 1.31 PFLOP/s on the decoder-LSTM weight gradient (4096 x 2560, K = 51200),
+// 1.53 on d [h_att | ctx] (51200 x 1536, K = 4096).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -25,9 +26,13 @@
 
 namespace gvx {
 
-constexpr int NG_BM = 128, NG_BN = 128, NG_BK = 64;
-constexpr int NG_STAGES = 6;
-constexpr int NG_STAGE_BYTES = (NG_BM + NG_BN) * NG_BK * 2;       // 32 KB
+// 128 x 256 tiles (the largest single-CTA UMMA): 87 flop per operand byte pulled from L2, against 64 for 128 x 128.  Measured
+// (profiles/nt_gemm_bench.py): 1.3-1.5 PFLOP/s on the long-K shapes with either tile, cuBLAS 1.8-2.0 - every SM ingests ~52 B/cycle
+// here, the same per-SM L2 -> SM rate the chains see with cp.async, so the next step is not a bigger single-CTA tile but
+// cta_group::2 (a CTA pair sharing its B halves: 131 flop per ingested byte).  Not built.
+constexpr int NG_BM = 128, NG_BN = 256, NG_BK = 64;
+constexpr int NG_STAGES = 4;
+constexpr int NG_STAGE_BYTES = (NG_BM + NG_BN) * NG_BK * 2;       // 48 KB
 constexpr int NG_THREADS = 192;
 
 struct NgShared {
@@ -93,7 +98,7 @@ __global__ void __launch_bounds__(NG_THREADS, 1) k_nt_gemm(const __grid_constant
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_slot)), "n"(256) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -122,6 +127,7 @@ __global__ void __launch_bounds__(NG_THREADS, 1) k_nt_gemm(const __grid_constant
     } else if (warp == 1) {
         if (elect_one()) {      // ---- MMA issuer
             constexpr uint32_t idesc = umma_idesc_bf16(NG_BM, NG_BN);
+            const uint64_t ad0 = umma_desc_sw128(smem_u32(smem));      // descriptors advance in 16-byte units
             int s = 0, it = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -135,8 +141,7 @@ __global__ void __launch_bounds__(NG_THREADS, 1) k_nt_gemm(const __grid_constant
                 for (int kb = kb0; kb < kb1; ++kb) {
                     if (!mbar_wait(sh->full + s, ph, a.err, 73)) return;
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)s * NG_STAGE_BYTES);
-                    const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + NG_BM * NG_BK * 2);
+                    const uint64_t ad = ad0 + (uint64_t)(s * (NG_STAGE_BYTES >> 4)), bd = ad + (uint64_t)((NG_BM * NG_BK * 2) >> 4);
 #pragma unroll
                     for (int j = 0; j < NG_BK / 16; ++j) umma_bf16(tacc, ad + 2 * j, bd + 2 * j, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
                     umma_commit(sh->empty + s);
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(NG_THREADS, 1) k_nt_gemm(const __grid_constant
     }
     __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
     }
 }
 
@@ -249,11 +254,21 @@ inline int nt_gemm_bf16(cudaStream_t st, int M, int N, int K, const __nv_bfloat1
     }
     int ntiles = a.tiles_m * a.tiles_n;
     const int nkb = (K + NG_BK - 1) / NG_BK;
-    if (ws && ntiles * 4 <= sms && nkb >= 64) {
-        int splits = sms / ntiles;
-        if (splits > nkb / 16) splits = nkb / 16;
-        while (splits > 1 && (size_t)splits * M * N > ws_floats) --splits;
-        if (splits > 1) { a.splits = splits; a.P = ws; ntiles *= splits; }
+    if (ws && nkb >= 128) {
+        // split K when that fills the last wave of the persistent grid (tiles x splits just under a multiple of the SM count) or
+        // when the tiles alone leave most SMs idle: each split keeps >= 64 K blocks, the partial tiles must fit the workspace
+        auto eff = [&](int sp) {
+            const int items = ntiles * sp, waves = (items + sms - 1) / sms;
+            return (double)items / ((double)waves * sms);
+        };
+        int best = 1;
+        double best_eff = eff(1);
+        for (int sp = 2; sp <= 64 && nkb / sp >= 64; ++sp) {
+            if ((size_t)sp * M * N > ws_floats) break;
+            const double e = eff(sp);
+            if (e > best_eff + 0.03) { best = sp; best_eff = e; }
+        }
+        if (best > 1) { a.splits = best; a.P = ws; ntiles *= best; }
     }
     k_nt_gemm<<<ntiles < sms ? ntiles : sms, NG_THREADS, NG_SMEM, st>>>(tmA, tmB, a);
     GVX_LAUNCHED(1);

@@ -27,7 +27,9 @@ def test_tc_gemm_matches_bf16_matmul(cuda_device, B, M, K, KS):
 
 
 @pytest.mark.parametrize("M,N,K,mode", [(128, 128, 64, 0), (300, 200, 136, 0), (4096, 256, 512, 0), (1000, 81, 1536, 0),
-                                        (256, 512, 2048, 1), (4096, 1792, 3208, 1), (128, 1024, 6400, 1)])
+                                        (256, 512, 2048, 1), (4096, 1792, 3208, 1), (128, 1024, 6400, 1),
+                                        # long K with few tiles: the deterministic split-K path (partial tiles + fixed-order reduction)
+                                        (128, 1024, 16384, 1), (256, 768, 8192, 0), (88, 1536, 12800, 1)])
 def test_nt_gemm_matches_torch(cuda_device, M, N, K, mode):
     """The tcgen05 GEMM of the time-batched contractions (csrc/gvx_nt_gemm.cuh): tails in M, N and K, the transposed
     (weight-gradient) path, bit-exact run to run."""
