@@ -105,7 +105,7 @@ int pack_weights_bf16(const Dims &d, const gvx_weights *w, float *packed, cudaSt
     k_to_bf16<<<grid_for((size_t)4 * d.H * d.Kd), 256, 0, st>>>(packed + PL.Wd, d.Kd, (size_t)4 * d.H, d.Kd, (bf16 *)(packed + BL.WdRM), d.Kd);
     GVX_LAUNCHED(1);
     if (d.H % 32 == 0) {
-        k_pc_pack_w<<<grid_for(pc_wimg_elems(d.H)), 256, 0, st>>>(w->dec_w_hh, d.H, d.H, pc_fwd_swap() ? 2 : 0, (bf16 *)(packed + BL.WdhhI));
+        k_pc_pack_w<<<grid_for(pc_wimg_elems(d.H)), 256, 0, st>>>(w->dec_w_hh, d.H, d.H, 0, (bf16 *)(packed + BL.WdhhI));
         k_pc_pack_w<<<grid_for(pc_wimg_elems(d.H)), 256, 0, st>>>(w->dec_w_hh, d.H, d.H, 1, (bf16 *)(packed + BL.WdhhTI));
         GVX_LAUNCHED(2);
     }
@@ -958,7 +958,6 @@ int check_tc_err_public(int *err_dev, cudaStream_t st, const char *what) { retur
 extern "C" int gvx_debug_option(const char *name, int value) {
     if (!strcmp(name, "fused")) gvx::fa_mode() = value;
     else if (!strcmp(name, "persistent")) gvx::pc_mode() = value;
-    else if (!strcmp(name, "decswap")) gvx::pc_fwd_swap() = value < 0 ? 1 : value;
     else { snprintf(gvx::g_err, sizeof(gvx::g_err), "gvx_debug_option: unknown option %s", name); return 1; }
     return 0;
 }
@@ -1063,7 +1062,7 @@ extern "C" int gvx_test_lstm_chain(const float *w_hh, const float *pre, int B, i
     GVX_CUDA(cudaMemsetAsync(himg, 0, pc_himg_elems(H) * 2, st));
     GVX_CUDA(cudaMemsetAsync(gimg, 0, pc_gimg_elems(H) * 2, st));
     GVX_CUDA(cudaMemsetAsync(c_out, 0, (size_t)B * H * sizeof(float), st));
-    k_pc_pack_w<<<grid_for(pc_wimg_elems(H)), 256, 0, st>>>(w_hh, H, H, pc_fwd_swap() ? 2 : 0, wimg);
+    k_pc_pack_w<<<grid_for(pc_wimg_elems(H)), 256, 0, st>>>(w_hh, H, H, 0, wimg);
     k_pc_pack_w<<<grid_for(pc_wimg_elems(H)), 256, 0, st>>>(w_hh, H, H, 1, wimgT);
     PcFwdArgs f;
     memset(&f, 0, sizeof(f));

@@ -6,23 +6,20 @@
 // remains on the sequential chain is   gates_t = pre_t + W_hh . h_{t-1}   followed by the cell.  These kernels run that
 // chain for all T steps in a single launch:
 //
-//   * grid = H/8 CTAs (128 for H = 1024), one per SM, all co-resident; CTA j owns hidden units [8j, 8j+8);
-//   * its slice of the recurrent weights (32 gate rows x H, bf16, 64 KB) is loaded ONCE into shared memory and stays
-//     there for the whole sequence; the cell state (forward) / its gradient (backward) of the CTA's units lives in
-//     registers across steps;
-//   * per step the hidden state of all units ([64 rows][H] bf16 operand image, written by all CTAs) is streamed in by
-//     TMA bulk copies and contracted on tcgen05 (UMMA 128 x 32 x 16, batch rows on the M side so that one TMEM lane =
-//     one batch row and the cell math is thread-local), accumulators in TMEM;
+//   * grid = H/8 CTAs (128 for H = 1024), one per SM, all co-resident;
+//   * a CTA's slice of the recurrent weights is loaded ONCE into shared memory and stays there for the whole sequence
+//     (forward: 64 gate rows x H = 128 KB; backward: 32 output units x a K quarter of 4H = 64 KB); the cell state (forward) /
+//     its gradient (backward) of the CTA's (row, unit) pairs lives in registers across steps;
+//   * per step the operand image written by all CTAs (h_{t-1}, resp. d gates_{t+1}; bf16, SWIZZLE_128B slabs of 64 K
+//     columns) is copied into shared memory by ALL threads of the CTA with 16-byte cp.async and contracted on tcgen05 by one
+//     unrolled block of UMMA 64 x 32 x 16 (accumulator in TMEM);
 //   * steps are separated by a grid-wide barrier (release/acquire counter in global memory).
 //
+// Forward: CTA (jc, rh) owns 16 hidden units for the 32 batch rows of half rh (see k_lstm_chain_fwd_swap).
 // Backward (BPTT of the same chain): d h_{t-1} = W_hh^T . d gates_t has K = 4H; the K range is split over the 4 CTAs of
-// a thread-block cluster (each keeps a [32 units x H] slice of W_hh^T resident), the four partial [64 x 32] tiles are
-// exchanged through distributed shared memory and summed in rank order (deterministic), and each CTA finishes the cell
-// backward of its own 8 units.
-//
-// Warp roles (128 threads): warps 0,1 = epilogue (TMEM lanes 0..63 = batch rows), warp 2 = TMA producer,
-// warp 3 = MMA issuer (one elected lane each).  Every wait is bounded; on timeout an error code is recorded, the CTA's
-// roles stop working (but keep the cluster barriers balanced) and the host raises.
+// a thread-block cluster, the four partial [64 x 32] tiles are pushed to the owner rank through distributed shared memory
+// (st.async + mbarrier complete_tx) and summed in rank order (deterministic), and each CTA finishes the cell backward of its
+// own 8 units.  Every wait is bounded; on timeout an error code is recorded, the CTA's roles stop working and the host raises.
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
@@ -96,14 +93,14 @@ struct PcOut {
 
 // ================================================================================================ forward
 struct PcFwdArgs {
-    const __nv_bfloat16 *Wimg;   // [H/8 CTAs][K/64 slabs][32 rows][64] SWIZZLE_128B; row = local gate row 4*lu+g  (W_hh, k_pc_pack_w mode 0)
+    const __nv_bfloat16 *Wimg;   // [H/16 blocks][K/64 slabs][64 rows][64] SWIZZLE_128B; row = local gate row 4*lu+g of the block's 16 units (W_hh, k_pc_pack_w mode 0)
     const float *pre;            // [T][B][4H]  unit-major columns 4u+g: input contribution (may alias gates_stash)
     const float *bias;           // [4H] unit-major b_ih + b_hh, or null
-    __nv_bfloat16 *himg;         // [2][K/64 slabs][64 rows][64] SWIZZLE_128B ping-pong operand image of h; half 0 = h_{-1} (zeros), pad rows zero
+    __nv_bfloat16 *himg;         // [2][2 batch halves][K/64 slabs][32 rows][64] SWIZZLE_128B ping-pong operand image of h (private to the kernel); image 0 = h_{-1} (zeros)
     float *c_stash;              // [T+1][B][H]  row 0 = c_{-1} (caller), row t+1 written at step t
     float *gates_stash;          // [T][B][4H] gate activations (i,f,g,o per unit) or null
     PcOut out[2];
-    unsigned *bar;               // grid barrier counter, zero at launch
+    unsigned *bar;               // two step-barrier counters (one per batch half, 128 B apart), zeroed by the launcher
     int *err;
     DropCfg drop;
     uint32_t site;
@@ -122,178 +119,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
-// Forward chain.  576 threads: warp 16 = TMA producer, warp 17 = MMA issuer (one elected lane each, lean single-thread
-// loops: no per-chunk empty barriers - the whole h image fits the ring and the grid barrier of step t already implies
-// that this CTA's MMAs of step t-1 have drained), warps 0..15 = epilogue.  The MMA is UMMA 64 x 32 x 16: the 64 batch rows
-// are exactly the M side (no over-read of ignored rows: 3 KB of operands per MMA instead of 5 KB), and an M = 64
-// accumulator lives in lanes 0..15 of each TMEM lane quadrant: row b -> lane (b & 15) + 32 (b >> 4).  Epilogue warp w
-// therefore owns quadrant w & 3 (rows 16 (w & 3) .. +15 in its lower 16 lanes) and column quarter w >> 2 (two units).
-// Measured: the MMA phase (2.4 us of the 5.6 us step) is NOT tensor-bound - issuing every MMA 2x / 4x adds only ~22 cycles
-// per extra 64x32x16 MMA - it is the 128 KB h image per CTA arriving at the chip-wide L2 throughput cap (~4900 B/cycle over
-// 128 CTAs); a cluster multicast of the image is the remaining lever.
-constexpr int PCF_THREADS = 512;           // backward chain (UMMA M = 128)
-constexpr int PCF64_THREADS = 576;
+constexpr int PCF_THREADS = 512;           // backward chain
+constexpr int PCF64_THREADS = 576;         // forward chain: 16 loader / epilogue warps + weight loader + MMA issuer
 
-__global__ void __launch_bounds__(PCF64_THREADS, 1) k_lstm_chain_fwd(const PcFwdArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    // 1 KB alignment computed as an OFFSET into the shared array: the compiler keeps the shared address space (LDS/STS,
-    // not generic LD/ST) for everything derived from it
-    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int H = a.H, T = a.T;
-    const int nchunk = (H + 63) / 64;                      // K slabs of 64 (K padded with zero columns); <= PC_MAXRING
-    const int img_bytes = nchunk * PC_CHUNK_BYTES;         // one h image: [slab][64 rows][128 B]
-    const uint32_t wbytes = (uint32_t)nchunk * 4096;       // [slab][32 rows][128 B]
-    uint8_t *ring = smem;
-    uint8_t *wsm = ring + (size_t)nchunk * PC_CHUNK_BYTES; // the M = 128 MMA over-reads 64 rows past a slab: lands here
-    PcShared *sh = (PcShared *)(wsm + wbytes);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, j = blockIdx.x;
-    const unsigned ncta = gridDim.x;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < PC_MAXRING; ++s) { mbar_init(sh->full + s, 1); mbar_init(sh->empty + s, 1); }
-        mbar_init(&sh->tmem_full, 1);
-        mbar_init(&sh->wbar, 1);
-        sh->dead = 0;
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_slot)), "n"(32) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = sh->tmem_slot;
-
-    if (warp == 16) {
-        // ------------------------------------------------ TMA producer
-        if (elect_one()) {
-            mbar_expect_tx(&sh->wbar, wbytes);
-            const uint8_t *wsrc = (const uint8_t *)a.Wimg + (size_t)j * wbytes;
-            for (uint32_t off = 0; off < wbytes; off += 16384) {
-                const uint32_t n = wbytes - off < 16384 ? wbytes - off : 16384;
-                tma_bulk_g2s(wsm + off, wsrc + off, n, &sh->wbar);
-            }
-            for (int t = 0; t < T; ++t) {
-                if (t > 0 && !gbar_wait(a.bar, ncta * (unsigned)t, &sh->dead, a.err, 11)) break;
-                pc_stamp(a.dbg, j, t, 0);
-                fence_proxy_async_global();       // other CTAs' generic-proxy stores of h -> this thread's async-proxy reads
-                pc_stamp(a.dbg, j, t, 7);
-                const uint8_t *src = (const uint8_t *)a.himg + (size_t)(t & 1) * img_bytes;
-                for (int c = 0; c < nchunk; ++c) {
-                    mbar_expect_tx(sh->full + c, PC_CHUNK_BYTES);
-                    tma_bulk_g2s(ring + (size_t)c * PC_CHUNK_BYTES, src + (size_t)c * PC_CHUNK_BYTES, PC_CHUNK_BYTES, sh->full + c);
-                }
-                pc_stamp(a.dbg, j, t, 1);
-            }
-        }
-        __syncwarp();
-    } else if (warp == 17) {
-        // ------------------------------------------------ MMA issuer
-        if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(64, PC_N);
-            bool ok = pc_mbar_wait(&sh->wbar, 0, &sh->dead, a.err, 13);
-            const uint64_t a0 = umma_desc_sw128(smem_u32(ring)), b0 = umma_desc_sw128(smem_u32(wsm));
-            for (int t = 0; t < T && ok; ++t) {
-                const uint32_t ph = (uint32_t)t & 1u;
-                for (int c = 0; c < nchunk; ++c) {
-                    if (!pc_mbar_wait(sh->full + c, ph, &sh->dead, a.err, 14)) { ok = false; break; }
-                    if (c < 16) pc_stamp(a.dbg, j, t, 8 + c);
-                    tc_fence_after();
-                    // descriptors advance in 16-byte units: slab stride 8 KB (A) / 4 KB (B), 32 B per K = 16 step
-                    const uint64_t ad = a0 + (uint64_t)(c * (PC_CHUNK_BYTES >> 4)), bd = b0 + (uint64_t)(c * (4096 >> 4));
-                    umma_bf16(tmem_base, ad, bd, idesc, c > 0 ? 1u : 0u);
-                    umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
-                    umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
-                    umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
-                }
-                if (ok) umma_commit(&sh->tmem_full);
-                pc_stamp(a.dbg, j, t, 2);
-            }
-        }
-        __syncwarp();
-    } else {
-        // ------------------------------------------------ epilogue.  TMEM hands the accumulator out with one batch row per lane
-        // (M = 64: rows 16 q .. 16 q + 15 in the lower half-warps of quadrant q), but with a row per lane every global access of
-        // the cell (pre-activations, gate / cell stashes, outputs) touches 32 different lines per instruction.  The [64 x 32] tile
-        // goes through shared memory once and the cell runs with thread = (row, unit), unit fastest: 8 consecutive lanes then
-        // read / write one contiguous run of a row.
-        float *gt = (float *)(((uintptr_t)(sh + 1) + 15) & ~(uintptr_t)15);     // [64 rows][36]: pre-activations of the 8 units x 4 gates
-        const int e = threadIdx.x;                         // 0 .. 511
-        const int b = e >> 3, uk = e & 7, u = 8 * j + uk;
-        const bool valid = b < a.B;
-        const int qrow = (warp & 3) * 16 + (lane & 15), cq = warp >> 2;       // TMEM side: row / column quarter of this thread
-        float c = valid ? a.c_stash[(size_t)b * H + u] : 0.f;
-        const float4 bi = a.bias ? *reinterpret_cast<const float4 *>(a.bias + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(8 * cq);
-        // 2-byte slot of (row b, unit u) inside the 16-byte chunk (units 8j..8j+7 of row b) of the swizzled h image
-        const size_t himg_off = (size_t)(j >> 3) * PC_CHUNK_BYTES + b * 128 + (((j & 7) ^ (b & 7)) << 4) + 2 * uk;
-        bool ok = true;
-        for (int t = 0; t < T; ++t) {
-            float4 pr = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) pr = __ldcs(reinterpret_cast<const float4 *>(a.pre + ((size_t)t * a.B + b) * 4 * H + 4 * u));
-            if (ok) ok = __all_sync(0xffffffffu, pc_mbar_wait(&sh->tmem_full, (uint32_t)t & 1u, &sh->dead, a.err, 15)) != 0;
-            if (threadIdx.x == 0) pc_stamp(a.dbg, j, t, 3);
-            if (ok) {
-                float acc[8];
-                tc_fence_after();
-                tmem_ld8(taddr, acc);
-                tc_fence_before();
-                if (lane < 16) {
-                    float4 *dst = reinterpret_cast<float4 *>(gt + qrow * 36 + 8 * cq);
-                    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-                }
-            }
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            float4 ga = make_float4(0.f, 0.f, 0.f, 0.f);
-            float hv = 0.f;
-            if (ok && valid) {
-                const float4 g4 = *reinterpret_cast<const float4 *>(gt + b * 36 + 4 * uk);
-                const float gi = sigmoidf_(g4.x + pr.x + bi.x), gf = sigmoidf_(g4.y + pr.y + bi.y);
-                const float gg = tanhf(g4.z + pr.z + bi.z), go = sigmoidf_(g4.w + pr.w + bi.w);
-                c = gf * c + gi * gg;
-                hv = go * tanhf(c) * drop_mult(a.drop, a.site, (uint32_t)t, (uint32_t)(b + a.row_offset), (uint32_t)u);
-                ga = make_float4(gi, gf, gg, go);
-            }
-            // two units per 4-byte store: the even lane of a unit pair writes both halves
-            const float hv_hi = __shfl_down_sync(0xffffffffu, hv, 1);
-            const uint32_t hp = pack_bf2(hv, hv_hi);
-            const bool writer = ok && valid && (uk & 1) == 0;
-            if (writer) {
-                // the next step's operand first: everything else is only read after the kernel and is written past the barrier
-                *reinterpret_cast<uint32_t *>((uint8_t *)a.himg + (size_t)((t + 1) & 1) * img_bytes + himg_off) = hp;
-                fence_proxy_async_global();
-            }
-            if (threadIdx.x == 0) pc_stamp(a.dbg, j, t, 4);
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            // release at gpu scope is cumulative over the stores ordered before it by the CTA barrier
-            if (threadIdx.x == 0) { gbar_arrive(a.bar); pc_stamp(a.dbg, j, t, 6); }
-            if (ok && valid) {
-                if (a.gates_stash) *reinterpret_cast<float4 *>(a.gates_stash + ((size_t)t * a.B + b) * 4 * H + 4 * u) = ga;
-                a.c_stash[((size_t)(t + 1) * a.B + b) * H + u] = c;
-                if (writer) {
-#pragma unroll
-                    for (int o = 0; o < 2; ++o) {
-                        const PcOut &d = a.out[o];
-                        if (d.p && t + d.toff < T)
-                            *reinterpret_cast<uint32_t *>(d.p + (size_t)(t + d.toff) * d.tstride + (size_t)b * d.ld + d.koff + u) = hp;
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(32) : "memory");
-    }
-}
-
-// Forward chain, operands swapped (the default).  The two halves of the batch never meet in the recurrence, so CTA
+// Forward chain.  The two halves of the batch never meet in the recurrence, so CTA
 // (jc, rh) = (j >> 1, j & 1) owns SIXTEEN hidden units (64 gate rows: the UMMA M side, 128 KB of W_hh resident) for the 32 batch
 // rows of half rh (the N side): it needs only its half of the h image - 64 KB per step - and the step barrier only joins the 64
-// CTAs of a half.  Two measured facts shape the step (profiles/chain_timeline.py, GVX_EXP experiments):
+// CTAs of a half.  Two measured facts shape the step (profiles/chain_timeline.py):
 //   * what bounded the TMA-fed version (one bulk copy + one mbarrier wait + 4 MMAs per 64-column slab, ~280 cycles per slab
 //     whether the slab is 4, 8 or 16 KB, whatever the MMA shape, with 1 or 4 accumulators) was the single-thread issue loop
 //     itself: ~45 dependent instructions per slab.  The 512 epilogue threads are idle at that moment, so THEY fetch the half image
@@ -710,7 +542,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PCF_THREADS, 1) k_ls
 // recurrent-weight images.  w_hh: torch layout [4H, H] (rows g*H + u), ld = row stride.  Per CTA j the image is
 // [Kp/64 slabs][32 rows][128 B] in the SWIZZLE_128B K-major layout (16-byte chunk c of row r at position c ^ (r & 7)),
 // K padded to a multiple of 64 with zeros.
-// mode 0 (forward):  row r = 4*lu+g, k  ->  w_hh[g*H + 8j+lu][k]
+// mode 0 (forward):  block jc = 16 units, [slab][64 rows m = 4*lu+g][128 B], k  ->  w_hh[g*H + 16jc+lu][k]
 // mode 1 (backward): CTA j = 4r'+s, row n = output unit 32r'+n, k  ->  w_hh[g*H + u][32r'+n] with 4u+g = s*H + k
 __global__ void k_pc_pack_w(const float *__restrict__ w_hh, int ld, int H, int mode, __nv_bfloat16 *__restrict__ img) {
     const int nslab = (H + 63) / 64;
@@ -720,7 +552,7 @@ __global__ void k_pc_pack_w(const float *__restrict__ w_hh, int ld, int H, int m
         const int j = (int)(i / per_cta);
         const int rem = (int)(i - (size_t)j * per_cta);
         int slab = rem >> 11, r = (rem >> 6) & 31, cpos = (rem >> 3) & 7, e = rem & 7;
-        if (mode == 2) {     // forward, operands swapped: block jc = 16 units, [slab][64 rows m = 4*lu+g][64]; two "CTAs" of this loop per block
+        if (mode == 0) {     // forward: block jc = 16 units, [slab][64 rows m = 4*lu+g][64]; two "CTAs" of this loop per block
             const size_t per_blk = 2 * per_cta;
             const int jc = (int)(i / per_blk), rm = (int)(i - (size_t)jc * per_blk);
             slab = rm >> 12;
@@ -732,10 +564,7 @@ __global__ void k_pc_pack_w(const float *__restrict__ w_hh, int ld, int H, int m
         const int k = slab * 64 + ((cpos ^ (r & 7)) << 3) + e;
         float v = 0.f;
         if (k < H) {
-            if (mode == 0) {
-                const int lu = r >> 2, g = r & 3;
-                v = w_hh[(size_t)(g * H + 8 * j + lu) * ld + k];
-            } else {
+            {
                 const int rr = j >> 2, sq = j & 3;
                 const int gk = sq * H + k, u = gk >> 2, g = gk & 3;
                 v = w_hh[(size_t)(g * H + u) * ld + 32 * rr + r];
@@ -820,17 +649,12 @@ inline long long *&pc_dbg_buffer() {
     return p;
 }
 
-inline int &pc_fwd_swap() {    // forward chain with the operands swapped (1, default) or batch rows on the M side (0): debug option "decswap"
-    static int on = 1;
-    return on;
-}
 inline bool pc_coresident(int H) {
     static int cached_H = -1;
     static bool cached = false;
     if (cached_H != H) {
         const int grid = H / 8;
-        const int fwd = min(max_resident_clusters(k_lstm_chain_fwd, PCF64_THREADS, pc_smem_bytes(H, false), 1, grid),
-                            max_resident_clusters(k_lstm_chain_fwd_swap, PCF64_THREADS, pc_smem_bytes_swap(H), 1, grid));
+        const int fwd = max_resident_clusters(k_lstm_chain_fwd_swap, PCF64_THREADS, pc_smem_bytes_swap(H), 1, grid);
         const int bwd = max_resident_clusters(k_lstm_chain_bwd, PCF_THREADS, pc_smem_bytes(H, true), 4, grid);
         cached = fwd >= grid && 4 * bwd >= grid;
         cached_H = H;
@@ -841,17 +665,14 @@ inline bool pc_coresident(int H) {
 inline int launch_lstm_chain_fwd(const PcFwdArgs &a_in, cudaStream_t st) {
     PcFwdArgs a = a_in;
     a.dbg = pc_dbg_buffer();
-    const bool swap = pc_fwd_swap() != 0;          // (the weight image must have been packed for the same variant: k_pc_pack_w mode 2 / 0)
-    const size_t smem = swap ? pc_smem_bytes_swap(a.H) : pc_smem_bytes(a.H, false);
-    static size_t configured[2] = {0, 0};
-    if (configured[swap] < smem) {
-        if (swap) GVX_CUDA(cudaFuncSetAttribute(k_lstm_chain_fwd_swap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else GVX_CUDA(cudaFuncSetAttribute(k_lstm_chain_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[swap] = smem;
+    const size_t smem = pc_smem_bytes_swap(a.H);
+    static size_t configured = 0;
+    if (configured < smem) {
+        GVX_CUDA(cudaFuncSetAttribute(k_lstm_chain_fwd_swap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
     }
-    GVX_CUDA(cudaMemsetAsync(a.bar, 0, 64 * sizeof(unsigned), st));          // two counters, 128 B apart
-    if (swap) k_lstm_chain_fwd_swap<<<a.H / 8, PCF64_THREADS, smem, st>>>(a);
-    else k_lstm_chain_fwd<<<a.H / 8, PCF64_THREADS, smem, st>>>(a);
+    GVX_CUDA(cudaMemsetAsync(a.bar, 0, 64 * sizeof(unsigned), st));          // two counters (one per batch half), 128 B apart
+    k_lstm_chain_fwd_swap<<<a.H / 8, PCF64_THREADS, smem, st>>>(a);
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     return 0;
