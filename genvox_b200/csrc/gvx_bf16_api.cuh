@@ -104,7 +104,7 @@ int pack_weights_bf16(const Dims &d, const gvx_weights *w, float *packed, cudaSt
     GVX_LAUNCHED(1);
     k_to_bf16<<<grid_for((size_t)4 * d.H * d.Kd), 256, 0, st>>>(packed + PL.Wd, d.Kd, (size_t)4 * d.H, d.Kd, (bf16 *)(packed + BL.WdRM), d.Kd);
     GVX_LAUNCHED(1);
-    if (d.H % 32 == 0) {
+    if (d.H % 64 == 0) {
         k_pc_pack_w<<<grid_for(pc_wimg_elems(d.H)), 256, 0, st>>>(w->dec_w_hh, d.H, d.H, 0, (bf16 *)(packed + BL.WdhhI));
         k_pc_pack_w<<<grid_for(pc_wimg_elems(d.H)), 256, 0, st>>>(w->dec_w_hh, d.H, d.H, 1, (bf16 *)(packed + BL.WdhhTI));
         GVX_LAUNCHED(2);
@@ -1044,7 +1044,7 @@ extern "C" int gvx_test_lstm_chain(const float *w_hh, const float *pre, int B, i
                                    float *dgates_out, void *stream) {
     using namespace gvx;
     GVX_CHECK(w_hh && pre && h_out && c_out && gates_out && B > 0 && T > 0, "bad argument");
-    GVX_CHECK(pc_supported(H, B), "persistent chain: unsupported shape (need H % 32 == 0, H/8 <= SM count, B <= 64)");
+    GVX_CHECK(pc_supported(H, B), "persistent chain: unsupported shape (need H % 64 == 0, H/8 <= SM count, B <= 64)");
     cudaStream_t st = (cudaStream_t)stream;
     bf16 *wimg = nullptr, *wimgT = nullptr, *himg = nullptr, *hrm = nullptr, *gimg = nullptr, *dgrm = nullptr;
     unsigned *bar = nullptr;

@@ -322,15 +322,15 @@ __global__ void __launch_bounds__(PCF64_THREADS, 1) k_lstm_chain_fwd_swap(const 
 
 // ================================================================================================ backward
 struct PcBwdArgs {
-    const __nv_bfloat16 *Wimg;   // [H/8 CTAs][K/64 slabs][32 rows][64] SWIZZLE_128B; CTA j = 4r+s: row n = output unit 32r+n, k = gate row s*H + kk (unit-major)
-    __nv_bfloat16 *gimg;         // [2][4 K-quarters][H/64 slabs][64 rows][64] SWIZZLE_128B ping-pong d-gates image (k = 4u+g); half 0 zero at launch
+    const __nv_bfloat16 *Wimg;   // [H/64 unit blocks][4 K quarters][H/64 slabs][64 rows][64] SWIZZLE_128B: row n = output unit 64 ro + n, k = gate row s*H + kk (unit-major)
+    __nv_bfloat16 *gimg;         // [2][4 K-quarters][2 batch halves][H/64 slabs][32 rows][64] SWIZZLE_128B ping-pong d-gates image (k = 4u+g), private to the kernel
     const float *dh_ext;         // d h (dropped) of frame t from everything but the recurrence: dh_ext[t*dh_tstride + b*dh_ld + u]
     int dh_ld;
     long long dh_tstride;
     const float *gates_stash;    // [T][B][4H]
     const float *c_stash;        // [T+1][B][H]
     __nv_bfloat16 *dg_rm;        // [T][B][4H] row-major d gates (columns 4u+g) for the time-batched GEMMs
-    unsigned *bar;
+    unsigned *bar;               // two step-barrier counters (one per batch half, 128 B apart), zeroed by the launcher
     int *err;
     DropCfg drop;
     uint32_t site;
@@ -338,17 +338,22 @@ struct PcBwdArgs {
     long long *dbg;
 };
 
-// 512 threads, one loop: thread = (batch row, hidden unit 8j + uk), unit fastest, keeps d c of its (row, unit) in a register
-// and does the cell backward with coalesced accesses to the stashes / the d-gates image.  Per step
-//   warp 0 (one elected lane): image barrier, then the 16 TMA bulk copies of this CTA's K quarter (whole quarter in the ring:
-//                              no empty barriers); warp 1 (one elected lane): UMMA 64 x 32 x 16 over the 16 slabs;
-//   all warps: tcgen05.ld of the [64 x 32] partial tile, PUSHED column-wise into the shared memory of the rank that owns the
-//              column's unit (st.async + mbarrier complete_tx: no cluster barrier, no fence - a cluster.sync per step costs a
-//              MEMBAR.ALL.GPU in every thread); each rank sums the four partials of its 8 units in rank order.
-constexpr int PCB_PLD = 68;        // row stride of a pushed partial column ([src rank][8 units][68]: reads by (row, unit) conflict-free)
+// 512 threads, one loop.  Cluster c = j >> 2 = (output-unit block ro = c >> 1 of 64 units, batch half rh = c & 1); rank s = j & 3 owns
+// the K quarter s of the 4H gate rows AND, for the cell backward, units 64 ro + 16 s .. + 15 of the 32 rows of its half:
+// thread = (local row ub, unit uk), unit fastest, keeps d c of its (row, unit) in a register.  The two batch halves never meet
+// in the recurrence: each half has its own step barrier (64 CTAs) and its own half of the d-gates image.  Per step
+//   thread 0: step barrier; ALL threads: the CTA's [32 rows x K quarter] piece of the d-gates image -> shared memory with 16-byte
+//             cp.async (64 KB, two commit groups); warp 1 (one elected lane): 64 x UMMA 64 x 32 x 16 from one unrolled block
+//             (A = W_hh^T slab [64 output units][64 k], resident; B = image slab [32 rows][64 k]);
+//   all warps: tcgen05.ld of the [64 units x 32 rows] partial tile (unit m in lane m & 15 of TMEM quadrant m >> 4 = the owner
+//              rank), PUSHED into the shared memory of the owner (st.async + mbarrier complete_tx: no cluster barrier, no fence -
+//              a cluster.sync per step costs a MEMBAR.ALL.GPU in every thread); each rank sums the four partials of its 16 units
+//              in rank order.
+constexpr int PCB_PLD = 16;        // pushed partials: [src rank][32 rows][16 units] - a push instruction (16 lanes = 16 units of one row) is one
+                                   // contiguous 64-byte DSMEM write, and the reads by (row, unit) are conflict-free
 
 struct PcbShared {
-    uint64_t full[PC_MAXRING], tmem_full, wbar, xb;
+    uint64_t full[2], tmem_full, wbar, xb;
     uint32_t tmem_slot;
     volatile int dead;
 };
@@ -379,21 +384,26 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PCF_THREADS, 1) k_ls
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int H = a.H, T = a.T;
-    const int nchunk = (H + 63) / 64;
-    const int q_bytes = nchunk * PC_CHUNK_BYTES;           // this CTA's K quarter of the d-gates image: [slab][64 rows][128 B]
-    const uint32_t wbytes = (uint32_t)nchunk * 4096;
-    uint8_t *ring = smem;
-    uint8_t *wsm = ring + (size_t)nchunk * PC_CHUNK_BYTES;
-    float *pin = (float *)(wsm + wbytes);                  // [4 src ranks][8 units][PCB_PLD] partial d h of the own units
-    PcbShared *sh = (PcbShared *)(pin + 4 * 8 * PCB_PLD);
+    const int nchunk = (H + 63) / 64;                      // K slabs of one quarter
+    constexpr uint32_t SLOT = 32 * 128;                    // one slab of a batch half: 32 rows x 128 B
+    const int qh_bytes = nchunk * (int)SLOT;               // [slab][32 rows][128 B]: one (K quarter, batch half) piece of the image
+    const int img_bytes = 8 * qh_bytes;                    // one d-gates image: [4 K quarters][2 batch halves] pieces
+    const uint32_t wbytes = (uint32_t)nchunk * 8192;       // [slab][64 output units][128 B]
+    uint8_t *wsm = smem;
+    uint8_t *ring = wsm + wbytes;
+    float *pin = (float *)(ring + (size_t)nchunk * SLOT);  // [4 src ranks][32 rows][PCB_PLD] partial d h of the own units
+    PcbShared *sh = (PcbShared *)(pin + 4 * 32 * PCB_PLD);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, j = blockIdx.x;
     const int s_rank = (int)cluster.block_rank();          // == j & 3
-    const unsigned ncta = gridDim.x;
-    const int ub = tid >> 3, uk = tid & 7, u = 8 * j + uk;
-    const bool valid = ub < a.B;
+    const int cl = j >> 2, ro = cl >> 1, rh = cl & 1;
+    const unsigned nhalf = gridDim.x >> 1;                 // CTAs of one batch half = arrivals per step barrier
+    unsigned *bar = a.bar + 32 * rh;
+    const int ub = tid >> 4, uk = tid & 15, b = 32 * rh + ub, u = 64 * ro + 16 * s_rank + uk;
+    const bool valid = b < a.B;
 
     if (tid == 0) {
-        for (int s = 0; s < PC_MAXRING; ++s) mbar_init(sh->full + s, 1);
+        mbar_init(sh->full + 0, 1);
+        mbar_init(sh->full + 1, 1);
         mbar_init(&sh->tmem_full, 1);
         mbar_init(&sh->wbar, 1);
         mbar_init(&sh->xb, 1);
@@ -411,7 +421,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PCF_THREADS, 1) k_ls
     const uint32_t tmem_base = sh->tmem_slot;
     if (tid == 0) {
         mbar_expect_tx(&sh->wbar, wbytes);
-        const uint8_t *wsrc = (const uint8_t *)a.Wimg + (size_t)j * wbytes;
+        const uint8_t *wsrc = (const uint8_t *)a.Wimg + (size_t)(ro * 4 + s_rank) * wbytes;
         for (uint32_t off = 0; off < wbytes; off += 16384) {
             const uint32_t n = wbytes - off < 16384 ? wbytes - off : 16384;
             tma_bulk_g2s(wsm + off, wsrc + off, n, &sh->wbar);
@@ -420,64 +430,76 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PCF_THREADS, 1) k_ls
     cluster.sync();                                        // every CTA's mbarriers exist before any remote push
     const bool okw = pc_mbar_wait(&sh->wbar, 0, &sh->dead, a.err, 23);
 
-    // gate rows 4u .. 4u+3 of the 4H range = 8 bytes of the swizzled image of K quarter (4u / H)
+    // gate rows 4u .. 4u+3 of the 4H range = 8 bytes of the swizzled image piece (K quarter 4u / H, batch half rh)
     const int kg = 4 * u, quarter = kg / H, kk = kg - quarter * H;
-    const size_t gimg_off = (size_t)quarter * q_bytes + (size_t)(kk >> 6) * PC_CHUNK_BYTES + ub * 128 + ((((kk & 63) >> 3) ^ (ub & 7)) << 4) + (kk & 7) * 2;
+    const size_t gimg_off = ((size_t)(quarter * 2 + rh) * nchunk + (kk >> 6)) * SLOT + ub * 128 + ((((kk & 63) >> 3) ^ (ub & 7)) << 4) + (kk & 7) * 2;
     const uint32_t my_pin = smem_u32(pin), my_xb = smem_u32(&sh->xb);
-    const int tq = warp & 3, tcq = warp >> 2;              // TMEM side: lane quadrant (rows 16 tq ..) and column quarter (owner rank) of this warp
+    const int tq = warp & 3, tcq = warp >> 2;              // TMEM side: lane quadrant (units 16 tq .. = owner rank tq) and row octet of this warp
     const uint32_t taddr = tmem_base + ((uint32_t)(tq * 32) << 16) + (uint32_t)(8 * tcq);
-    const uint32_t dst_pin = pcb_mapa(my_pin, (uint32_t)tcq) + 4u * (uint32_t)(s_rank * 8 * PCB_PLD + 16 * tq + (lane & 15));
-    const uint32_t dst_xb = pcb_mapa(my_xb, (uint32_t)tcq);
+    const uint32_t dst_pin = pcb_mapa(my_pin, (uint32_t)tq) + 4u * (uint32_t)((s_rank * 32 + 8 * tcq) * PCB_PLD + (lane & 15));
+    const uint32_t dst_xb = pcb_mapa(my_xb, (uint32_t)tq);
+    const int nvec = qh_bytes / 16, nv0 = (nchunk / 2) * (int)SLOT / 16;
     float dc = 0.f;
-    float c_new = valid ? a.c_stash[((size_t)T * a.B + ub) * H + u] : 0.f;
+    float c_new = valid ? a.c_stash[((size_t)T * a.B + b) * H + u] : 0.f;
     for (int i = 0; i < T; ++i) {
         const int t = T - 1 - i;
         float4 ga = make_float4(0.f, 0.f, 0.f, 0.f);
         float c_prev = 0.f, dhe = 0.f;
         if (valid) {
-            ga = __ldcs(reinterpret_cast<const float4 *>(a.gates_stash + ((size_t)t * a.B + ub) * 4 * H + 4 * u));
-            c_prev = __ldcs(a.c_stash + ((size_t)t * a.B + ub) * H + u);
-            dhe = __ldcs(a.dh_ext + (size_t)t * a.dh_tstride + (size_t)ub * a.dh_ld + u);
+            ga = __ldcs(reinterpret_cast<const float4 *>(a.gates_stash + ((size_t)t * a.B + b) * 4 * H + 4 * u));
+            c_prev = __ldcs(a.c_stash + ((size_t)t * a.B + b) * H + u);
+            dhe = __ldcs(a.dh_ext + (size_t)t * a.dh_tstride + (size_t)b * a.dh_ld + u);
         }
-        const float mult = valid ? drop_mult(a.drop, a.site, (uint32_t)t, (uint32_t)(ub + a.row_offset), (uint32_t)u) : 1.f;
+        const float mult = valid ? drop_mult(a.drop, a.site, (uint32_t)t, (uint32_t)(b + a.row_offset), (uint32_t)u) : 1.f;
         float rec = 0.f;
         if (i > 0) {       // d h_t from the recurrence: W_hh^T . d gates_{t+1} (at t = T-1 there is none)
             const uint32_t par = (uint32_t)(i - 1) & 1u;
-            if (tid == 0) mbar_expect_tx(&sh->xb, 4u * 8u * PC_ROWS * 4u);
-            // the K quarter of the d-gates image -> shared memory by ALL 512 threads (16-byte cp.async: 128 KB in ~2.5k cycles),
-            // then ONE unrolled block of 64 MMAs: the per-slab single-thread loop (mbarrier wait + descriptor arithmetic + 4 MMAs,
-            // ~280 cycles a slab) was what bounded this phase, not L2 and not the tensor pipe
+            if (tid == 0) mbar_expect_tx(&sh->xb, 4u * 16u * 32u * 4u);
             if (tid == 0 && okw) {
-                gbar_wait(a.bar, ncta * (unsigned)i, &sh->dead, a.err, 21);
+                gbar_wait(bar, nhalf * (unsigned)i, &sh->dead, a.err, 21);
                 pc_stamp(a.dbg, j, i, 0);
             }
             __syncthreads();
             {
-                const uint8_t *src = (const uint8_t *)a.gimg + (size_t)(i & 1) * 4 * q_bytes + (size_t)s_rank * q_bytes;
-                for (int v = tid; v < q_bytes / 16; v += PCF_THREADS) cp_async16(ring + (size_t)v * 16, src + (size_t)v * 16, true);
+                const uint8_t *src = (const uint8_t *)a.gimg + (size_t)(i & 1) * img_bytes + (size_t)(s_rank * 2 + rh) * qh_bytes;
+                for (int v = tid; v < nv0; v += PCF_THREADS) cp_async16(ring + (size_t)v * 16, src + (size_t)v * 16, true);
                 cp_async_commit();
-                cp_async_wait<0>();
+                for (int v = nv0 + tid; v < nvec; v += PCF_THREADS) cp_async16(ring + (size_t)v * 16, src + (size_t)v * 16, true);
+                cp_async_commit();
+                cp_async_wait<1>();
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
             __syncthreads();
+            if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sh->full + 0)) : "memory");
+            cp_async_wait<0>();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sh->full + 1)) : "memory");
             if (warp == 1) {
                 if (elect_one()) {
-                    constexpr uint32_t idesc = umma_idesc_bf16(64, PC_N);
-                    const uint64_t a0 = umma_desc_sw128(smem_u32(ring)), b0 = umma_desc_sw128(smem_u32(wsm));
+                    constexpr uint32_t idesc = umma_idesc_bf16(64, 32);
+                    const uint64_t a0 = umma_desc_sw128(smem_u32(wsm)), b0 = umma_desc_sw128(smem_u32(ring));
                     if (okw && !sh->dead) {
-                        tc_fence_after();
+                        bool ok = true;
                         if (nchunk == 16) {
 #pragma unroll
-                            for (int c = 0; c < 16; ++c) {
-                                const uint64_t ad = a0 + (uint64_t)(c * (PC_CHUNK_BYTES >> 4)), bd = b0 + (uint64_t)(c * (4096 >> 4));
-                                umma_bf16(tmem_base, ad, bd, idesc, c > 0 ? 1u : 0u);
-                                umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
-                                umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
-                                umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
+                            for (int hf = 0; hf < 2; ++hf) {
+                                if (ok) ok = pc_mbar_wait(sh->full + hf, par, &sh->dead, a.err, 24);
+                                tc_fence_after();
+#pragma unroll
+                                for (int c = 8 * hf; c < 8 * hf + 8; ++c) {
+                                    const uint64_t ad = a0 + (uint64_t)(c * (8192 >> 4)), bd = b0 + (uint64_t)(c * (SLOT >> 4));
+                                    umma_bf16(tmem_base, ad, bd, idesc, c > 0 ? 1u : 0u);
+                                    umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
+                                    umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
+                                    umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
+                                }
                             }
                         } else {
+                            ok = pc_mbar_wait(sh->full + 0, par, &sh->dead, a.err, 24) && pc_mbar_wait(sh->full + 1, par, &sh->dead, a.err, 24);
+                            tc_fence_after();
                             for (int c = 0; c < nchunk; ++c) {
-                                const uint64_t ad = a0 + (uint64_t)(c * (PC_CHUNK_BYTES >> 4)), bd = b0 + (uint64_t)(c * (4096 >> 4));
+                                const uint64_t ad = a0 + (uint64_t)(c * (8192 >> 4)), bd = b0 + (uint64_t)(c * (SLOT >> 4));
                                 umma_bf16(tmem_base, ad, bd, idesc, c > 0 ? 1u : 0u);
                                 umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
                                 umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
@@ -512,8 +534,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PCF_THREADS, 1) k_ls
                     while (!pcb_try_wait_cluster(&sh->xb, par)) {}
                 }
             }
-            const int o = uk * PCB_PLD + ub;
-            rec = ((pin[o] + pin[8 * PCB_PLD + o]) + pin[16 * PCB_PLD + o]) + pin[24 * PCB_PLD + o];
+            const int o = ub * PCB_PLD + uk;
+            rec = ((pin[o] + pin[32 * PCB_PLD + o]) + pin[64 * PCB_PLD + o]) + pin[96 * PCB_PLD + o];
             if (tid == 0) pc_stamp(a.dbg, j, i, 4);
         }
         uint2 dgp = make_uint2(0u, 0u);
@@ -523,13 +545,12 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PCF_THREADS, 1) k_ls
             dc = dcp;
             c_new = c_prev;
             dgp = make_uint2(pack_bf2(d4.x, d4.y), pack_bf2(d4.z, d4.w));
-            *reinterpret_cast<uint2 *>((uint8_t *)a.gimg + (size_t)((i + 1) & 1) * 4 * q_bytes + gimg_off) = dgp;
-            fence_proxy_async_global();
+            *reinterpret_cast<uint2 *>((uint8_t *)a.gimg + (size_t)((i + 1) & 1) * img_bytes + gimg_off) = dgp;
         }
         if (tid == 0) pc_stamp(a.dbg, j, i, 5);
         __syncthreads();
-        if (tid == 0) { gbar_arrive(a.bar); pc_stamp(a.dbg, j, i, 6); }
-        if (valid) *reinterpret_cast<uint2 *>(a.dg_rm + ((size_t)t * a.B + ub) * 4 * H + 4 * u) = dgp;
+        if (tid == 0) { gbar_arrive(bar); pc_stamp(a.dbg, j, i, 6); }
+        if (valid) *reinterpret_cast<uint2 *>(a.dg_rm + ((size_t)t * a.B + b) * 4 * H + 4 * u) = dgp;
     }
     __syncthreads();
     cluster.sync();                                        // peers may still be pushing into this CTA's shared memory
@@ -543,31 +564,23 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PCF_THREADS, 1) k_ls
 // [Kp/64 slabs][32 rows][128 B] in the SWIZZLE_128B K-major layout (16-byte chunk c of row r at position c ^ (r & 7)),
 // K padded to a multiple of 64 with zeros.
 // mode 0 (forward):  block jc = 16 units, [slab][64 rows m = 4*lu+g][128 B], k  ->  w_hh[g*H + 16jc+lu][k]
-// mode 1 (backward): CTA j = 4r'+s, row n = output unit 32r'+n, k  ->  w_hh[g*H + u][32r'+n] with 4u+g = s*H + k
+// mode 1 (backward): block (ro, s) = 64 output units x K quarter, [slab][64 rows n][128 B], k  ->  w_hh[g*H + u][64 ro + n] with 4u+g = s*H + k
 __global__ void k_pc_pack_w(const float *__restrict__ w_hh, int ld, int H, int mode, __nv_bfloat16 *__restrict__ img) {
     const int nslab = (H + 63) / 64;
-    const size_t per_cta = (size_t)nslab * 2048;
-    const size_t total = (size_t)(H / 8) * per_cta;
+    const size_t per_blk = (size_t)nslab * 4096;              // one block: [slab][64 rows][64]
+    const size_t total = (size_t)(H / 16) * per_blk;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int j = (int)(i / per_cta);
-        const int rem = (int)(i - (size_t)j * per_cta);
-        int slab = rem >> 11, r = (rem >> 6) & 31, cpos = (rem >> 3) & 7, e = rem & 7;
-        if (mode == 0) {     // forward: block jc = 16 units, [slab][64 rows m = 4*lu+g][64]; two "CTAs" of this loop per block
-            const size_t per_blk = 2 * per_cta;
-            const int jc = (int)(i / per_blk), rm = (int)(i - (size_t)jc * per_blk);
-            slab = rm >> 12;
-            const int m = (rm >> 6) & 63;
-            const int kk = slab * 64 + ((cpos ^ (m & 7)) << 3) + e;
-            img[i] = __float2bfloat16(kk < H ? w_hh[(size_t)((m & 3) * H + 16 * jc + (m >> 2)) * ld + kk] : 0.f);
-            continue;
-        }
-        const int k = slab * 64 + ((cpos ^ (r & 7)) << 3) + e;
+        const int blk = (int)(i / per_blk), rm = (int)(i - (size_t)blk * per_blk);
+        const int slab = rm >> 12, row = (rm >> 6) & 63, cpos = (rm >> 3) & 7, e = rm & 7;
+        const int k = slab * 64 + ((cpos ^ (row & 7)) << 3) + e;
         float v = 0.f;
         if (k < H) {
-            {
-                const int rr = j >> 2, sq = j & 3;
+            if (mode == 0) {          // forward: block = 16 units, row m = 4*lu+g
+                v = w_hh[(size_t)((row & 3) * H + 16 * blk + (row >> 2)) * ld + k];
+            } else {                  // backward: block = (ro, sq): row n = output unit 64 ro + n, k = index inside K quarter sq
+                const int ro = blk >> 2, sq = blk & 3;
                 const int gk = sq * H + k, u = gk >> 2, g = gk & 3;
-                v = w_hh[(size_t)(g * H + u) * ld + 32 * rr + r];
+                v = w_hh[(size_t)(g * H + u) * ld + 64 * ro + row];
             }
         }
         img[i] = __float2bfloat16(v);
@@ -577,12 +590,10 @@ __global__ void k_pc_pack_w(const float *__restrict__ w_hh, int ld, int H, int m
 inline size_t pc_wimg_elems(int H) { return (size_t)(H / 8) * ((H + 63) / 64) * 2048; }   // == 4 * H * H when H % 64 == 0
 inline size_t pc_himg_elems(int H) { return (size_t)2 * ((H + 63) / 64) * 64 * PC_ROWS; }     // ping-pong h image (bf16 elements)
 inline size_t pc_gimg_elems(int H) { return 4 * pc_himg_elems(H); }                            // ping-pong d-gates image
-inline size_t pc_smem_bytes(int H, bool bwd) {
+inline size_t pc_smem_bytes(int H, bool bwd) {     // backward chain: resident 64-row W^T slabs + half-image piece + partial tiles
+    (void)bwd;
     const int nchunk = (H + 63) / 64;
-    const int R = nchunk;
-    // + 8 KB: the M = 128 MMA reads 64 rows past the last ring slot (ignored accumulator lanes) - keep that inside the allocation
-    // (forward: + the [64][36] fp32 tile the epilogue re-maps its threads through)
-    return (size_t)R * PC_CHUNK_BYTES + (size_t)nchunk * 4096 + (bwd ? 4 * 8 * 68 * 4 + 256 : PC_ROWS * 36 * 4) + sizeof(PcShared) + 8192 + 1024;
+    return (size_t)nchunk * 8192 + (size_t)nchunk * 4096 + 4 * 32 * PCB_PLD * 4 + sizeof(PcbShared) + 256 + 1024;
 }
 inline size_t pc_smem_bytes_swap(int H) {       // k_lstm_chain_fwd_swap: resident 64-row weight slabs + half-image ring + the [32][68] tile
     const int nchunk = (H + 63) / 64;
@@ -626,7 +637,7 @@ inline bool pc_supported(int H, int B) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    if (H % 32 != 0 || H < 32 || B < 1 || B > PC_ROWS) return false;
+    if (H % 64 != 0 || H < 64 || B < 1 || B > PC_ROWS) return false;      // 64-unit blocks (backward), 16-unit blocks (forward)
     if (H / 8 > sms || (H + 63) / 64 > PC_MAXRING) return false;
     if (pc_smem_bytes(H, true) > 227 * 1024) return false;
     return pc_coresident(H);
@@ -686,7 +697,7 @@ inline int launch_lstm_chain_bwd(const PcBwdArgs &a_in, cudaStream_t st) {
         GVX_CUDA(cudaFuncSetAttribute(k_lstm_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    GVX_CUDA(cudaMemsetAsync(a.bar, 0, sizeof(unsigned), st));
+    GVX_CUDA(cudaMemsetAsync(a.bar, 0, 64 * sizeof(unsigned), st));          // two counters (one per batch half), 128 B apart
     k_lstm_chain_bwd<<<a.H / 8, PCF_THREADS, smem, st>>>(a);
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());

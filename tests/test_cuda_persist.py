@@ -42,7 +42,7 @@ def _reference(w_hh, pre_um, dh_ext, B, T, H, p, seed, training):
 
 
 @pytest.mark.parametrize("B,T,H,p,training", [(64, 12, 1024, 0.1, True), (5, 7, 64, 0.0, False), (33, 20, 256, 0.1, True),
-                                              (16, 9, 96, 0.25, True), (64, 40, 1024, 0.1, False)])
+                                              (16, 9, 192, 0.25, True), (64, 40, 1024, 0.1, False)])
 def test_persistent_lstm_chain_fwd_bwd(cuda_device, B, T, H, p, training):
     from genvox_b200 import _native
     from genvox_b200.decoder import _ptr, _stream
