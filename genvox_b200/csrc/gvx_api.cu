@@ -11,6 +11,7 @@
 #include "gvx_misc.cuh"
 #include "gvx_tc.cuh"
 #include "gvx_bf16.cuh"
+#include "gvx_blas.cuh"
 
 namespace gvx {
 thread_local char g_err[512] = {0};
@@ -51,9 +52,41 @@ int check_dims(const gvx_dims *d) {
     return 0;
 }
 
+// ReLU + always-on dropout of a prenet layer in place (tacotron2.py:143), plus the optional bf16 copies: the epilogue of the
+// time-batched path below.  Element (row m, column c): frame m / rows_per_frame, batch row m % rows_per_frame.
+__global__ void __launch_bounds__(256) k_prenet_epilogue(float *__restrict__ x, int ld, size_t rows, int cols, DropCfg drop, uint32_t site,
+                                                         int t0, int rows_per_frame, int row_offset, BfDsts bf) {
+    const size_t total = rows * (size_t)cols;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t m = i / cols;
+        const int c = (int)(i - m * cols);
+        const int f = (int)(m / rows_per_frame), brow = (int)(m - (size_t)f * rows_per_frame);
+        const float v = fmaxf(x[m * ld + c], 0.f) * drop_mult(drop, site, (uint32_t)(t0 + f), (uint32_t)(brow + row_offset), (uint32_t)c);
+        x[m * ld + c] = v;
+        if (bf.n) bf_store1_t(bf, f, brow, c, v);
+    }
+}
+
 // Prenet.forward over `rows` = F*B rows (tacotron2.py:140-144)
 int run_prenet(const Dims &d, const gvx_weights *w, const float *frames, int frames_ld, int rows, int B, uint64_t seed,
                int t0, int row_offset, float *pre1, float *pre2, cudaStream_t st, const BfDsts *bf = nullptr) {
+    if (rows >= 4096) {
+        // all frames of a teacher-forced pass at once: a plain fp32 library GEMM per layer (exact fp32 products, like the skinny
+        // FFMA kernel below, which needs 0.84 ms for the 51200 rows of configs[2]) + one elementwise pass
+        for (int layer = 0; layer < 2; ++layer) {
+            float *out = layer == 0 ? pre1 : pre2;
+            if (layer == 0) GVX_TRY(sgemm_nt(st, rows, d.P, d.M, frames, frames_ld, w->prenet_w0, d.M, out, d.P));
+            else GVX_TRY(sgemm_nt(st, rows, d.P, d.P, pre1, d.P, w->prenet_w1, d.P, out, d.P));
+            BfDsts none;
+            memset(&none, 0, sizeof(none));
+            k_prenet_epilogue<<<grid_for((size_t)rows * d.P), 256, 0, st>>>(out, d.P, (size_t)rows, d.P, make_drop(seed, 0.5f, 1),
+                                                                          layer == 0 ? SITE_PRENET0 : SITE_PRENET1, t0, B, row_offset,
+                                                                          (layer == 1 && bf) ? *bf : none);
+            GVX_LAUNCHED(1);
+            GVX_CUDA(cudaGetLastError());
+        }
+        return 0;
+    }
     for (int layer = 0; layer < 2; ++layer) {
         GemmIn g = gemm_in(layer == 0 ? w->prenet_w0 : w->prenet_w1, layer == 0 ? d.M : d.P, d.P, rows);
         if (layer == 0) add_seg(g, frames, d.M, frames_ld);

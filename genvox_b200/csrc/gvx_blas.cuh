@@ -49,6 +49,14 @@ inline int gemm_tn(cudaStream_t st, int M, int N, int K, const float *A, int lda
     GVX_CUBLAS(cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, N, M, K, &alpha, B, ldb, A, lda, &beta, C, ldc));
     return 0;
 }
+// NT: A [M,K] (lda), W [N,K] (ldw):  C = A . W^T   (a linear layer over many rows)
+inline int sgemm_nt(cudaStream_t st, int M, int N, int K, const float *A, int lda, const float *W, int ldw, float *C, int ldc) {
+    cublasHandle_t h;
+    GVX_TRY(blas(&h, st));
+    const float alpha = 1.f, beta = 0.f;
+    GVX_CUBLAS(cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, N, M, K, &alpha, W, ldw, A, lda, &beta, C, ldc));
+    return 0;
+}
 // column sums of a row-major X [rows, ncols] (ld): out[c] = sum_r X[r, c]
 inline int colsum(cudaStream_t st, const float *X, int rows, int ncols, int ld, const float *ones, float *out) {
     cublasHandle_t h;
