@@ -113,7 +113,8 @@ inline bool infer_prenet_fused_ok(const Dims &d, int B) {
         const char *e = getenv("GVX_FUSED_PRENET");
         on = (e && e[0] == '0') ? 0 : 1;
     }
-    return on == 1 && B <= IPN_ROWS && d.M % 4 == 0 && d.P % IPN_COLS == 0 && d.P / IPN_COLS <= 64;
+    // (d.M <= d.P: the shared tile is sized [64][P + 1] and layer 0 fills it as [64][M + 1])
+    return on == 1 && B <= IPN_ROWS && d.M % 4 == 0 && d.M <= d.P && d.P % IPN_COLS == 0 && d.P / IPN_COLS <= 64;
 }
 
 // prev -> PRE2 (fp32, optional) and/or bf16 images; `bar` = monotonic counter zeroed before step 0, t = step index

@@ -123,6 +123,7 @@ class Decoder(nn.Module):
         self.last_n_frames = None
         self._pack_key = None
         self._packed = None
+        self._pack_epoch = 0          # bumped by invalidate_packed()
 
     # ------------------------------------------------------------------ plumbing
     def set_dropout_seed(self, seed):
@@ -152,6 +153,20 @@ class Decoder(nn.Module):
     def _weights_struct(params):
         return _native.GvxWeights(*[_ptr(p) for p in params])
 
+    def invalidate_packed(self):
+        """Force a repack of the kernel-side weight images on the next call.  Needed after in-place edits that bypass autograd's
+        version counter (`p.data.copy_(...)`, an EMA swap through `.data`, manual re-initialisation): the cache key is
+        (data_ptr, version) per parameter and `.data` writes do not bump the version."""
+        self._pack_epoch += 1
+
+    def _last_step_gate_fired(self, gate, n_frames, steps):
+        """True when every row that reached the last allowed step did so because its gate fired there (then the reference's
+        loop ends through the gate `break`, tacotron2.py:405-406, without the max-steps warning)."""
+        rows = n_frames >= steps
+        if not bool(rows.any()):
+            return True
+        return bool((torch.sigmoid(gate[rows, steps - 1]) > self.gate_threshold).all())
+
     def _native_state(self, params):
         """(dims, weights struct, packed weights) — repacks when any parameter changed."""
         lib = _native.load()
@@ -160,13 +175,14 @@ class Decoder(nn.Module):
                 raise RuntimeError("genvox_b200: decoder parameters must be contiguous float32 CUDA tensors")
         dims = self._dims()
         weights = self._weights_struct(params)
-        key = (self.precision,) + tuple((p.data_ptr(), p._version) for p in params)
+        key = (self.precision, self._pack_epoch) + tuple((p.data_ptr(), p._version) for p in params)
         if key != self._pack_key:
             nbytes = lib.gvx_dec_packed_bytes(C.byref(dims))
             if nbytes == 0:
                 _native.check(1, "gvx_dec_packed_bytes")
-            if self._packed is None or self._packed.numel() * 4 < nbytes or self._packed.device != params[0].device:
-                self._packed = _buffer(nbytes, params[0].device)
+            # a FRESH buffer per repack: an autograd graph of an earlier forward may still hold the previous one
+            # (save_for_backward), and its backward must see the weights that forward used
+            self._packed = _buffer(nbytes, params[0].device)
             _native.check(lib.gvx_dec_pack_weights(C.byref(dims), C.byref(weights), _ptr(self._packed), _stream()),
                           "gvx_dec_pack_weights")
             self._pack_key = key
@@ -212,7 +228,9 @@ class Decoder(nn.Module):
                       "gvx_dec_infer")
         self.last_n_frames = n_frames
         tmax = steps if ignore_gate else int(n_frames.max().item())
-        if not ignore_gate and tmax >= steps:
+        # tacotron2.py:405-409 breaks on the gate BEFORE it tests the step count: a row whose gate fires on the last allowed
+        # step does not warn.  `ran` counts the decoder steps executed: the loop ran out only if no stop ended it.
+        if not ignore_gate and tmax >= steps and int(ran.value) >= steps and not self._last_step_gate_fired(gate, n_frames, steps):
             print("Warning! Reached max decoder steps")      # tacotron2.py:408
         return mel[:, :, :tmax], gate[:, :tmax], align[:, :tmax]
 

@@ -277,6 +277,28 @@ def test_max_decoder_steps_guard_prints_the_reference_warning(cuda_device, capsy
     assert "Reached max decoder steps" in capsys.readouterr().out       # tacotron2.py:408
 
 
+def test_invalidate_packed_after_data_edit(cuda_device):
+    """In-place edits through `.data` do not bump autograd's version counter: `invalidate_packed()` is the documented way to make
+    the kernels see them; ordinary optimizer steps / `copy_` on the parameter itself are picked up without it."""
+    dims = synth.DecoderDims(max_decoder_steps=4, gate_threshold=0.999999)
+    W = synth.make_decoder_weights(7, dims)
+    mem, _, _ = synth.make_inputs(3, 2, 11, 0, dims, ragged=False)
+    dec = make_decoder(dims, W, cuda_device, False)
+    x = torch.from_numpy(mem).to(cuda_device)
+    dec.set_dropout_seed(5)
+    m0 = dec.inference(x, ignore_gate=True)[0].clone()
+    dec.linear_projection.linear_layer.weight.data.mul_(2.0)
+    dec.invalidate_packed()
+    dec.set_dropout_seed(5)
+    m1 = dec.inference(x, ignore_gate=True)[0].clone()
+    assert not torch.allclose(m0[:, :, 0], m1[:, :, 0])
+    with torch.no_grad():
+        dec.linear_projection.linear_layer.weight.mul_(0.5)          # versioned edit: no explicit invalidation needed
+    dec.set_dropout_seed(5)
+    m2 = dec.inference(x, ignore_gate=True)[0]
+    assert torch.allclose(m0[:, :, 0], m2[:, :, 0], rtol=1e-5, atol=1e-6)
+
+
 # --------------------------------------------------------------------------- oracle at config-1 batch shape
 def test_forward_backward_match_oracle_config1_shape(cuda_device):
     """B=16, N=120 (config 1's batch/token shape), T=24 frames, ragged lengths, training mode."""
