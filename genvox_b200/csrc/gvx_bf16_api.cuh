@@ -164,8 +164,7 @@ struct StashBfL {
 
 struct BwdBfL {
     size_t DOUT, DOUTB, DHC, GDI, GAI, DQI, DGDRM, DGARM, DQRM, PDXD, PDXA, PS4, DCD, DCA, DCTX, DE, DCONV, DZ2, DZ1, DPM, DW, DCUM,
-        DWA, DWD, DBIAS, PART1, PART2, ONES, TMP, COLP, ERR, GIMG, DXDALL, BAR, GIMGA, DCTXX, DQX, BARA, GDT, XDT, GAT, XAT, HCT, DQT, DOT, GWS, total;
-    int TBp;                           // frames rounded up to a multiple of 8: row stride of the transposed operands
+        DWA, DWD, DBIAS, PART1, PART2, ONES, TMP, COLP, ERR, GIMG, DXDALL, BAR, GIMGA, DCTXX, DQX, BARA, GWS, total;
     size_t gws_floats;
     size_t pdxd_stride, pdxa_stride;   // floats per ping-pong half
     int NPAD, KSdT, KSaT, KSs4, post_blocks, colchunks;
@@ -177,7 +176,7 @@ struct BwdBfL {
         colchunks = 64;
         Carver c;
         const size_t TB = (size_t)T * B;
-        DOUT = c.take(TB * d.OL); DOUTB = c.take(TB * d.OL / 2 + 8);
+        DOUT = c.take(TB * d.OL); DOUTB = c.take(TB * ((d.OL + 7) & ~7) / 2 + 8);     // bf16 copy, row stride rounded up to 8 (TMA)
         DHC = c.take(TB * d.Kp);
         GDI = c.take((size_t)g.G4H * NPAD / 2); GAI = c.take((size_t)g.G4A * NPAD / 2); DQI = c.take((size_t)g.Dp * NPAD / 2);
         DGDRM = c.take(TB * 4 * d.H / 2 + 8); DGARM = c.take(TB * 4 * d.A / 2 + 8); DQRM = c.take(TB * d.D / 2 + 8);
@@ -205,11 +204,6 @@ struct BwdBfL {
         DCTXX = c.take(2 * fb_dctxx_words());      // 64-bit (value, tag) words
         DQX = c.take(2 * fb_dqx_words());
         BARA = c.take(32 * 4);
-        // frame-major operands transposed for the weight-gradient contractions (K = frames must be the contiguous axis)
-        TBp = (T * B + 7) & ~7;
-        GDT = c.take((size_t)4 * d.H * TBp / 2); XDT = c.take((size_t)d.Kd * TBp / 2);
-        GAT = c.take((size_t)4 * d.A * TBp / 2); XAT = c.take((size_t)d.Ka * TBp / 2);
-        HCT = c.take((size_t)d.Kp * TBp / 2); DQT = c.take((size_t)d.D * TBp / 2); DOT = c.take((size_t)d.OL * TBp / 2);
         gws_floats = (size_t)32 << 20;         // 128 MB: up to 3 partial copies of the largest weight gradient
         GWS = c.take(gws_floats);              // split-K partial tiles of the small weight gradients
         total = c.o;
@@ -606,7 +600,8 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     GVX_LAUNCHED(1);
     k_pack_dout<<<grid_for((size_t)TB * d.OL), 256, 0, st>>>(d_mel, d_gate, B, d.M, d.OL, T, x + W.DOUT);
     GVX_LAUNCHED(1);
-    k_to_bf16<<<grid_for((size_t)TB * d.OL), 256, 0, st>>>(x + W.DOUT, d.OL, (size_t)TB, d.OL, DOUTB, d.OL);
+    const int OLB = (d.OL + 7) & ~7;          // row stride of the bf16 copy: a multiple of 8 elements (16-byte rows for TMA)
+    k_to_bf16<<<grid_for((size_t)TB * d.OL), 256, 0, st>>>(x + W.DOUT, d.OL, (size_t)TB, d.OL, DOUTB, OLB);
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     GVX_TRY(gemm_nn(st, TB, d.Kp, d.M + 1, x + W.DOUT, d.OL, packed + PL.Wpg, d.Kp, x + W.DHC, d.Kp, 0.f));
@@ -759,27 +754,11 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     }
     // projections: d Wpg = DOUT^T . [h_dec | ctx];  biases = column sums
     float *tmp = x + W.TMP;
-    // weight gradients: d W = G^T . X over all frames.  Own GEMM: both operands transposed first so that the frame axis is the
-    // contiguous K axis (k_transpose_bf16, HBM-bound), small outputs split over K (deterministic reduction)
-    const int TBp = W.TBp;
-    bf16 *GDT = (bf16 *)(x + W.GDT), *XDT = (bf16 *)(x + W.XDT), *GAT = (bf16 *)(x + W.GAT), *XAT = (bf16 *)(x + W.XAT),
-         *HCT = (bf16 *)(x + W.HCT), *DQT = (bf16 *)(x + W.DQT), *DOT = (bf16 *)(x + W.DOT);
+    // weight gradients: d W = G^T . X over all frames.  Own GEMM: the frame-major operands are consumed as they lie in HBM (MN-major
+    // tcgen05 operands, gvx_nt_gemm.cuh: no transpose pass), small outputs split over K (deterministic reduction)
     const bool og = own_gemm();
-    if (og) {
-        if (TBp != TB) {      // K padding columns must be finite (zero) in both operands
-            GVX_CUDA(cudaMemsetAsync(GDT, 0, ((size_t)(W.GWS - W.GDT)) * sizeof(float), st));
-        }
-        GVX_TRY(transpose_bf16(st, DGDRM, TB, 4 * d.H, 4 * d.H, GDT, TBp));
-        GVX_TRY(transpose_bf16(st, XDRM, TB, d.Kd, d.Kd, XDT, TBp));
-        GVX_TRY(transpose_bf16(st, DGARM, TB, 4 * d.A, 4 * d.A, GAT, TBp));
-        GVX_TRY(transpose_bf16(st, XARM, TB, d.Ka, d.Ka, XAT, TBp));
-        GVX_TRY(transpose_bf16(st, HCRM, TB, d.Kp, d.Kp, HCT, TBp));
-        GVX_TRY(transpose_bf16(st, DQRM, TB, d.D, d.D, DQT, TBp));
-        GVX_TRY(transpose_bf16(st, DOUTB, TB, d.OL, d.OL, DOT, TBp));
-        GVX_TRY(nt_gemm_bf16(st, d.M + 1, d.Kp, TBp, DOT, TBp, HCT, TBp, tmp, d.Kp, err, x + W.GWS, W.gws_floats));
-    } else {
-        GVX_TRY(gemm_tn_bf16(st, d.M + 1, d.Kp, TB, DOUTB, d.OL, HCRM, d.Kp, tmp, d.Kp));
-    }
+    if (og) GVX_TRY(tn_gemm_bf16(st, d.M + 1, d.Kp, TB, DOUTB, OLB, HCRM, d.Kp, tmp, d.Kp, err, x + W.GWS, W.gws_floats));
+    else GVX_TRY(gemm_tn_bf16(st, d.M + 1, d.Kp, TB, DOUTB, OLB, HCRM, d.Kp, tmp, d.Kp));
     GVX_CUDA(cudaMemcpyAsync(g->proj_w, tmp, (size_t)d.M * d.Kp * sizeof(float), cudaMemcpyDeviceToDevice, st));
     GVX_CUDA(cudaMemcpyAsync(g->gate_w, tmp + (size_t)d.M * d.Kp, (size_t)d.Kp * sizeof(float), cudaMemcpyDeviceToDevice, st));
     GVX_TRY(colsum(st, x + W.DOUT, TB, d.M + 1, d.OL, x + W.ONES, x + W.DBIAS));
@@ -795,14 +774,14 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
         GVX_CUDA(cudaGetLastError());
         return 0;
     };
-    if (og) GVX_TRY(nt_gemm_bf16(st, 4 * d.H, d.Kd, TBp, GDT, TBp, XDT, TBp, x + W.DWD, d.Kd, err, x + W.GWS, W.gws_floats));
+    if (og) GVX_TRY(tn_gemm_bf16(st, 4 * d.H, d.Kd, TB, DGDRM, 4 * d.H, XDRM, d.Kd, x + W.DWD, d.Kd, err, x + W.GWS, W.gws_floats));
     else GVX_TRY(gemm_tn_bf16(st, 4 * d.H, d.Kd, TB, DGDRM, 4 * d.H, XDRM, d.Kd, x + W.DWD, d.Kd));
     k_unpack_lstm_grad<<<grid_for((size_t)4 * d.H * d.Kd), 256, 0, st>>>(x + W.DWD, d.H, d.A + d.E, g->dec_w_ih, g->dec_w_hh);
     GVX_LAUNCHED(1);
     GVX_TRY(colsum_bf(DGDRM, 4 * d.H, x + W.DBIAS));
     k_unpack_bias_grad<<<grid_for((size_t)4 * d.H), 256, 0, st>>>(x + W.DBIAS, d.H, g->dec_b_ih, g->dec_b_hh);
     GVX_LAUNCHED(1);
-    if (og) GVX_TRY(nt_gemm_bf16(st, 4 * d.A, d.Ka, TBp, GAT, TBp, XAT, TBp, x + W.DWA, d.Ka, err, x + W.GWS, W.gws_floats));
+    if (og) GVX_TRY(tn_gemm_bf16(st, 4 * d.A, d.Ka, TB, DGARM, 4 * d.A, XARM, d.Ka, x + W.DWA, d.Ka, err, x + W.GWS, W.gws_floats));
     else GVX_TRY(gemm_tn_bf16(st, 4 * d.A, d.Ka, TB, DGARM, 4 * d.A, XARM, d.Ka, x + W.DWA, d.Ka));
     k_unpack_lstm_grad<<<grid_for((size_t)4 * d.A * d.Ka), 256, 0, st>>>(x + W.DWA, d.A, d.P + d.E, g->att_w_ih, g->att_w_hh);
     GVX_LAUNCHED(1);
@@ -811,7 +790,7 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     // query layer: d Wq [D, A] = DQ^T . h_att   (h_att_t = first A columns of the decoder-LSTM input rows)
-    if (og) GVX_TRY(nt_gemm_bf16(st, d.D, d.A, TBp, DQT, TBp, XDT, TBp, g->query_w, d.A, err, x + W.GWS, W.gws_floats));
+    if (og) GVX_TRY(tn_gemm_bf16(st, d.D, d.A, TB, DQRM, d.D, XDRM, d.Kd, g->query_w, d.A, err, x + W.GWS, W.gws_floats));
     else GVX_TRY(gemm_tn_bf16(st, d.D, d.A, TB, DQRM, d.D, XDRM, d.Kd, g->query_w, d.A));
 
     BwdPostArgs pa;
@@ -967,8 +946,8 @@ extern "C" int gvx_debug_timeline(void *device_buffer) {
     return 0;
 }
 
-// ---- test hook: the tcgen05 NT GEMM (+ transpose) on its own: C[M,N] = A[M,K] . B[N,K]^T, or with mode 1 A given as [K,M] and
-// B as [K,N] (both transposed on the device first, the weight-gradient path).  fp32 in, rounded to bf16 on the device.
+// ---- test hook: the own tcgen05 GEMM on its own: C[M,N] = A[M,K] . B[N,K]^T (mode 0, K-major operands), or with mode 1 A given as
+// [K,M] and B as [K,N] (MN-major operands, the weight-gradient path).  fp32 in, rounded to bf16 on the device.
 extern "C" int gvx_test_nt_gemm(const float *A, const float *B, int M, int N, int K, int mode, float *C, void *stream) {
     using namespace gvx;
     GVX_CHECK(A && B && C && M > 0 && N > 0 && K > 0 && K % 8 == 0, "bad argument");
@@ -989,13 +968,9 @@ extern "C" int gvx_test_nt_gemm(const float *A, const float *B, int M, int N, in
         rc = nt_gemm_bf16(st, M, N, K, a, K, b, K, C, N, err, ws, ws_floats);
     } else {
         GVX_CHECK(M % 8 == 0 && N % 8 == 0, "mode 1 needs M, N multiples of 8");
-        GVX_CUDA(cudaMalloc(&at, (size_t)M * K * 2));
-        GVX_CUDA(cudaMalloc(&bt, (size_t)N * K * 2));
         k_to_bf16<<<grid_for((size_t)M * K), 256, 0, st>>>(A, M, (size_t)K, M, a, M);        // A given as [K, M]
         k_to_bf16<<<grid_for((size_t)N * K), 256, 0, st>>>(B, N, (size_t)K, N, b, N);        // B given as [K, N]
-        rc = transpose_bf16(st, a, K, M, M, at, K);
-        if (!rc) rc = transpose_bf16(st, b, K, N, N, bt, K);
-        if (!rc) rc = nt_gemm_bf16(st, M, N, K, at, K, bt, K, C, N, err, ws, ws_floats);
+        rc = tn_gemm_bf16(st, M, N, K, a, M, b, N, C, N, err, ws, ws_floats);             // MN-major operands straight from memory
     }
     if (!rc) rc = check_tc_err(err, st, "nt_gemm");
     else cudaStreamSynchronize(st);

@@ -6,9 +6,10 @@
 //   forward : prenet part of the attention-LSTM gates, input part of the decoder-LSTM gates, mel / gate projections;
 //   backward: d [h_att | ctx] through W_ih of the decoder LSTM, d prenet_out through W_ih of the attention LSTM,
 //             and every weight gradient  d W = G^T . X  (K = T*B = 51200 at configs[2]: 1.8 TFLOP of the train step).
-// One kernel serves all of them in the "NT" form (both operands K-major): weights that are needed transposed are packed
-// transposed once (they are static), activations / gradients whose contraction runs over the frame axis are transposed by
-// k_transpose_bf16 first (HBM-bound, ~0.1 ms each).
+// One kernel serves all of them: the "NT" form (both operands K-major: weights that are needed transposed are packed transposed
+// once, they are static) and the "TN" form for contractions over the frame axis (both operands MN-major, i.e. the frame-major
+// activations / gradients exactly as they lie in HBM - tcgen05 takes MN-major shared-memory operands, so there is no transpose
+// pass: that pass was 1.0 ms of the train step).
 //
 // Kernel: persistent, one CTA per SM, 128 x 256 output tiles, K blocks of 64.
 //   warp 0  TMA producer  : cp.async.bulk.tensor.2d (tensor maps, SWIZZLE_128B) into a 4-stage ring, OOB rows / K tail zero-filled
@@ -74,6 +75,12 @@ struct NgArgs {
     int *err;
 };
 
+// MN = false: both operands K-major in memory (A [M, K], B [N, K]);  MN = true: both MN-major (A^T [K, M], B^T [K, N], the frame-major
+// activations / gradients of the weight-gradient contractions as they lie in HBM: no transpose pass).  MN-major tiles are loaded as
+// 64 (MN elements = 128 B) x 64 (K rows) boxes - one SWIZZLE_128B atom column each, 8 KB apart (the descriptor's leading byte
+// offset), 8-row K groups 1 KB apart (stride byte offset), a K = 16 MMA step = 2 KB - and the instruction descriptor carries the
+// a_major / b_major bits.
+template <bool MN>
 __global__ void __launch_bounds__(NG_THREADS, 1) k_nt_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                            const NgArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -118,16 +125,25 @@ __global__ void __launch_bounds__(NG_THREADS, 1) k_nt_gemm(const __grid_constant
                     if (!mbar_wait(sh->empty + s, ph ^ 1u, a.err, 71)) return;
                     uint8_t *dst = smem + (size_t)s * NG_STAGE_BYTES;
                     mbar_expect_tx(sh->full + s, NG_STAGE_BYTES);
-                    tma_load_2d(dst, &tmA, kb * NG_BK, tm * NG_BM, sh->full + s);
-                    tma_load_2d(dst + NG_BM * NG_BK * 2, &tmB, kb * NG_BK, tn * NG_BN, sh->full + s);
+                    if (MN) {
+#pragma unroll
+                        for (int q = 0; q < NG_BM / 64; ++q) tma_load_2d(dst + q * 8192, &tmA, tm * NG_BM + 64 * q, kb * NG_BK, sh->full + s);
+#pragma unroll
+                        for (int q = 0; q < NG_BN / 64; ++q)
+                            tma_load_2d(dst + NG_BM * NG_BK * 2 + q * 8192, &tmB, tn * NG_BN + 64 * q, kb * NG_BK, sh->full + s);
+                    } else {
+                        tma_load_2d(dst, &tmA, kb * NG_BK, tm * NG_BM, sh->full + s);
+                        tma_load_2d(dst + NG_BM * NG_BK * 2, &tmB, kb * NG_BK, tn * NG_BN, sh->full + s);
+                    }
                     if (++s == NG_STAGES) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {      // ---- MMA issuer
-            constexpr uint32_t idesc = umma_idesc_bf16(NG_BM, NG_BN);
-            const uint64_t ad0 = umma_desc_sw128(smem_u32(smem));      // descriptors advance in 16-byte units
+            constexpr uint32_t idesc = umma_idesc_bf16(NG_BM, NG_BN) | (MN ? (1u << 15) | (1u << 16) : 0u);
+            constexpr int kstep = MN ? (2048 >> 4) : 2;                 // descriptor advance per K = 16 step, in 16-byte units
+            const uint64_t ad0 = MN ? umma_desc_sw128_mn(smem_u32(smem)) : umma_desc_sw128(smem_u32(smem));
             int s = 0, it = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -143,7 +159,7 @@ __global__ void __launch_bounds__(NG_THREADS, 1) k_nt_gemm(const __grid_constant
                     tc_fence_after();
                     const uint64_t ad = ad0 + (uint64_t)(s * (NG_STAGE_BYTES >> 4)), bd = ad + (uint64_t)((NG_BM * NG_BK * 2) >> 4);
 #pragma unroll
-                    for (int j = 0; j < NG_BK / 16; ++j) umma_bf16(tacc, ad + 2 * j, bd + 2 * j, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+                    for (int j = 0; j < NG_BK / 16; ++j) umma_bf16(tacc, ad + kstep * j, bd + kstep * j, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
                     umma_commit(sh->empty + s);
                     if (++s == NG_STAGES) { s = 0; ph ^= 1u; }
                 }
@@ -204,6 +220,23 @@ inline PFN_encodeTiled ng_encode_fn() {
     }
     return fn;
 }
+// frame-major bf16 matrix [K rows, MN columns] with row stride ld: box = 64 MN-elements (128 B) x 64 K rows, SWIZZLE_128B
+inline int ng_tensor_map_mn(CUtensorMap *tm, const __nv_bfloat16 *base, int K, int MNsize, int ld) {
+    PFN_encodeTiled fn = ng_encode_fn();
+    GVX_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+    GVX_CHECK(((uintptr_t)base & 15) == 0 && ld % 8 == 0, "tn_gemm: operands must be 16-byte aligned with a row stride that is a multiple of 8");
+    const cuuint64_t dims[2] = {(cuuint64_t)MNsize, (cuuint64_t)K};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)NG_BK};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled (MN-major) failed: %d (K %d, MN %d, ld %d)", (int)r, K, MNsize, ld);
+        return 1;
+    }
+    return 0;
+}
 // row-major bf16 matrix [rows, K] with row stride ld (elements): box = 64 K-elements x `box_rows` rows, SWIZZLE_128B
 inline int ng_tensor_map(CUtensorMap *tm, const __nv_bfloat16 *base, int rows, int K, int ld, int box_rows) {
     PFN_encodeTiled fn = ng_encode_fn();
@@ -235,12 +268,17 @@ __global__ void __launch_bounds__(256) k_ng_reduce_splits(const float *__restric
 // C[M, N] (ldc) = A[M, K] (lda) . B[N, K]^T (ldb); K may be any multiple of 8 (the tail of the last K block is zero-filled by TMA).
 // `ws` (optional, `ws_floats` floats): when the tiles alone would leave most SMs idle and K is long (the small weight gradients over
 // all frames), the K blocks are split over several CTAs per tile; the partial tiles are summed in a fixed order afterwards.
-inline int nt_gemm_bf16(cudaStream_t st, int M, int N, int K, const __nv_bfloat16 *A, int lda, const __nv_bfloat16 *B, int ldb, float *C,
-                        int ldc, int *err, float *ws = nullptr, size_t ws_floats = 0) {
-    GVX_CHECK(M > 0 && N > 0 && K > 0 && K % 8 == 0, "nt_gemm: bad shape");
+inline int ng_gemm_bf16(bool mn, cudaStream_t st, int M, int N, int K, const __nv_bfloat16 *A, int lda, const __nv_bfloat16 *B, int ldb,
+                       float *C, int ldc, int *err, float *ws, size_t ws_floats) {
+    GVX_CHECK(M > 0 && N > 0 && K > 0 && (mn || K % 8 == 0), "nt_gemm: bad shape");
     CUtensorMap tmA, tmB;
-    GVX_TRY(ng_tensor_map(&tmA, A, M, K, lda, NG_BM));
-    GVX_TRY(ng_tensor_map(&tmB, B, N, K, ldb, NG_BN));
+    if (mn) {
+        GVX_TRY(ng_tensor_map_mn(&tmA, A, K, M, lda));
+        GVX_TRY(ng_tensor_map_mn(&tmB, B, K, N, ldb));
+    } else {
+        GVX_TRY(ng_tensor_map(&tmA, A, M, K, lda, NG_BM));
+        GVX_TRY(ng_tensor_map(&tmB, B, N, K, ldb, NG_BN));
+    }
     NgArgs a;
     a.C = C; a.M = M; a.N = N; a.K = K; a.ldc = ldc; a.err = err;
     a.tiles_m = (M + NG_BM - 1) / NG_BM; a.tiles_n = (N + NG_BN - 1) / NG_BN;
@@ -250,7 +288,8 @@ inline int nt_gemm_bf16(cudaStream_t st, int M, int N, int K, const __nv_bfloat1
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        GVX_CUDA(cudaFuncSetAttribute(k_nt_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NG_SMEM));
+        GVX_CUDA(cudaFuncSetAttribute(k_nt_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NG_SMEM));
+        GVX_CUDA(cudaFuncSetAttribute(k_nt_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NG_SMEM));
     }
     int ntiles = a.tiles_m * a.tiles_n;
     const int nkb = (K + NG_BK - 1) / NG_BK;
@@ -270,7 +309,8 @@ inline int nt_gemm_bf16(cudaStream_t st, int M, int N, int K, const __nv_bfloat1
         }
         if (best > 1) { a.splits = best; a.P = ws; ntiles *= best; }
     }
-    k_nt_gemm<<<ntiles < sms ? ntiles : sms, NG_THREADS, NG_SMEM, st>>>(tmA, tmB, a);
+    if (mn) k_nt_gemm<true><<<ntiles < sms ? ntiles : sms, NG_THREADS, NG_SMEM, st>>>(tmA, tmB, a);
+    else k_nt_gemm<false><<<ntiles < sms ? ntiles : sms, NG_THREADS, NG_SMEM, st>>>(tmA, tmB, a);
     GVX_LAUNCHED(1);
     GVX_CUDA(cudaGetLastError());
     if (a.splits > 1) {
@@ -282,37 +322,15 @@ inline int nt_gemm_bf16(cudaStream_t st, int M, int N, int K, const __nv_bfloat1
     return 0;
 }
 
-// out[c][r] = in[r][c]   (bf16; rows x cols -> cols x rows, leading dimensions in elements)
-__global__ void __launch_bounds__(256) k_transpose_bf16(const __nv_bfloat16 *__restrict__ in, int rows, int cols, int ld_in,
-                                                        __nv_bfloat16 *__restrict__ out, int ld_out) {
-    __shared__ __nv_bfloat16 tile[64][66];
-    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
-    for (int i = threadIdx.x; i < 64 * 32; i += 256) {         // 64 rows x 32 column pairs
-        const int r = i >> 5, cp = i & 31;
-        __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
-        if (r0 + r < rows) {
-            if (c0 + 2 * cp + 1 < cols) v = *reinterpret_cast<const __nv_bfloat162 *>(in + (size_t)(r0 + r) * ld_in + c0 + 2 * cp);
-            else if (c0 + 2 * cp < cols) v.x = in[(size_t)(r0 + r) * ld_in + c0 + 2 * cp];
-        }
-        tile[r][2 * cp] = v.x;
-        tile[r][2 * cp + 1] = v.y;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 64 * 32; i += 256) {         // 64 output rows (input columns) x 32 row pairs
-        const int c = i >> 5, rp = i & 31;
-        if (c0 + c < cols) {
-            const __nv_bfloat162 v = __halves2bfloat162(tile[2 * rp][c], tile[2 * rp + 1][c]);
-            if (r0 + 2 * rp + 1 < rows) *reinterpret_cast<__nv_bfloat162 *>(out + (size_t)(c0 + c) * ld_out + r0 + 2 * rp) = v;
-            else if (r0 + 2 * rp < rows) out[(size_t)(c0 + c) * ld_out + r0 + 2 * rp] = v.x;
-        }
-    }
+// C[M, N] = A[M, K] . B[N, K]^T   (both operands K-major)
+inline int nt_gemm_bf16(cudaStream_t st, int M, int N, int K, const __nv_bfloat16 *A, int lda, const __nv_bfloat16 *B, int ldb, float *C,
+                        int ldc, int *err, float *ws = nullptr, size_t ws_floats = 0) {
+    return ng_gemm_bf16(false, st, M, N, K, A, lda, B, ldb, C, ldc, err, ws, ws_floats);
 }
-inline int transpose_bf16(cudaStream_t st, const __nv_bfloat16 *in, int rows, int cols, int ld_in, __nv_bfloat16 *out, int ld_out) {
-    dim3 grid((cols + 63) / 64, (rows + 63) / 64);
-    k_transpose_bf16<<<grid, 256, 0, st>>>(in, rows, cols, ld_in, out, ld_out);
-    GVX_LAUNCHED(1);
-    GVX_CUDA(cudaGetLastError());
-    return 0;
+// C[M, N] = At[K, M]^T . Bt[K, N]   (both operands frame-major as they lie in HBM: the weight gradients d W = G^T . X)
+inline int tn_gemm_bf16(cudaStream_t st, int M, int N, int K, const __nv_bfloat16 *At, int lda, const __nv_bfloat16 *Bt, int ldb, float *C,
+                        int ldc, int *err, float *ws = nullptr, size_t ws_floats = 0) {
+    return ng_gemm_bf16(true, st, M, N, K, At, lda, Bt, ldb, C, ldc, err, ws, ws_floats);
 }
 
 }  // namespace gvx

@@ -108,6 +108,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                 // layout_type SWIZZLE_128B
     return d;
 }
+// MN-major SWIZZLE_128B operand: 128-byte rows = 64 elements along M/N, 8-row K groups 1 KB apart (stride byte offset),
+// successive 64-element M/N columns `atom_bytes` apart (leading byte offset)
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t saddr, uint32_t atom_bytes = 8192) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((atom_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, dense
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
