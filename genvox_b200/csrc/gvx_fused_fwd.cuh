@@ -12,18 +12,23 @@
 //     SWIZZLE_128B K-major) stays in shared memory for the whole sequence, the cell state in registers.  The prenet part
 //     of the gate pre-activations does not depend on the chain and comes from one time-batched GEMM (`pre`).
 //   * per step the [64 rows x 1536] bf16 operand image (h_att_{t-1} | ctx_{t-1}), written by all CTAs, is streamed in by
-//     TMA bulk copies through a 4-slot ring and contracted on tcgen05 (UMMA 128 x 32 x 16, batch rows on the M side,
+//     TMA bulk copies through a 5-slot ring and contracted on tcgen05 (UMMA 128 x 32 x 16, batch rows on the M side,
 //     accumulator in TMEM).  The h_att part (2/3 of K) is already complete while the attention phase of the previous step
 //     is still running, so its copies and MMAs overlap that phase; only the ctx part is on the critical path.
 //   * the attention phase is row-parallel: a group of 8 consecutive CTAs owns batch rows 4g..4g+3, two CTAs (one
 //     cluster) per row (token halves).  The query projection is split over the group - each CTA keeps a 16 x 1024 slice of
-//     W_q in REGISTERS as mma.sync B fragments and computes 16 dims for the 4 rows - and exchanged through a small global
-//     buffer with a release/acquire counter per group (an 8-CTA cluster would use distributed shared memory, but only 15
-//     clusters of 8 are co-resident on this part: measured, the 16th never starts); the softmax and the context are
-//     combined across the two CTAs of a row in one DSMEM exchange (local max / sum / partial context).
-//   * the location conv + dense layer of step t only needs (w_{t-1}, cum_{t-1}), which live in shared memory: they are
-//     computed BEFORE the LSTM epilogue of step t, i.e. while the tensor core contracts the ctx part.
-//   * two grid-wide barriers per step (release/acquire counters): h_att_t complete, ctx_t complete.
+//     W_q in REGISTERS as mma.sync B fragments and computes 16 dims for the 4 rows.  Both of its exchanges are TAGGED WORDS
+//     in global memory that the consumers poll - the data is its own flag, no barrier, no release fence: h_att_t from the
+//     cells that produce it ((bf16 pair, step) words, `hq`) and the query slices ((fp32, step) words, `qbuf`).  (An 8-CTA
+//     cluster would use distributed shared memory, but only 15 clusters of 8 are co-resident on this part: measured, the
+//     16th never starts.)  The softmax statistics, the 15-token halo and the partial context cross the pair as st.async
+//     pushes counted on the receiver's mbarrier.
+//   * the location conv + dense layer of step t only needs (w_{t-1}, cum_{t-1}), which live in shared memory: they run on
+//     mma.sync (hi + lo bf16 split of every fp32 operand; the conv accumulators are the dense A fragments; processed
+//     memory prefetched into the tile by cp.async) on the six worker warps that have no LSTM-epilogue role, while the
+//     tensor core contracts the ctx part and the epilogue warps wait for it.
+//   * two grid-wide counters per step (release/acquire): h_att_t complete (only the TMA thread of the next step's h_att
+//     part waits for it) and ctx_t complete.  The arrives are issued before the stash-only stores of the step.
 //
 // Everything the backward pass needs is stashed exactly as the per-step kernels do (gvx_bf16_api.cuh).
 #pragma once
