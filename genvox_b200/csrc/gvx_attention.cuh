@@ -60,6 +60,8 @@ struct AttnFwdArgs {
     BfDsts ctx_bf;           // bf16 copies of the context (bf16 mode)
     float *th_stash;         // [B, N, D] tanh(q + loc + pm) for the backward pass, or null
     float *conv_stash;       // [B, N, F] location-conv output for the backward pass, or null
+    int th_bf16;             // k_attention_fwd_c2 only: write th_stash as bf16 rows of 256 B with 16-byte chunks swizzled by (token & 7),
+                             // the format the persistent BPTT chain reads (gvx_fused_bwd.cuh)
 };
 
 // stage w_{t-1} / cum_{t-1} (zero halo), the small weights and q into shared memory

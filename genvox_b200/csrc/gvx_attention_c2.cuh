@@ -165,8 +165,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1) k_att
                     th.y = tanh_fast((q4.y + acc[j][1]) + p[j].y);
                     th.z = tanh_fast((q4.z + acc[j][2]) + p[j].z);
                     th.w = tanh_fast((q4.w + acc[j][3]) + p[j].w);
-                    if (a.th_stash)
-                        *reinterpret_cast<float4 *>(a.th_stash + ((size_t)b * N + n_lo + n0 + j) * AF_D + lane * 4) = th;
+                    if (a.th_stash) {
+                        const int ng = n_lo + n0 + j;
+                        if (a.th_bf16)
+                            *reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(a.th_stash) + ((size_t)b * N + ng) * (AF_D * 2) +
+                                                       (((lane >> 1) ^ (ng & 7)) << 4) + (lane & 1) * 8) =
+                                make_uint2(pack_bf2(th.x, th.y), pack_bf2(th.z, th.w));
+                        else
+                            *reinterpret_cast<float4 *>(a.th_stash + ((size_t)b * N + ng) * AF_D + lane * 4) = th;
+                    }
                     part[j] = fmaf(v4.x, th.x, fmaf(v4.y, th.y, fmaf(v4.z, th.z, v4.w * th.w)));
                 }
             }
@@ -637,12 +644,19 @@ inline bool attention_c2_enabled() {
     return on == 1;
 }
 
+inline bool attention_fwd_uses_c2(const AttnShape &s) {
+    const AttnC2FwdSmem L(s.N, s.E);
+    const size_t bytes = (size_t)L.total * sizeof(float);
+    // the split pays when the rows alone cannot fill the machine
+    return attention_c2_enabled() && attention_fast_ok(s) && s.B <= 74 && s.N >= 32 && s.E % 8 == 0 && bytes <= 200 * 1024;
+}
 inline int launch_attention_fwd_best(const AttnFwdArgs &a, cudaStream_t stream) {
     const AttnC2FwdSmem L(a.s.N, a.s.E);
     const size_t bytes = (size_t)L.total * sizeof(float);
-    // the split pays when the rows alone cannot fill the machine
-    if (!attention_c2_enabled() || !attention_fast_ok(a.s) || a.s.B > 74 || a.s.N < 32 || a.s.E % 8 != 0 || bytes > 200 * 1024)
+    if (!attention_fwd_uses_c2(a.s)) {
+        GVX_CHECK(!a.th_bf16, "the bf16 tanh stash is only written by the cluster attention kernel");
         return launch_attention_fwd_any(a, stream);
+    }
     static size_t configured = 0;
     if (bytes > configured) {
         GVX_CUDA(cudaFuncSetAttribute(k_attention_fwd_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));

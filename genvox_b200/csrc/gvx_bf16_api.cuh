@@ -356,6 +356,13 @@ __global__ void k_add_bias_rows(float *x, size_t rows, int cols, int ld, const f
 inline bool fused_chains_ok(const Dims &d, int B, int N) {
     return pc_enabled() && pc_supported(d.H, B) && fa_enabled() && fa_supported(d, B, N) && fb_supported(d, B, N);
 }
+// the persistent BPTT attention chain behind a PER-STEP forward chain (shapes the persistent forward does not cover, e.g.
+// configs[4]: B = 32, N = 300): the per-step attention kernel then writes the stashes in the formats the BPTT chain reads
+// (bf16 / swizzled tanh rows, fp32 context per frame) and the bf16 copy of the encoder memory is made up front
+inline bool fused_bwd_only_ok(const Dims &d, int B, int N) {
+    return pc_enabled() && pc_supported(d.H, B) && fa_enabled() && !fa_supported(d, B, N) && fb_supported(d, B, N) &&
+           attention_fwd_uses_c2(AttnShape{B, N, d.D, d.E, d.F, d.KS});
+}
 
 // ======================================================================================= forward (training)
 int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, const float *memory, const float *mel_in,
@@ -377,6 +384,7 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     const bool pc = pc_enabled() && pc_supported(d.H, B);
     // fused attention chain: attention LSTM + query + attention of all frames in ONE persistent launch (gvx_fused_fwd.cuh)
     const bool fa = fused_chains_ok(d, B, N);
+    const bool fbo = !fa && fused_bwd_only_ok(d, B, N);      // per-step forward, persistent BPTT attention chain
 
     ProfScope *ps_setup = new ProfScope(PS_SETUP, st);
     GVX_CUDA(cudaMemsetAsync(err, 0, 64 * sizeof(float), st));
@@ -386,6 +394,8 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
         GVX_CUDA(cudaMemsetAsync(XDI, 0, (size_t)T * S.xdi_stride * sizeof(bf16), st));
     } else {
         GVX_CUDA(cudaMemsetAsync(s + S.XIMG, 0, fa_ximg_bytes(), st));
+    }
+    if (fa || fbo) {
         k_to_bf16<<<grid_for((size_t)B * N * d.E), 256, 0, st>>>(memory, d.E, (size_t)B * N, d.E, (bf16 *)(s + S.MEMB), d.E);
         GVX_LAUNCHED(1);
     }
@@ -468,6 +478,11 @@ int train_fwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
             add_img(a.ctx_bf, xa_n, d.P, NPAD); add_rm(a.ctx_bf, xarm_n, d.P, d.Ka);
             add_rm(a.ctx_bf, hcrm, d.H, d.Kp);
             a.th_stash = s + S.TH + (size_t)t * B * N * d.D;
+            if (fbo) {
+                a.th_bf16 = 1;
+                a.th_stash = reinterpret_cast<float *>(reinterpret_cast<bf16 *>(s + S.TH) + (size_t)t * B * N * d.D);
+                a.ctx_out = s + S.CTX32 + (size_t)t * B * d.E;
+            }
             a.conv_stash = s + S.CONVS + (size_t)t * B * N * d.F;
             GVX_TRY(launch_attention_fwd_best(a, st));
         }
@@ -639,7 +654,7 @@ int train_bwd_bf16(const Dims &d, const gvx_weights *w, const float *packed, con
     static const bool dhq_env = !(getenv("GVX_DHQ_FOLDED") && getenv("GVX_DHQ_FOLDED")[0] == '0');
     const bool dhq_folded = dhq_env && !s4_fused && d.A % 16 == 0 && d.A <= 1024 && attention_bwd_uses_c2(AttnShape{B, N, d.D, d.E, d.F, d.KS});
     // the fused forward chain left a bf16 copy of the encoder memory in the stash: operand of d w in the attention backward
-    const bool fb = fused_chains_ok(d, B, N);
+    const bool fb = fused_chains_ok(d, B, N) || fused_bwd_only_ok(d, B, N);
     const bool have_memb = fb;
     if (fb) {   // BPTT of the attention chain for all frames in one persistent launch (gvx_fused_bwd.cuh)
         ProfScope ps(PS_BWD_ATTENTION, st);

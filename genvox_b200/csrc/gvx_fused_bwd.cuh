@@ -812,9 +812,19 @@ inline size_t fb_dqx_words() { return (size_t)2 * PC_ROWS * 4 * (AF_D / 2); }
 // CTAs per batch row: 4 when the rows leave half of the grid idle AND a quarter row is still wider than the 15-token conv halo
 inline int fb_row_split(int B, int N) { return (B <= 32 && FbGeom(N, 4).NH >= 16) ? 4 : 2; }
 
+// (own shape test: the BPTT chain splits a row over 2 or 4 CTAs, so it reaches N = 320 at B <= 32 where the forward chain,
+// two halves per row, stops at 160)
 inline bool fb_supported(const Dims &d, int B, int N) {
-    if (!fa_supported(d, B, N)) return false;
+    static int sms = -1;
+    if (sms < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (d.A != FA_A || d.E != FA_E || d.D != AF_D || d.F != AF_F || d.KS != AF_KS) return false;
+    if (B < 1 || B > PC_ROWS || N < 1 || sms < 128 || d.P % 8 != 0 || d.H % 8 != 0) return false;
     const int RS = fb_row_split(B, N);
+    if (FbGeom(N, RS).NH > ((FA_MAXN / 2 + 7) & ~7)) return false;       // per-CTA token range the kernel's tiles are sized for
     const size_t smem = FbSmem(N, RS).total;
     if (smem > 227 * 1024) return false;
     static size_t cached_smem = 0;
