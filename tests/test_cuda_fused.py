@@ -39,7 +39,9 @@ def _run(dec, mem, mel, lens, r_mel, r_gate, seed, dev, fused):
 
 
 @pytest.mark.parametrize("B,N,T,training,ragged", [(64, 150, 24, True, False), (64, 150, 9, False, True), (5, 37, 11, True, True),
-                                                   (33, 160, 7, True, True), (1, 8, 5, True, False), (16, 120, 30, True, True)])
+                                                   (33, 160, 7, True, True), (1, 8, 5, True, False), (16, 120, 30, True, True),
+                                                       # N > 160 at B <= 32: per-step forward chain + persistent BPTT chain (configs[4] path)
+                                                       (16, 200, 9, True, True), (32, 320, 6, True, False)])
 def test_fused_chain_matches_per_step_chain_and_oracle(cuda_device, B, N, T, training, ragged):
     dims = synth.DecoderDims()
     seed = 4242
