@@ -119,6 +119,30 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
+// SFU activations (ex2 / rcp, abs. error ~2e-7) for the cells on the sequential chains, as in the attention chains
+__device__ __forceinline__ float pc_sigmoid(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+    return r;
+}
+__device__ __forceinline__ float pc_tanh(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+    return fmaf(-2.f, r, 1.f);
+}
+__device__ __forceinline__ float4 pc_lstm_bwd_point(float dh_dropped, float mult, float4 ga, float c_prev, float c_new, float dc_in,
+                                                    float &dc_prev) {
+    const float dh = dh_dropped * mult;
+    const float tc = pc_tanh(c_new);
+    const float d_o = dh * tc;
+    const float dc = dc_in + dh * ga.w * (1.f - tc * tc);
+    const float d_i = dc * ga.z, d_g = dc * ga.x, d_f = dc * c_prev;
+    dc_prev = dc * ga.y;
+    return make_float4(d_i * ga.x * (1.f - ga.x), d_f * ga.y * (1.f - ga.y), d_g * (1.f - ga.z * ga.z), d_o * ga.w * (1.f - ga.w));
+}
+
 constexpr int PCF_THREADS = 512;           // backward chain
 constexpr int PCF64_THREADS = 576;         // forward chain: 16 loader / epilogue warps + weight loader + MMA issuer
 
@@ -285,10 +309,10 @@ __global__ void __launch_bounds__(PCF64_THREADS, 1) k_lstm_chain_fwd_swap(const 
             float hv = 0.f;
             if (ok && valid) {
                 const float4 g4 = *reinterpret_cast<const float4 *>(gt + bl * GS + 4 * lu);
-                const float gi = sigmoidf_(g4.x + pr.x + bi.x), gf = sigmoidf_(g4.y + pr.y + bi.y);
-                const float gg = tanhf(g4.z + pr.z + bi.z), go = sigmoidf_(g4.w + pr.w + bi.w);
+                const float gi = pc_sigmoid(g4.x + pr.x + bi.x), gf = pc_sigmoid(g4.y + pr.y + bi.y);
+                const float gg = pc_tanh(g4.z + pr.z + bi.z), go = pc_sigmoid(g4.w + pr.w + bi.w);
                 c = gf * c + gi * gg;
-                hv = go * tanhf(c) * dm;
+                hv = go * pc_tanh(c) * dm;
                 ga = make_float4(gi, gf, gg, go);
             }
             // two units per 4-byte store: the even lane of a unit pair writes both halves
@@ -541,7 +565,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PCF_THREADS, 1) k_ls
         uint2 dgp = make_uint2(0u, 0u);
         if (valid && !sh->dead) {
             float dcp;
-            const float4 d4 = lstm_bwd_point(dhe + rec, mult, ga, c_prev, c_new, dc, dcp);
+            const float4 d4 = pc_lstm_bwd_point(dhe + rec, mult, ga, c_prev, c_new, dc, dcp);
             dc = dcp;
             c_new = c_prev;
             dgp = make_uint2(pack_bf2(d4.x, d4.y), pack_bf2(d4.z, d4.w));
