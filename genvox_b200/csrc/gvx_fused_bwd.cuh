@@ -130,7 +130,6 @@ struct FbArgs {
     int *err;
     DropCfg drop;
     int row_offset, B, N, T, RS;
-    int flags;                       // timing experiments (GVX_FB_FLAGS): 1 memory prefetch at the top of the step, 2 no conv transpose
     long long *dbg;
 };
 
@@ -321,7 +320,6 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
         const int t = T - 1 - i;
         const uint32_t par = (uint32_t)i & 1u;
         if (tid == 0) { pc_stamp(a.dbg, j, i, 0); fb_gstamp(a.dbg, j, i, 0); }
-        if ((a.flags & 1) && i > 0) load_mem(0);
         // ============================================================ attention backward of step t: the critical path is local
         if (i > 0 && tid < FA_E) {
             // (CTAs without a batch row poll a valid row too: seeing the tags of ALL CTAs is what orders the reuse of buffers)
@@ -690,7 +688,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
             const int wt = tid - 64;                                  // 0..447
             if (has_left || has_right) fb_wait_warp(sh->xb + 2, par, &sh->dead, a.err, 56);     // the neighbours' d conv halos are in
             {   // conv transpose: d wcat[c][m] = sum_{f,k} d conv[f][m + 15 - k] wlc[f][c][k]; task = (filter pair, channel, 8 tokens)
-                const int ntask = (a.flags & 2) ? 0 : 16 * 2 * G.nblk;
+                const int ntask = 16 * 2 * G.nblk;
                 for (int task = wt; task < ntask; task += 448) {
                     const int fp = task & 15, rest = task >> 4;
                     const int ch = rest / G.nblk, m0 = (rest - ch * G.nblk) * 8;
@@ -737,7 +735,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FB_THREADS, 1) k_att
                 if (lane < RS) st_async_f32(mapa_u32(my_xch + 4 * prt, (uint32_t)(gbase + lane)), p, mapa_u32(my_xb0, (uint32_t)(gbase + lane)));
             }
         }
-        if (!(a.flags & 1)) load_mem(0);            // encoder-memory operand of step t-1's d w phase
+        load_mem(0);            // encoder-memory operand of step t-1's d w phase
         if (uvalid) mult = drop_mult(drop, SITE_ATT, (uint32_t)(t - 1), (uint32_t)(ub + a.row_offset), (uint32_t)uu);
         __syncthreads();
         const bool okt = sh->dead == 0;
@@ -839,7 +837,6 @@ inline bool fb_supported(const Dims &d, int B, int N) {
 inline int launch_att_chain_bwd(const FbArgs &a_in, cudaStream_t st) {
     FbArgs a = a_in;
     a.dbg = pc_dbg_buffer() ? pc_dbg_buffer() + 32 * 1024 : nullptr;      // plane 1 (the decoder-LSTM BPTT chain wrote its stamps before)
-    a.flags = getenv("GVX_FB_FLAGS") ? atoi(getenv("GVX_FB_FLAGS")) : 0;
     const size_t smem = FbSmem(a.N, a.RS).total;
     static size_t configured = 0;
     if (configured < smem) {
